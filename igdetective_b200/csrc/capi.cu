@@ -1,0 +1,481 @@
+// C ABI of libigd_b200.so (declared in include/igd_b200.h): handle management, host-side table
+// preparation, H2D/D2H plumbing and launch sequencing.  All computation on contig bases and DP
+// cells happens in the CUDA kernels of pack.cu / rss_scan.cu / gotoh.cu; there is no CPU path.
+#include "common.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+static thread_local std::string g_err;
+
+void igd_set_error(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+}
+int igd_cuda_fail(cudaError_t e, const char *what)
+{
+    igd_set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return IGD_ERR_CUDA;
+}
+
+int igd_reserve(igd_handle *h, int slot, size_t bytes)
+{
+    if (bytes < 256) bytes = 256;
+    if (h->scratch_cap[slot] >= bytes) return IGD_OK;
+    if (h->d_scratch[slot]) { IGD_CUDA(cudaFree(h->d_scratch[slot])); h->d_scratch[slot] = nullptr; h->scratch_cap[slot] = 0; }
+    const size_t cap = bytes + bytes / 8;
+    IGD_CUDA(cudaMalloc(&h->d_scratch[slot], cap));
+    h->scratch_cap[slot] = cap;
+    return IGD_OK;
+}
+
+enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY };
+
+extern "C" {
+
+const char *igd_last_error(void) { return g_err.c_str(); }
+
+int igd_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+igd_handle *igd_create(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        igd_set_error("no CUDA device available (%s); igd_b200 has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { igd_set_error("device %d out of range (0..%d)", device, n - 1); return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { igd_cuda_fail(e, "cudaGetDeviceProperties"); return nullptr; }
+    if (prop.major != 10) {
+        igd_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return nullptr;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { igd_cuda_fail(e, "cudaSetDevice"); return nullptr; }
+    igd_handle *h = new igd_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess
+           && cudaMalloc(&h->d_count, 64 * sizeof(unsigned long long)) == cudaSuccess
+           && cudaMalloc(&h->d_lut7, 16384) == cudaSuccess && cudaMalloc(&h->d_lut9, 262144) == cudaSuccess
+           && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
+    if (!ok) { igd_cuda_fail(cudaGetLastError(), "igd_create allocations"); igd_destroy(h); return nullptr; }
+    return h;
+}
+
+void igd_destroy(igd_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any7);
+    cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
+    cudaFree(h->d_hits); cudaFree(h->d_count);
+    for (int i = 0; i < 12; ++i) cudaFree(h->d_scratch[i]);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int igd_sync(igd_handle *h)
+{
+    if (!h) { igd_set_error("null handle"); return IGD_ERR_ARG; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    return IGD_OK;
+}
+
+int igd_get_timing(igd_handle *h, igd_timing *out)
+{
+    if (!h || !out) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    *out = h->timing;
+    return IGD_OK;
+}
+
+// ---- motifs ---------------------------------------------------------------------------------------
+
+// natural index (first letter most significant, A0 C1 G2 T3) -> kernel index ((hi bits << k) | lo bits)
+static inline unsigned kernel_index(unsigned nat, int k)
+{
+    unsigned lo = 0, hi = 0;
+    for (int i = 0; i < k; ++i) {
+        const unsigned code = (nat >> (2 * (k - 1 - i))) & 3u;
+        lo |= (code & 1u) << i; hi |= (code >> 1) << i;
+    }
+    return (hi << k) | lo;
+}
+static inline unsigned revcomp_index(unsigned nat, int k)
+{
+    unsigned r = 0;
+    for (int i = 0; i < k; ++i) { r = (r << 2) | (3u - (nat & 3u)); nat >>= 2; }
+    return r;
+}
+
+int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
+{
+    if (!h || !flags7 || !flags9) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    std::vector<uint8_t> l7(16384), l9(262144);
+    std::vector<uint32_t> a7(512, 0), a9(8192, 0);
+    for (int k = 7; k <= 9; k += 2) {
+        const unsigned n = 1u << (2 * k);
+        const uint8_t *src = (k == 7) ? flags7 : flags9;
+        std::vector<uint8_t> &dst = (k == 7) ? l7 : l9;
+        std::vector<uint32_t> &any = (k == 7) ? a7 : a9;
+        for (unsigned nat = 0; nat < n; ++nat) {
+            if (src[nat] & 0xF0) { igd_set_error("motif flags use bits 0..3 only"); return IGD_ERR_ARG; }
+            const uint8_t f = (uint8_t)(src[nat] | (src[revcomp_index(nat, k)] << 4));
+            const unsigned ki = kernel_index(nat, k);
+            dst[ki] = f;
+            if (f) any[ki >> 5] |= 1u << (ki & 31);
+        }
+    }
+    IGD_CUDA(cudaMemcpyAsync(h->d_lut7, l7.data(), 16384, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_lut9, l9.data(), 262144, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_any7, a7.data(), 2048, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_any9, a9.data(), 32768, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    h->motifs_set = true;
+    return IGD_OK;
+}
+
+// ---- contigs --------------------------------------------------------------------------------------
+
+int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs)
+{
+    if (!h || !offsets || n_contigs < 0 || (!seq && n_contigs > 0 && offsets[n_contigs] > 0)) {
+        igd_set_error("bad arguments to igd_load_contigs"); return IGD_ERR_ARG;
+    }
+    IGD_CUDA(cudaSetDevice(h->device));
+    h->contigs_loaded = false;
+    h->contig_chunk0.assign(n_contigs, 0);
+    h->contig_len.assign(n_contigs, 0);
+    uint64_t chunk = 1;                               // chunk 0 is the leading pad
+    for (int c = 0; c < n_contigs; ++c) {
+        if (offsets[c + 1] < offsets[c]) { igd_set_error("offsets must be non-decreasing"); return IGD_ERR_ARG; }
+        const uint64_t len = offsets[c + 1] - offsets[c];
+        h->contig_chunk0[c] = chunk;
+        h->contig_len[c] = len;
+        chunk += (len + 63) / 64 + 1;                 // data chunks + one pad chunk
+    }
+    h->total_bases = n_contigs ? offsets[n_contigs] - offsets[0] : 0;
+    const uint64_t data_chunks = chunk - 1;
+    h->n_tiles = (data_chunks + IGD_TILE_CHUNKS - 1) / IGD_TILE_CHUNKS;
+    if (h->n_tiles == 0) h->n_tiles = 1;
+    h->n_chunks = h->n_tiles * IGD_TILE_CHUNKS + 2;
+    if (h->n_chunks > h->planes_cap) {
+        cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
+        h->d_planes = nullptr; h->d_inv = nullptr; h->d_invsum = nullptr; h->planes_cap = 0;
+        const uint64_t cap = h->n_chunks + h->n_chunks / 16;
+        IGD_CUDA(cudaMalloc(&h->d_planes, cap * sizeof(uint4)));
+        IGD_CUDA(cudaMalloc(&h->d_inv, cap * sizeof(unsigned long long)));
+        IGD_CUDA(cudaMalloc(&h->d_invsum, ((cap + 31) / 32 + 1) * sizeof(uint32_t)));
+        h->planes_cap = cap;
+    }
+    const uint64_t nbytes = h->total_bases;
+    int rc;
+    if ((rc = igd_reserve(h, S_SEQ, nbytes))) return rc;
+    if ((rc = igd_reserve(h, S_SEQOFF, (size_t)(n_contigs + 1) * 8))) return rc;
+    if ((rc = igd_reserve(h, S_CHUNK0, (size_t)(n_contigs + 1) * 8))) return rc;
+    std::vector<uint64_t> rel(n_contigs + 1);
+    for (int c = 0; c <= n_contigs; ++c) rel[c] = offsets[c] - offsets[0];
+    if (nbytes)
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_SEQ], seq + offsets[0], nbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_SEQOFF], rel.data(), (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n_contigs)
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_CHUNK0], h->contig_chunk0.data(), (size_t)n_contigs * 8, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = igd_launch_pack(h, (const uint8_t *)h->d_scratch[S_SEQ], (const unsigned long long *)h->d_scratch[S_SEQOFF],
+                              (const unsigned long long *)h->d_scratch[S_CHUNK0], n_contigs))) return rc;
+    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));       // rel / offsets are host temporaries
+    IGD_CUDA(cudaEventElapsedTime(&h->timing.pack_ms, h->ev0, h->ev1));
+    // hit buffer sized for the k-mer scan's ~1 % density with slack; regrown on overflow
+    const uint64_t want = std::max<uint64_t>(1u << 20, h->total_bases / 32);
+    if (want > h->hit_cap) {
+        cudaFree(h->d_hits); h->d_hits = nullptr; h->hit_cap = 0;
+        IGD_CUDA(cudaMalloc(&h->d_hits, want * sizeof(unsigned long long)));
+        h->hit_cap = want;
+    }
+    h->contigs_loaded = true;
+    h->last_scan_kind = 0;
+    return IGD_OK;
+}
+
+static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint64_t *n_hits)
+{
+    if (!h || !n_hits) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (!h->motifs_set || !h->contigs_loaded) { igd_set_error("igd_set_motifs and igd_load_contigs must precede a scan"); return IGD_ERR_STATE; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    h->timing.scan_launches = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        IGD_CUDA(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+        int rc = (kind == 1) ? igd_launch_rss_scan(h, spacer) : igd_launch_kmer_scan(h, k);
+        if (rc) return rc;
+        h->timing.scan_launches++;
+        IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+        unsigned long long count = 0;
+        IGD_CUDA(cudaMemcpyAsync(&count, h->d_count, sizeof count, cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+        IGD_CUDA(cudaEventElapsedTime(&h->timing.scan_ms, h->ev0, h->ev1));
+        h->timing.scan_bases = h->total_bases;
+        if (count <= h->hit_cap) {
+            *n_hits = count;
+            h->host_hits.clear();
+            h->last_scan_kind = kind; h->last_k = k;
+            if (spacer) memcpy(h->last_spacer, spacer, sizeof h->last_spacer);
+            return IGD_OK;
+        }
+        // overflow: grow to the observed count and rerun once
+        cudaFree(h->d_hits); h->d_hits = nullptr; h->hit_cap = 0;
+        const uint64_t want = count + count / 8 + 1024;
+        IGD_CUDA(cudaMalloc(&h->d_hits, want * sizeof(unsigned long long)));
+        h->hit_cap = want;
+    }
+    igd_set_error("hit buffer overflow persisted after regrow");
+    return IGD_ERR_CAPACITY;
+}
+
+int igd_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits)
+{
+    if (!spacer) { igd_set_error("null spacer"); return IGD_ERR_ARG; }
+    for (int t = 0; t < 4; ++t)
+        if (spacer[t] < 2 || spacer[t] > 23) {
+            // the staged halo is one chunk (64 bases): 9 + (s+1) <= 33 and 7 + (s+1) + 9 <= 40 must hold
+            igd_set_error("spacer[%d]=%d outside the supported range 2..23", t, spacer[t]); return IGD_ERR_ARG;
+        }
+    return run_scan(h, 1, 0, spacer, n_hits);
+}
+
+int igd_scan_kmers(igd_handle *h, int32_t k, uint64_t *n_hits)
+{
+    if (k != 7 && k != 9) { igd_set_error("k must be 7 or 9"); return IGD_ERR_ARG; }
+    return run_scan(h, 2, k, nullptr, n_hits);
+}
+
+static int pull_hits(igd_handle *h, uint64_t n)
+{
+    if (h->host_hits.size() == n) return IGD_OK;
+    h->host_hits.resize(n);
+    if (n) {
+        IGD_CUDA(cudaMemcpyAsync(h->host_hits.data(), h->d_hits, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return IGD_OK;
+}
+
+// contig holding chunk index ch
+static inline uint32_t contig_of(const igd_handle *h, uint64_t ch)
+{
+    return (uint32_t)(std::upper_bound(h->contig_chunk0.begin(), h->contig_chunk0.end(), ch) - h->contig_chunk0.begin() - 1);
+}
+
+static int current_count(igd_handle *h, uint64_t *n)
+{
+    unsigned long long count = 0;
+    IGD_CUDA(cudaMemcpyAsync(&count, h->d_count, sizeof count, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    *n = count;
+    return IGD_OK;
+}
+
+int igd_fetch_hits(igd_handle *h, igd_hit *out, uint64_t capacity)
+{
+    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (h->last_scan_kind != 1) { igd_set_error("no RSS scan result to fetch"); return IGD_ERR_STATE; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    uint64_t n = 0; int rc;
+    if ((rc = current_count(h, &n))) return rc;
+    if (n > capacity) { igd_set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)n); return IGD_ERR_CAPACITY; }
+    if ((rc = pull_hits(h, n))) return rc;
+    struct Rec { uint64_t k0, k1; igd_hit hit; };
+    std::vector<Rec> recs(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned long long key = h->host_hits[i];
+        const uint64_t g = key >> 8;
+        const int t = (int)((key >> 4) & 3), strand = (int)((key >> 3) & 1), d = (int)(key & 3);
+        const uint32_t c = contig_of(h, g >> 6);
+        const int64_t hept = (int64_t)(g - h->contig_chunk0[c] * 64);
+        const int s1 = h->last_spacer[t] + (d == 0 ? 0 : (d == 1 ? -1 : 1));
+        const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
+        int64_t nona;
+        if (strand == 0) nona = hept_first ? hept + 7 + s1 : hept - 9 - s1;
+        else             nona = hept_first ? hept - s1 - 9 : hept + 7 + s1;
+        const int64_t L = (int64_t)h->contig_len[c];
+        const int64_t first = hept_first ? hept : nona;
+        const int64_t kf = hept_first ? 7 : 9;
+        const int64_t scan_idx = strand == 0 ? first : L - first - kf;
+        Rec &r = recs[i];
+        r.k0 = ((uint64_t)c << 8) | ((uint64_t)t << 4) | (uint64_t)strand;
+        r.k1 = (uint64_t)scan_idx;
+        r.hit.hept = hept; r.hit.nona = nona; r.hit.contig = c;
+        r.hit.sig_type = (uint8_t)t; r.hit.strand = (uint8_t)strand; r.hit.spacer = (uint8_t)s1; r.hit.reserved = 0;
+    }
+    std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.k0 != b.k0 ? a.k0 < b.k0 : a.k1 < b.k1; });
+    for (uint64_t i = 0; i < n; ++i) out[i] = recs[i].hit;
+    return IGD_OK;
+}
+
+int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity)
+{
+    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (h->last_scan_kind != 2) { igd_set_error("no k-mer scan result to fetch"); return IGD_ERR_STATE; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    uint64_t n = 0; int rc;
+    if ((rc = current_count(h, &n))) return rc;
+    if (n > capacity) { igd_set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)n); return IGD_ERR_CAPACITY; }
+    if ((rc = pull_hits(h, n))) return rc;
+    std::sort(h->host_hits.begin(), h->host_hits.end());
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned long long key = h->host_hits[i];
+        const uint64_t g = key >> 8;
+        const uint32_t c = contig_of(h, g >> 6);
+        out[i].pos = (int64_t)(g - h->contig_chunk0[c] * 64);
+        out[i].contig = c;
+        out[i].flags = (uint8_t)(key & 0xff);
+        out[i].reserved[0] = out[i].reserved[1] = out[i].reserved[2] = 0;
+    }
+    return IGD_OK;
+}
+
+// ---- alignment ------------------------------------------------------------------------------------
+
+int igd_align_batch(igd_handle *h,
+                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                    const int32_t *pair_t, const int32_t *pair_q, int64_t n_pairs,
+                    const igd_scoring *sc,
+                    int32_t *score, int32_t *matches, int32_t *start, int32_t *end, int32_t *ient)
+{
+    if (!h || !tgt_off || !qry_off || !sc || n_tgt < 0 || n_qry < 0 || n_pairs < 0 || (n_pairs && (!pair_t || !pair_q || !score))) {
+        igd_set_error("bad arguments to igd_align_batch"); return IGD_ERR_ARG;
+    }
+    if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
+    if (sc->target_end_open != sc->target_internal_open || sc->target_end_extend != sc->target_internal_extend) {
+        igd_set_error("target_end_* gap scores must equal target_internal_*"); return IGD_ERR_UNSUPPORTED;
+    }
+    if (sc->target_internal_extend < sc->target_internal_open || sc->query_internal_extend < sc->query_internal_open ||
+        sc->query_end_extend < sc->query_end_open) {
+        igd_set_error("gap extend scores must be >= gap open scores"); return IGD_ERR_UNSUPPORTED;
+    }
+    const int vals[] = {sc->match, sc->mismatch, sc->target_internal_open, sc->target_internal_extend,
+                        sc->query_internal_open, sc->query_internal_extend, sc->query_end_open, sc->query_end_extend};
+    for (int v : vals) if (v < -1000 || v > 1000) { igd_set_error("scores must lie in [-1000, 1000]"); return IGD_ERR_UNSUPPORTED; }
+    IGD_CUDA(cudaSetDevice(h->device));
+    h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
+    if (n_pairs == 0) return IGD_OK;
+
+    // validate, bucket by target length, detect lower-case letters
+    const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
+    bool mixed = false;
+    for (size_t i = 0; i < tbytes && !mixed; ++i) mixed = (unsigned)(tgt[i] - 'a') < 26u;
+    for (size_t i = 0; i < qbytes && !mixed; ++i) mixed = (unsigned)(qry[i] - 'a') < 26u;
+    constexpr int NB = 6;
+    std::vector<int32_t> work[NB];
+    std::vector<int64_t> trivial;                      // empty target: closed form
+    uint64_t cells = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int t = pair_t[p], q = pair_q[p];
+        if (t < 0 || t >= n_tgt || q < 0 || q >= n_qry) { igd_set_error("pair %lld indexes outside the sequence tables", (long long)p); return IGD_ERR_ARG; }
+        const int nA = tgt_off[t + 1] - tgt_off[t], nB = qry_off[q + 1] - qry_off[q];
+        if (nA < 0 || nB < 1) { igd_set_error("pair %lld: query must be non-empty", (long long)p); return IGD_ERR_ARG; }
+        if (nA > IGD_MAX_TARGET_LEN || nB > IGD_MAX_QUERY_LEN) {
+            igd_set_error("pair %lld: lengths %d x %d exceed %d x %d", (long long)p, nA, nB, IGD_MAX_TARGET_LEN, IGD_MAX_QUERY_LEN);
+            return IGD_ERR_TOO_LONG;
+        }
+        if (nA == 0) { trivial.push_back(p); continue; }
+        work[igd_align_bucket_of(nA)].push_back((int32_t)p);
+        cells += (uint64_t)nA * (uint64_t)nB;
+    }
+    int rc;
+    if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
+    if ((rc = igd_reserve(h, S_TGTOFF, (size_t)(n_tgt + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_QRYOFF, (size_t)(n_qry + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_PT, (size_t)n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_PQ, (size_t)n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_WORK, (size_t)n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_SCORE, (size_t)n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_PAY, (size_t)n_pairs * 4))) return rc;
+    if (tbytes) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGT], tgt, tbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], tgt_off, (size_t)(n_tgt + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRY], qry, qbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, (size_t)(n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PT], pair_t, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PQ], pair_q, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+    std::vector<int32_t> flat; flat.reserve((size_t)n_pairs);
+    size_t woff[NB + 1]; woff[0] = 0;
+    for (int b = 0; b < NB; ++b) { flat.insert(flat.end(), work[b].begin(), work[b].end()); woff[b + 1] = flat.size(); }
+    if (!flat.empty())
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_WORK], flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, h->stream));
+
+    std::vector<int32_t> h_score((size_t)n_pairs), h_pay((size_t)n_pairs);
+    const int passes = ient ? 2 : 1;
+    std::vector<int32_t> trail;
+    for (int pass = 0; pass < passes; ++pass) {
+        IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, NB * sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+        for (int b = 0; b < NB; ++b) {
+            if (work[b].empty()) continue;
+            igd_align_job job;
+            job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
+            job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
+            job.d_pair_t = (const int32_t *)h->d_scratch[S_PT]; job.d_pair_q = (const int32_t *)h->d_scratch[S_PQ];
+            job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[b];
+            job.n_work = (int32_t)work[b].size();
+            job.bucket = b; job.mixed_case = mixed; job.pay_mode = pass; job.sc = *sc;
+            job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
+            job.d_counter = (unsigned int *)(h->d_count + 8 + b);
+            if ((rc = igd_launch_gotoh(h, job))) return rc;
+        }
+        IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+        IGD_CUDA(cudaMemcpyAsync(h_score.data(), h->d_scratch[S_SCORE], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaMemcpyAsync(h_pay.data(), h->d_scratch[S_PAY], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->timing.align_ms += ms;
+        h->timing.align_cells += cells;
+        for (int64_t p = 0; p < n_pairs; ++p) {
+            const int q = pair_q[p], t = pair_t[p];
+            const int nA = tgt_off[t + 1] - tgt_off[t], nB = qry_off[q + 1] - qry_off[q];
+            if (nA == 0) continue;
+            const uint32_t pay = (uint32_t)h_pay[p];
+            if (pass == 0) {
+                const int lead = (int)(pay >> 20) & 1023, intx = (int)(pay >> 10) & 1023;
+                score[p] = h_score[p];
+                if (matches) matches[p] = (int)(pay & 1023);
+                if (start) start[p] = lead;
+                if (end) end[p] = lead + nB + intx;
+            } else {
+                ient[p] = nA - ((int)(pay >> 20) & 1023);
+            }
+        }
+    }
+    // empty target: the gene row is all letters against gaps (row 0 of the DP)
+    for (int64_t p : trivial) {
+        const int q = pair_q[p];
+        const int nB = qry_off[q + 1] - qry_off[q];
+        score[p] = sc->target_end_open + sc->target_end_extend * (nB - 1);
+        if (matches) matches[p] = 0;
+        if (start) start[p] = 0;
+        if (end) end[p] = nB;
+        if (ient) ient[p] = 0;
+    }
+    return IGD_OK;
+}
+
+} // extern "C"

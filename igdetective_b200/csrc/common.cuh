@@ -1,0 +1,96 @@
+// Shared declarations of the igd_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/igd_b200.h"
+
+// ---- packed contig layout in HBM ---------------------------------------------------------------
+// One "chunk" = 64 consecutive bases = one 16-byte record {lo0, lo1, hi0, hi1}:
+//   bit b of lo0 / hi0 = low / high bit of the 2-bit code of base b       (bases  0..31)
+//   bit b of lo1 / hi1 = the same for base 32 + b                          (bases 32..63)
+// codes A=0 C=1 G=2 T=3 (complement = both bits flipped); anything else packs as 0 and sets the
+// base's bit in the validity plane inv[chunk] (one uint64 per chunk) and the chunk's bit in the
+// summary bitmap invsum[chunk / 32].  The scan reads the 16-byte records (0.25 B/base) for every
+// base and the validity plane only for windows that survive the motif lookups.
+// Chunk 0 is an all-invalid pad; each contig starts on a chunk boundary and is followed by at
+// least one all-invalid pad chunk, so no k-mer window or RSS can straddle two contigs; the array
+// is padded with invalid chunks to a whole number of tiles plus one trailing halo chunk.
+constexpr int IGD_CHUNK_BASES = 64;
+constexpr int IGD_TILE_CHUNKS = 256;                  // chunks per scan tile = threads per CTA
+constexpr int IGD_STAGE_CHUNKS = IGD_TILE_CHUNKS + 2; // one halo chunk each side (RSS span <= 40 bases)
+
+struct igd_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+
+    // motif tables (kernel index order: (hi bits << k) | lo bits, first base = bit 0)
+    uint8_t *d_lut7 = nullptr;    // 16384 flags: bit t = strand +, bit 4+t = strand -
+    uint8_t *d_lut9 = nullptr;    // 262144 flags
+    uint32_t *d_any9 = nullptr;   // 262144-bit bitmap: lut9 != 0
+    uint32_t *d_any7 = nullptr;   // 16384-bit bitmap: lut7 != 0
+    bool motifs_set = false;
+
+    // contigs
+    uint4 *d_planes = nullptr;
+    unsigned long long *d_inv = nullptr;
+    uint32_t *d_invsum = nullptr;
+    uint64_t n_chunks = 0;        // allocated chunks (incl. pads)
+    uint64_t n_tiles = 0;
+    std::vector<uint64_t> contig_chunk0;   // first chunk of each contig
+    std::vector<uint64_t> contig_len;
+    uint64_t total_bases = 0;
+    bool contigs_loaded = false;
+    size_t planes_cap = 0;        // chunks of capacity currently allocated
+
+    // hit buffers
+    unsigned long long *d_hits = nullptr;
+    uint64_t hit_cap = 0;
+    unsigned long long *d_count = nullptr;
+    std::vector<unsigned long long> host_hits;   // last scan's raw keys
+    int last_scan_kind = 0;                      // 0 none, 1 rss, 2 kmers
+    int last_k = 0;
+    int32_t last_spacer[4] = {0, 0, 0, 0};
+
+    // generic growable device scratch for the aligner
+    void *d_scratch[12] = {nullptr};
+    size_t scratch_cap[12] = {0};
+
+    igd_timing timing = {};
+};
+
+void igd_set_error(const char *fmt, ...);
+int igd_cuda_fail(cudaError_t e, const char *what);
+#define IGD_CUDA(call)                                                     \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) return igd_cuda_fail(_e, #call);            \
+    } while (0)
+
+int igd_reserve(igd_handle *h, int slot, size_t bytes);
+
+// pack.cu
+int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,
+                    const unsigned long long *d_chunk0, int n_contigs);
+// rss_scan.cu
+int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4]);
+int igd_launch_kmer_scan(igd_handle *h, int k);
+// gotoh.cu
+struct igd_align_job {
+    const uint8_t *d_tgt; const int32_t *d_tgt_off;
+    const uint8_t *d_qry; const int32_t *d_qry_off;
+    const int32_t *d_pair_t; const int32_t *d_pair_q;
+    const int32_t *d_work;      // pair indices of this bucket
+    int32_t n_work;
+    int bucket;                 // kernel shape selector
+    bool mixed_case;
+    int pay_mode;               // 0: (matches, internal Ix, lead)   1: (matches, internal Ix, trailing Ix)
+    igd_scoring sc;
+    int32_t *d_score; uint32_t *d_pay;
+    unsigned int *d_counter;
+};
+int igd_align_bucket_of(int target_len);
+int igd_launch_gotoh(igd_handle *h, const igd_align_job &job);

@@ -1,0 +1,223 @@
+// K3: batched integer Gotoh global aligner that carries the reference's alignment statistics
+// forward through the DP instead of tracing back.
+//
+// Replaces ALIGNER.align(target, query)[0] + BioAlign (py/IGDetective.py:310-311,
+// py/extract_aligned_genes.py:9-56,92-95) with the scheme of SetupAligner (:72-83).
+// BioPython's aligner keeps, per cell and state, the set of optimal predecessors and returns as
+// alignment [0] the path that prefers M over Ix over Iy at the end cell and at every step back.
+// Here every state carries the statistics of exactly that path:
+//   key  = 4 * score + priority of the state the value came from (M 2, Ix 1, Iy 0), so a plain
+//          integer max reproduces the reference's tie-break;
+//   pay  = matches | internal-Ix-moves << 10 | (lead or trailing-Ix-moves) << 20, selected by the
+//          same comparison.  matches counts M moves whose upper-cased letters are equal (the DP
+//          itself compares raw bytes, as the reference does on raw-case windows).
+// From the end cell: start = lead, end = start + nB + internal Ix, ient = nA - trailing Ix.
+//
+// Mapping: one pair per group of G lanes; lane l owns C consecutive target rows in registers and
+// sweeps the gene columns as a systolic wavefront (lane l works on column t-l at step t); the
+// bottom row of each lane travels to the next lane by shuffle.  No shared memory, no tensor
+// cores: the work is integer add / max / select.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GT_THREADS = 128;
+constexpr int NEGKEY = -(1 << 26);
+
+struct GotohParams {
+    const uint8_t *tgt; const int32_t *tgt_off;
+    const uint8_t *qry; const int32_t *qry_off;
+    const int32_t *pair_t; const int32_t *pair_q;
+    const int32_t *work; int32_t n_work;
+    int match4, mismatch4;       // 4 * substitution scores
+    int to4, te4;                // 4 * target gap open / extend (internal == end)
+    int qio4, qie4;              // 4 * query internal gap open / extend
+    int qeo4, qee4;              // 4 * query end gap open / extend
+    unsigned u_int, u_trail;     // payload units of an Ix move in 0<j<nB / j==nB
+    int lead_shift;              // 20: store lead in bits 20..29, -1: do not
+    int32_t *out_score; uint32_t *out_pay;
+    unsigned int *counter;
+};
+
+__device__ __forceinline__ unsigned up8(unsigned c) { return (c - 'a' < 26u) ? c - 32u : c; }
+
+template <int G, int C, bool MIXED>
+__global__ void __launch_bounds__(GT_THREADS)
+gotoh_kernel(const GotohParams P)
+{
+    constexpr int GROUPS_PER_WARP = 32 / G;
+    const unsigned lane = threadIdx.x & 31u;
+    const int l = lane % G;                  // lane within the group
+    const int grp = lane / G;
+
+    for (;;) {
+        // ---- fetch one pair per group (warp-uniform control flow) -----------------------------
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(P.counter, (unsigned)GROUPS_PER_WARP);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)P.n_work) break;
+        const bool have = base + grp < (unsigned)P.n_work;
+        int pair = 0, nA = 0, nB = 0;
+        const uint8_t *A = P.tgt, *B = P.qry;
+        if (have) {
+            pair = P.work[base + grp];
+            const int t = P.pair_t[pair], q = P.pair_q[pair];
+            const int a0 = P.tgt_off[t], b0 = P.qry_off[q];
+            nA = P.tgt_off[t + 1] - a0; nB = P.qry_off[q + 1] - b0;
+            A += a0; B += b0;
+        }
+        int steps = have ? nB + G - 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+        // ---- per-lane rows ------------------------------------------------------------------
+        unsigned a[C];
+        int Dk[C], Yk[C];
+        unsigned Dp[C], Yp[C];
+        const int i0 = l * C;                                   // row above this lane's first row
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+            const int i = i0 + r + 1;
+            unsigned ch = (have && i <= nA) ? A[i - 1] : 0u;
+            a[r] = MIXED ? (ch | (up8(ch) << 8)) : ch;
+            Dk[r] = (P.qeo4 + P.qee4 * (i - 1)) | 1;            // D(i,0) = Ix(i,0): free/left query-end gap
+            Dp[r] = P.lead_shift >= 0 ? ((unsigned)i << P.lead_shift) : 0u;
+            Yk[r] = NEGKEY; Yp[r] = 0u;
+        }
+        // D(i0, j-1) as seen by this lane's first row: column-0 boundary before the first step
+        int diagk = (l == 0) ? 2 : ((P.qeo4 + P.qee4 * (i0 - 1)) | 1);
+        unsigned diagp = (l == 0 || P.lead_shift < 0) ? 0u : ((unsigned)i0 << P.lead_shift);
+        int botDk = NEGKEY, botXk = NEGKEY; unsigned botDp = 0, botXp = 0;
+
+        for (int t = 0; t < steps; ++t) {
+            // bottom row of the lane above, computed one step ago for the same column
+            int upDk = __shfl_up_sync(0xffffffffu, botDk, 1, G);
+            unsigned upDp = __shfl_up_sync(0xffffffffu, botDp, 1, G);
+            int upXk = __shfl_up_sync(0xffffffffu, botXk, 1, G);
+            unsigned upXp = __shfl_up_sync(0xffffffffu, botXp, 1, G);
+            const int j = t - l + 1;
+            if (j >= 1 && j <= nB) {
+                if (l == 0) {                                   // row 0: Iy(0,j), target end gap
+                    upDk = P.to4 + P.te4 * (j - 1); upDp = 0u; upXk = NEGKEY; upXp = 0u;
+                }
+                const unsigned braw = B[j - 1];
+                const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
+                const bool lastcol = (j == nB);
+                const int qo4 = lastcol ? P.qeo4 : P.qio4;
+                const int qe4 = lastcol ? P.qee4 + 1 : P.qie4 + 1;   // +1: priority of the Ix state on the extend candidate
+                const unsigned ux = lastcol ? P.u_trail : P.u_int;
+                const int nextdiagk = upDk; const unsigned nextdiagp = upDp;
+                int dk = diagk; unsigned dp = diagp;              // D(i-1, j-1)
+                int uk = upDk; unsigned upay = upDp;              // D(i-1, j)
+                int xk = upXk; unsigned xp = upXp;                // Ix(i-1, j), key without priority bits
+#pragma unroll
+                for (int r = 0; r < C; ++r) {
+                    // M(i,j)
+                    bool eq_s, eq_m;
+                    if (MIXED) {
+                        const unsigned x = a[r] ^ b;
+                        eq_s = (x & 0xffu) == 0u; eq_m = (x & 0xff00u) == 0u;
+                    } else {
+                        eq_s = eq_m = (a[r] == b);
+                    }
+                    const int mk = ((dk & ~3) | 2) + (eq_s ? P.match4 : P.mismatch4);
+                    const unsigned mp = dp + (eq_m ? 1u : 0u);
+                    // Ix(i,j) from (i-1,j): open from D (priority of D's origin) vs extend Ix (priority 1)
+                    const int c1 = uk + qo4, c2 = xk + qe4;
+                    const bool px = c1 >= c2;
+                    const int nxk = max(c1, c2) & ~3;             // stored without priority
+                    const unsigned nxp = (px ? upay : xp) + ux;
+                    // Iy(i,j) from (i,j-1): open from D vs extend Iy (priority 0)
+                    const int e1 = Dk[r] + P.to4, e2 = Yk[r] + P.te4;
+                    const bool py = e1 >= e2;
+                    const int nyk = max(e1, e2) & ~3;
+                    const unsigned nyp = py ? Dp[r] : Yp[r];
+                    // D(i,j) = best of M (2), Ix (1), Iy (0)
+                    const int xk1 = nxk | 1;
+                    const bool p1 = mk >= xk1;
+                    int bk = max(mk, xk1); unsigned bp = p1 ? mp : nxp;
+                    const bool p2 = bk >= nyk;
+                    bp = p2 ? bp : nyp; bk = max(bk, nyk);
+                    // shift the window
+                    dk = Dk[r]; dp = Dp[r];
+                    Dk[r] = bk; Dp[r] = bp; Yk[r] = nyk; Yp[r] = nyp;
+                    uk = bk; upay = bp; xk = nxk; xp = nxp;
+                }
+                botDk = uk; botDp = upay; botXk = xk; botXp = xp;
+                diagk = nextdiagk; diagp = nextdiagp;
+                if (l == 0) {                                   // D(0, j) for the next column's diagonal
+                    diagk = P.to4 + P.te4 * (j - 1); diagp = 0u;
+                }
+            }
+        }
+        // ---- result: D(nA, nB) sits in the lane / row that owns target row nA ----------------
+        if (have && nA >= 1) {
+            const int ls = (nA - 1) / C, rs = (nA - 1) % C;
+            if (l == ls) {
+                int k = 0; unsigned p = 0;
+#pragma unroll
+                for (int r = 0; r < C; ++r) if (r == rs) { k = Dk[r]; p = Dp[r]; }
+                P.out_score[pair] = k >> 2;
+                P.out_pay[pair] = p;
+            }
+        }
+    }
+}
+
+template <int G, int C>
+int launch(igd_handle *h, const GotohParams &P, bool mixed)
+{
+    const unsigned warps_needed = (unsigned)((P.n_work + (32 / G) - 1) / (32 / G));
+    unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);
+    const unsigned cap = (unsigned)h->sm_count * 4u;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (mixed) gotoh_kernel<G, C, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    else       gotoh_kernel<G, C, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    h->timing.total_launches++;
+    h->timing.align_launches++;
+    IGD_CUDA(cudaGetLastError());
+    return IGD_OK;
+}
+
+} // namespace
+
+// kernel shapes: target rows = G * C
+//   0: 8 x 9   (<= 72,  J flanks of 70)      1: 32 x 6  (<= 192)
+//   2: 32 x 11 (<= 352, V flanks of 350)     3: 32 x 16 (<= 512)
+//   4: 32 x 25 (<= 800, scoring-B windows)   5: 32 x 32 (<= 1024)
+int igd_align_bucket_of(int target_len)
+{
+    if (target_len <= 72) return 0;
+    if (target_len <= 192) return 1;
+    if (target_len <= 352) return 2;
+    if (target_len <= 512) return 3;
+    if (target_len <= 800) return 4;
+    if (target_len <= 1024) return 5;
+    return -1;
+}
+
+int igd_launch_gotoh(igd_handle *h, const igd_align_job &job)
+{
+    GotohParams P;
+    P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
+    P.pair_t = job.d_pair_t; P.pair_q = job.d_pair_q; P.work = job.d_work; P.n_work = job.n_work;
+    P.match4 = 4 * job.sc.match; P.mismatch4 = 4 * job.sc.mismatch;
+    P.to4 = 4 * job.sc.target_internal_open; P.te4 = 4 * job.sc.target_internal_extend;
+    P.qio4 = 4 * job.sc.query_internal_open; P.qie4 = 4 * job.sc.query_internal_extend;
+    P.qeo4 = 4 * job.sc.query_end_open; P.qee4 = 4 * job.sc.query_end_extend;
+    P.u_int = 1u << 10;
+    P.u_trail = job.pay_mode == 1 ? (1u << 20) : 0u;
+    P.lead_shift = job.pay_mode == 0 ? 20 : -1;
+    P.out_score = job.d_score; P.out_pay = job.d_pay; P.counter = job.d_counter;
+    switch (job.bucket) {
+    case 0: return launch<8, 9>(h, P, job.mixed_case);
+    case 1: return launch<32, 6>(h, P, job.mixed_case);
+    case 2: return launch<32, 11>(h, P, job.mixed_case);
+    case 3: return launch<32, 16>(h, P, job.mixed_case);
+    case 4: return launch<32, 25>(h, P, job.mixed_case);
+    case 5: return launch<32, 32>(h, P, job.mixed_case);
+    }
+    igd_set_error("bad align bucket %d", job.bucket);
+    return IGD_ERR_ARG;
+}

@@ -1,0 +1,155 @@
+/*
+ * igd_b200.h -- C ABI of the B200-native RSS scan + V/D/J scoring library
+ * (libigd_b200.so, hand-written sm_100a CUDA behind plain C entry points).
+ *
+ * The reference (Immunotools/IgDetective) has no FFI: its hot path is Python
+ * functions over BioPython.  Each entry point below names the reference
+ * function it replaces (paths relative to the reference checkout); the ctypes
+ * binding a maintainer would add is shown in INTEGRATION.md and implemented in
+ * igdetective_b200/_lib.py.
+ *
+ * Conventions: all pointers are HOST pointers to caller-owned, contiguous
+ * buffers; every function returns 0 (IGD_OK) or a negative IGD_ERR_* code and
+ * leaves a message for igd_last_error(); no exceptions cross the ABI; a handle
+ * owns one device, one CUDA stream and its device buffers, and is
+ * thread-compatible (one thread at a time per handle).  There is NO CPU
+ * fallback: without a usable CUDA device igd_create fails.
+ */
+#ifndef IGD_B200_H
+#define IGD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGD_OK               0
+#define IGD_ERR_CUDA        -1   /* CUDA runtime / launch failure */
+#define IGD_ERR_ARG         -2   /* invalid argument */
+#define IGD_ERR_STATE       -3   /* call out of order (e.g. scan before load) */
+#define IGD_ERR_TOO_LONG    -4   /* sequence longer than the kernel limits below */
+#define IGD_ERR_UNSUPPORTED -5   /* scoring scheme outside what the kernel implements */
+#define IGD_ERR_CAPACITY    -6   /* output buffer too small */
+
+#define IGD_MAX_TARGET_LEN  1023 /* fragment / window rows held in registers (32 lanes x 32); 10-bit payload fields */
+#define IGD_MAX_QUERY_LEN   1023 /* gene columns; bounded by the 10-bit payload fields */
+
+/* signal types, in the bit order of the motif flag tables */
+#define IGD_SIG_V       0
+#define IGD_SIG_D_LEFT  1
+#define IGD_SIG_D_RIGHT 2
+#define IGD_SIG_J       3
+#define IGD_STRAND_FWD  0
+#define IGD_STRAND_REV  1
+
+typedef struct igd_handle igd_handle;
+
+/* One RSS = (heptamer, nonamer) pair, forward-strand 0-based contig coordinates:
+ * the tuples find_valid_rss returns (py/IGDetective.py:147-177). */
+typedef struct {
+    int64_t  hept;      /* start of the heptamer (of its reverse complement for strand REV) */
+    int64_t  nona;      /* start of the nonamer  (ditto) */
+    uint32_t contig;    /* index into the contigs given to igd_load_contigs */
+    uint8_t  sig_type;  /* IGD_SIG_* */
+    uint8_t  strand;    /* IGD_STRAND_* */
+    uint8_t  spacer;    /* spacer length that matched (s, s-1 or s+1) */
+    uint8_t  reserved;
+} igd_hit;
+
+/* One k-mer membership hit: an element of the set find_valid_motif_idx returns
+ * (py/IGDetective.py:138-144), for all signal types and both strands at once. */
+typedef struct {
+    int64_t  pos;       /* forward-strand 0-based start of the k-mer window */
+    uint32_t contig;
+    uint8_t  flags;     /* bit t: window in motifs[t][k] (strand +); bit 4+t: RC(window) in motifs[t][k] (strand -) */
+    uint8_t  reserved[3];
+} igd_kmer_hit;
+
+/* SetupAligner (py/extract_aligned_genes.py:72-83): the ten PairwiseAligner
+ * attributes the reference sets, as integers.  "target" is the first argument
+ * of align() (fragment / window), "query" the second (gene).  The kernel
+ * requires target_end_* == target_internal_* (true for the reference scheme);
+ * anything else returns IGD_ERR_UNSUPPORTED. */
+typedef struct {
+    int32_t match, mismatch;
+    int32_t target_internal_open, target_internal_extend;
+    int32_t target_end_open, target_end_extend;
+    int32_t query_internal_open, query_internal_extend;
+    int32_t query_end_open, query_end_extend;
+} igd_scoring;
+
+/* device-side timings of the most recent calls, CUDA events on the handle's stream */
+typedef struct {
+    float    pack_ms;          /* igd_load_contigs: pack kernel */
+    float    scan_ms;          /* igd_scan / igd_scan_kmers: scan kernel only */
+    float    align_ms;         /* igd_align_batch: all DP kernel launches of the call */
+    uint32_t scan_launches;    /* kernels launched by the last scan call */
+    uint32_t align_launches;   /* kernels launched by the last align call */
+    uint64_t scan_bases;       /* contig bases covered by the last scan */
+    uint64_t align_cells;      /* sum len(target)*len(query) over pairs (x passes) of the last align call */
+    uint64_t total_launches;   /* kernels launched by this handle since igd_create */
+} igd_timing;
+
+const char *igd_last_error(void);
+int         igd_device_count(void);
+igd_handle *igd_create(int device);            /* NULL on failure (see igd_last_error) */
+void        igd_destroy(igd_handle *h);
+int         igd_sync(igd_handle *h);
+int         igd_get_timing(igd_handle *h, igd_timing *out);
+
+/* ---- RSS scan ------------------------------------------------------------------------------- */
+
+/* VALID_MOTIFS (py/IGDetective.py:54-58, datafiles/motifs) as flag tables:
+ * flags7[16384], flags9[262144]; index = base-4 value of the k-mer, first
+ * letter most significant, A=0 C=1 G=2 T=3; bit t set iff the k-mer is in
+ * motifs[t][k] (t = IGD_SIG_*).  Reverse-strand tables are derived inside. */
+int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9);
+
+/* parent_seq of get_contigwise_rss (py/IGDetective.py:180): contigs as raw ASCII
+ * (any case, IUPAC allowed), concatenated; offsets[n_contigs+1].  Copies to the
+ * device and packs to 2-bit planes + validity plane there. */
+int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs);
+
+/* find_valid_motif_idx + find_valid_rss over both strands and the four signal
+ * types (py/IGDetective.py:138-177, call site :443) in one pass over the packed
+ * contigs.  spacer[t] = SPACER_LENGTH of signal type t.  Hits stay on the
+ * device until fetched; *n_hits is their number. */
+int igd_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits);
+
+/* Hits of the last igd_scan, sorted by (contig, sig_type, strand, index of the
+ * 5' k-mer in scanned-strand coordinates) -- the order find_valid_rss would emit
+ * if its first_set were iterated ascending. */
+int igd_fetch_hits(igd_handle *h, igd_hit *out, uint64_t capacity);
+
+/* find_valid_motif_idx (py/IGDetective.py:138-144) for k = 7 or 9: every window
+ * whose upper-cased k-mer (or its reverse complement) is in any motif set of
+ * that k.  Hits sorted by (contig, pos). */
+int igd_scan_kmers(igd_handle *h, int32_t k, uint64_t *n_hits);
+int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity);
+
+/* ---- candidate-vs-gene scoring -------------------------------------------------------------- */
+
+/* ALIGNER.align(target, query)[0] followed by BioAlign
+ * (py/IGDetective.py:310-311, py/extract_aligned_genes.py:9-56,92-95) for a
+ * list of (target, query) pairs.  Sequences are raw bytes (case preserved:
+ * the DP compares bytes, the match count compares upper-cased bytes, as the
+ * reference does).  Outputs, one per pair (any may be NULL except score):
+ *   score   optimal global score
+ *   matches number of equal (upper-cased) columns inside the gene range
+ *           -- the TRUE count; BioAlign.NumMatches() returns matches-1
+ *   start   BioAlign.AlignmentRange()[0]  (columns before the first gene letter)
+ *   end     BioAlign.AlignmentRange()[1]  (len(BioAlign) == end - start)
+ *   ient    BioAlign.QuerySeq() == upper(target[start:ient]); costs a second DP pass
+ */
+int igd_align_batch(igd_handle *h,
+                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                    const int32_t *pair_t, const int32_t *pair_q, int64_t n_pairs,
+                    const igd_scoring *sc,
+                    int32_t *score, int32_t *matches, int32_t *start, int32_t *end, int32_t *ient);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGD_B200_H */

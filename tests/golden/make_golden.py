@@ -1,0 +1,151 @@
+"""Generates everything under tests/golden/ from the reference checkout.  Run HERE (the
+container that has /root/reference); the GPU box only ever sees the committed outputs.
+
+    python tests/golden/make_golden.py [--only data|igdetective|scoring_b] [--jobs 8]
+
+1. data fixtures: motif sets, V/J reference gene sets and the three example loci, re-encoded
+   (text / gzip) from /root/reference/datafiles and /root/reference/examples.
+2. igdetective/: genes_{V,D,J}.tsv and rss_*.csv written by the UNMODIFIED reference script
+   /root/reference/py/IGDetective.py running on oracle/bio_shim (no BioPython here).
+3. scoring_b/: genes.tsv / genes.fasta written by the UNMODIFIED
+   /root/reference/py/extract_aligned_genes.py main() on the shim, with oracle/stubs/minimap2
+   serving a fixed SAM (minimap2 is not installed either).
+"""
+import argparse
+import gzip
+import os
+import pickle
+import shutil
+import subprocess
+import sys
+import tempfile
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SHIM = os.path.join(ROOT, "oracle", "bio_shim")
+STUBS = os.path.join(ROOT, "oracle", "stubs")
+
+EXAMPLES = {"human": "human.fa", "mouse": "mouse.fa", "cow": "cow.fasta"}
+
+
+def read_fasta(path):
+    recs, title, chunks = [], None, []
+    for line in open(path):
+        if line.startswith(">"):
+            if title is not None:
+                recs.append((title, "".join(chunks)))
+            title, chunks = line[1:].rstrip("\n"), []
+        else:
+            chunks.append(line.strip())
+    if title is not None:
+        recs.append((title, "".join(chunks)))
+    return recs
+
+
+def write_fasta_gz(path, recs):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "wb") as raw:
+        with gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as f:
+            for t, s in recs:
+                f.write((">%s\n%s\n" % (t, s)).encode())
+
+
+def make_data():
+    d = os.path.join(HERE, "datafiles")
+    os.makedirs(d, exist_ok=True)
+    motifs = pickle.load(open(os.path.join(REF, "datafiles", "motifs"), "rb"))
+    with open(os.path.join(d, "motif_sets.txt"), "w") as f:
+        for t in ("V", "D_left", "D_right", "J"):
+            for k in ("7", "9"):
+                for kmer in sorted(motifs[t][k]):
+                    f.write("%s\t%s\t%s\n" % (t, k, kmer))
+    for sub in ("combined_reference_genes", "human_reference_genes"):
+        for fn in sorted(os.listdir(os.path.join(REF, "datafiles", sub))):
+            if fn[3] in "VJ":      # C genes are used only by the minimap2 prefilter
+                write_fasta_gz(os.path.join(d, sub, fn + ".gz"), read_fasta(os.path.join(REF, "datafiles", sub, fn)))
+    for name, fn in EXAMPLES.items():
+        write_fasta_gz(os.path.join(HERE, "inputs", name + ".fa.gz"),
+                       read_fasta(os.path.join(REF, "examples", "igh_locus_examples", fn)))
+
+
+def run_reference_igdetective(example, gene_dir, jobs, rss_only):
+    """cwd gets a datafiles/ view whose combined_reference_genes points at `gene_dir`
+    (the script hard-codes that name, IGDetective.py:133)."""
+    out = os.path.join(HERE, "igdetective", "%s__%s" % (example, gene_dir))
+    os.makedirs(out, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "datafiles"))
+        os.symlink(os.path.join(REF, "datafiles", "motifs"), os.path.join(tmp, "datafiles", "motifs"))
+        os.symlink(os.path.join(REF, "datafiles", gene_dir),
+                   os.path.join(tmp, "datafiles", "combined_reference_genes"))
+        env = dict(os.environ, PYTHONPATH=SHIM, PYTHONHASHSEED="0")
+        cmd = [sys.executable, os.path.join(REF, "py", "IGDetective.py"),
+               "-i", os.path.join(REF, "examples", "igh_locus_examples", EXAMPLES[example]),
+               "-o", os.path.join(tmp, "out"), "-m", str(jobs), "-l", "IGH"] + (["-r"] if rss_only else [])
+        subprocess.run(cmd, cwd=tmp, env=env, check=True, stdout=subprocess.DEVNULL)
+        for fn in sorted(os.listdir(os.path.join(tmp, "out"))):
+            shutil.copyfile(os.path.join(tmp, "out", fn), os.path.join(out, fn))
+            print("  wrote", os.path.relpath(os.path.join(out, fn), ROOT))
+
+
+def make_igdetective(jobs):
+    for ex in EXAMPLES:
+        run_reference_igdetective(ex, "combined_reference_genes", jobs, rss_only=True)
+        run_reference_igdetective(ex, "combined_reference_genes", jobs, rss_only=False)
+    run_reference_igdetective("human", "human_reference_genes", jobs, rss_only=False)
+
+
+# scoring-B scenarios: (name, example, gene fasta, 1-based SAM positions)
+def scoring_b_scenarios():
+    import csv
+    sc = []
+    for ex, gene_dir in (("human", "combined_reference_genes"), ("cow", "combined_reference_genes")):
+        tsv = os.path.join(HERE, "igdetective", "%s__%s" % (ex, gene_dir), "genes_V.tsv")
+        rows = list(csv.reader(open(tsv, newline=""), delimiter="\t"))[1:]
+        starts = sorted(int(r[6]) for r in rows)
+        n = 12 if ex == "human" else 5
+        pos = [starts[i * len(starts) // n] + 1 + (37 * i) % 90 for i in range(n)]
+        seqlen = len(read_fasta(os.path.join(REF, "examples", "igh_locus_examples", EXAMPLES[ex]))[0][1])
+        pos += [5, 250, 390, 2000, 2300, seqlen - 120, seqlen - 500, seqlen // 2, seqlen // 3]
+        pos += [pos[0]]                       # duplicate POS is dropped by ProcessSamFile
+        sc.append(("%s_IGHV" % ex, ex, os.path.join(REF, "datafiles", gene_dir, "IGHV.fa"), pos))
+    return sc
+
+
+def make_scoring_b():
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, os.path.join(REF, "py"))
+    os.environ["PATH"] = STUBS + os.pathsep + os.environ["PATH"]
+    import extract_aligned_genes as ref_mod
+    for name, ex, gene_fa, positions in scoring_b_scenarios():
+        out = os.path.join(HERE, "scoring_b", name)
+        os.makedirs(out, exist_ok=True)
+        genome = os.path.join(REF, "examples", "igh_locus_examples", EXAMPLES[ex])
+        contig = read_fasta(genome)[0][0].split()[0]
+        sam = os.path.join(out, "alignment.sam")
+        with open(sam, "w") as f:
+            f.write("@HD\tVN:1.6\n")
+            for i, p in enumerate(positions):
+                f.write("g%d\t0\t%s\t%d\t60\t*\t*\t0\t0\t*\t*\n" % (i, contig, p))
+            f.write("gu\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n")
+        os.environ["IGD_STUB_SAM"] = sam
+        with tempfile.TemporaryDirectory() as tmp:
+            ref_mod.main(genome, gene_fa, os.path.join(tmp, "o"))
+            for fn in ("genes.tsv", "genes.fasta"):
+                shutil.copyfile(os.path.join(tmp, "o", fn), os.path.join(out, fn))
+                print("  wrote", os.path.relpath(os.path.join(out, fn), ROOT))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    ap.add_argument("--jobs", type=int, default=len(os.sched_getaffinity(0)))
+    a = ap.parse_args()
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
+    if a.only in ("", "data"):
+        make_data()
+    if a.only in ("", "igdetective"):
+        make_igdetective(a.jobs)
+    if a.only in ("", "scoring_b"):
+        make_scoring_b()
