@@ -1,0 +1,87 @@
+"""ctypes binding of libigd_b200.so -- the stub a reference maintainer would add.
+
+The product path has no fallback: if the CUDA library is missing or no B200 is visible,
+loading / Engine creation raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libigd_b200.so")
+
+IGD_OK, IGD_ERR_CUDA, IGD_ERR_ARG, IGD_ERR_STATE = 0, -1, -2, -3
+IGD_ERR_TOO_LONG, IGD_ERR_UNSUPPORTED, IGD_ERR_CAPACITY = -4, -5, -6
+MAX_TARGET_LEN, MAX_QUERY_LEN = 1023, 1023
+SIG_V, SIG_D_LEFT, SIG_D_RIGHT, SIG_J = 0, 1, 2, 3
+
+HIT_DTYPE = np.dtype([("hept", "<i8"), ("nona", "<i8"), ("contig", "<u4"), ("sig_type", "u1"),
+                      ("strand", "u1"), ("spacer", "u1"), ("reserved", "u1")])
+KMER_HIT_DTYPE = np.dtype([("pos", "<i8"), ("contig", "<u4"), ("flags", "u1"), ("reserved", "u1", (3,))])
+
+
+class Scoring(ctypes.Structure):
+    """igd_scoring == the ten PairwiseAligner attributes of SetupAligner (extract_aligned_genes.py:72-83)."""
+    _fields_ = [(n, ctypes.c_int32) for n in (
+        "match", "mismatch", "target_internal_open", "target_internal_extend",
+        "target_end_open", "target_end_extend", "query_internal_open", "query_internal_extend",
+        "query_end_open", "query_end_extend")]
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("pack_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("align_ms", ctypes.c_float),
+                ("scan_launches", ctypes.c_uint32), ("align_launches", ctypes.c_uint32),
+                ("scan_bases", ctypes.c_uint64), ("align_cells", ctypes.c_uint64),
+                ("total_launches", ctypes.c_uint64)]
+
+
+class IgdError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("igd_b200 error %d: %s" % (code, message))
+        self.code = code
+
+
+EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "igd_sync", "igd_get_timing",
+           "igd_set_motifs", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
+           "igd_fetch_kmer_hits", "igd_align_batch")
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: build it with `python -m igdetective_b200.build` "
+                           "(igdetective_b200 has no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u64p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.POINTER(ctypes.c_uint64)
+    lib.igd_last_error.restype = ctypes.c_char_p
+    lib.igd_last_error.argtypes = []
+    lib.igd_device_count.restype = ctypes.c_int
+    lib.igd_create.restype = vp
+    lib.igd_create.argtypes = [ctypes.c_int]
+    lib.igd_destroy.restype = None
+    lib.igd_destroy.argtypes = [vp]
+    lib.igd_sync.argtypes = [vp]
+    lib.igd_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
+    lib.igd_set_motifs.argtypes = [vp, vp, vp]
+    lib.igd_load_contigs.argtypes = [vp, vp, vp, i32]
+    lib.igd_scan.argtypes = [vp, vp, u64p]
+    lib.igd_fetch_hits.argtypes = [vp, vp, ctypes.c_uint64]
+    lib.igd_scan_kmers.argtypes = [vp, i32, u64p]
+    lib.igd_fetch_kmer_hits.argtypes = [vp, vp, ctypes.c_uint64]
+    lib.igd_align_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i64,
+                                    ctypes.POINTER(Scoring), vp, vp, vp, vp, vp]
+    for name in ("igd_sync", "igd_get_timing", "igd_set_motifs", "igd_load_contigs", "igd_scan",
+                 "igd_fetch_hits", "igd_scan_kmers", "igd_fetch_kmer_hits", "igd_align_batch"):
+        getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != IGD_OK:
+        raise IgdError(rc, load().igd_last_error().decode("utf-8", "replace"))

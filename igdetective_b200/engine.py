@@ -1,0 +1,163 @@
+"""Engine: one igd_handle (one GPU, one stream).  numpy arrays in, numpy arrays out."""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+SIGNAL_INDEX = {"V": _lib.SIG_V, "D_left": _lib.SIG_D_LEFT, "D_right": _lib.SIG_D_RIGHT, "J": _lib.SIG_J}
+SIGNAL_NAMES = ["V", "D_left", "D_right", "J"]
+
+# SetupAligner, py/extract_aligned_genes.py:72-83
+REFERENCE_SCORING = dict(match=2, mismatch=0,
+                         target_internal_open=-2, target_internal_extend=-1,
+                         target_end_open=-2, target_end_extend=-1,
+                         query_internal_open=-2, query_internal_extend=-1,
+                         query_end_open=0, query_end_extend=0)
+
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def motif_flag_tables(motifs):
+    """VALID_MOTIFS dict (py/IGDetective.py:54-58) -> (flags7[16384], flags9[262144]) for igd_set_motifs.
+    Index = base-4 value of the k-mer, first letter most significant; bit t = signal type t."""
+    tabs = {7: np.zeros(4 ** 7, np.uint8), 9: np.zeros(4 ** 9, np.uint8)}
+    for name, t in SIGNAL_INDEX.items():
+        for k in (7, 9):
+            for kmer in motifs[name][str(k)]:
+                if len(kmer) != k or any(c not in _CODE for c in kmer):
+                    continue        # cannot match: windows are upper-cased ACGT or rejected (:141-142)
+                v = 0
+                for c in kmer:
+                    v = v * 4 + _CODE[c]
+                tabs[k][v] |= 1 << t
+    return tabs[7], tabs[9]
+
+
+def concat(seqs):
+    """list[str | bytes] -> (uint8 buffer, int32 offsets[n+1])"""
+    bs = [s if isinstance(s, (bytes, bytearray)) else s.encode("latin-1") for s in seqs]
+    off = np.zeros(len(bs) + 1, np.int64)
+    if bs:
+        off[1:] = np.cumsum([len(b) for b in bs])
+    if off[-1] >= 2 ** 31:
+        raise ValueError("sequence table exceeds 2 GiB")
+    buf = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(0, np.uint8)
+    return buf, off.astype(np.int32)
+
+
+class Engine:
+    def __init__(self, device=0, motifs=None):
+        self._lib = _lib.load()
+        self._h = self._lib.igd_create(int(device))
+        if not self._h:
+            raise _lib.IgdError(_lib.IGD_ERR_CUDA, self._lib.igd_last_error().decode("utf-8", "replace"))
+        self.device = int(device)
+        self.contig_ids = []
+        self.contig_lens = np.zeros(0, np.int64)
+        if motifs is not None:
+            self.set_motifs(motifs)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.igd_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- scan -------------------------------------------------------------------------------
+    def set_motifs(self, motifs):
+        f7, f9 = motifs if isinstance(motifs, tuple) else motif_flag_tables(motifs)
+        f7 = np.ascontiguousarray(f7, np.uint8)
+        f9 = np.ascontiguousarray(f9, np.uint8)
+        assert f7.size == 16384 and f9.size == 262144
+        _lib.check(self._lib.igd_set_motifs(self._h, f7.ctypes.data, f9.ctypes.data))
+
+    def load_contigs(self, seqs, ids=None):
+        """seqs: dict {id: str} (parent_seq of the reference), list of str/bytes, or a
+        (uint8 buffer, uint64 offsets) pair already concatenated (e.g. pinned host memory)."""
+        if isinstance(seqs, dict):
+            ids, seqs = list(seqs.keys()), list(seqs.values())
+        if isinstance(seqs, tuple):
+            buf, off = seqs
+            off = np.ascontiguousarray(off, np.uint64)
+            ptr = buf if isinstance(buf, int) else np.ascontiguousarray(buf, np.uint8).ctypes.data
+        else:
+            bs = [s if isinstance(s, (bytes, bytearray)) else str(s).encode("latin-1") for s in seqs]
+            off = np.zeros(len(bs) + 1, np.uint64)
+            if bs:
+                off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
+            buf = np.frombuffer(b"".join(bs), np.uint8) if bs else np.zeros(1, np.uint8)
+            ptr = buf.ctypes.data
+        n = len(off) - 1
+        self.contig_ids = list(ids) if ids is not None else list(range(n))
+        self.contig_lens = np.diff(off.astype(np.int64))
+        _lib.check(self._lib.igd_load_contigs(self._h, ptr, off.ctypes.data, n))
+        return n
+
+    def scan_rss(self, spacers):
+        """spacers: {signal name: length} or 4 ints in (V, D_left, D_right, J) order.
+        Returns a HIT_DTYPE array sorted by (contig, sig_type, strand, scan-order index)."""
+        if isinstance(spacers, dict):
+            spacers = [spacers[n] for n in SIGNAL_NAMES]
+        sp = np.asarray(spacers, np.int32)
+        n = ctypes.c_uint64()
+        _lib.check(self._lib.igd_scan(self._h, sp.ctypes.data, ctypes.byref(n)))
+        out = np.zeros(n.value, _lib.HIT_DTYPE)
+        _lib.check(self._lib.igd_fetch_hits(self._h, out.ctypes.data, n.value))
+        return out
+
+    def scan_rss_count(self, spacers):
+        """Scan only (hits stay on the device); returns the hit count."""
+        sp = np.asarray([spacers[n] for n in SIGNAL_NAMES] if isinstance(spacers, dict) else spacers, np.int32)
+        n = ctypes.c_uint64()
+        _lib.check(self._lib.igd_scan(self._h, sp.ctypes.data, ctypes.byref(n)))
+        return n.value
+
+    def scan_kmers(self, k):
+        n = ctypes.c_uint64()
+        _lib.check(self._lib.igd_scan_kmers(self._h, int(k), ctypes.byref(n)))
+        out = np.zeros(n.value, _lib.KMER_HIT_DTYPE)
+        _lib.check(self._lib.igd_fetch_kmer_hits(self._h, out.ctypes.data, n.value))
+        return out
+
+    # ---- alignment --------------------------------------------------------------------------
+    def align(self, targets, queries, pair_t, pair_q, scoring=None, want_ient=False):
+        """targets / queries: list[str|bytes] or (uint8 buffer, int32 offsets).  Returns a dict of int32
+        arrays: score, matches (TRUE count), start, end and, if want_ient, ient."""
+        tb, to = targets if isinstance(targets, tuple) else concat(targets)
+        qb, qo = queries if isinstance(queries, tuple) else concat(queries)
+        tb = np.ascontiguousarray(tb, np.uint8)
+        qb = np.ascontiguousarray(qb, np.uint8)
+        to = np.ascontiguousarray(to, np.int32)
+        qo = np.ascontiguousarray(qo, np.int32)
+        pt = np.ascontiguousarray(pair_t, np.int32)
+        pq = np.ascontiguousarray(pair_q, np.int32)
+        n = len(pt)
+        assert len(pq) == n
+        sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
+        res = {k: np.zeros(n, np.int32) for k in ("score", "matches", "start", "end")}
+        ient = np.zeros(n, np.int32) if want_ient else None
+        _lib.check(self._lib.igd_align_batch(
+            self._h, tb.ctypes.data if tb.size else None, to.ctypes.data, len(to) - 1,
+            qb.ctypes.data if qb.size else None, qo.ctypes.data, len(qo) - 1,
+            pt.ctypes.data, pq.ctypes.data, n, ctypes.byref(sc),
+            res["score"].ctypes.data, res["matches"].ctypes.data, res["start"].ctypes.data,
+            res["end"].ctypes.data, ient.ctypes.data if want_ient else None))
+        if want_ient:
+            res["ient"] = ient
+        return res
+
+    def sync(self):
+        _lib.check(self._lib.igd_sync(self._h))
+
+    def timing(self):
+        t = _lib.Timing()
+        _lib.check(self._lib.igd_get_timing(self._h, ctypes.byref(t)))
+        return {f[0]: getattr(t, f[0]) for f in _lib.Timing._fields_}

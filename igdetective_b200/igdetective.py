@@ -1,0 +1,210 @@
+"""De-novo stage: same command line and output files as the reference's py/IGDetective.py, with the
+RSS scan and the candidate scoring running on the GPU.
+
+    python -m igdetective_b200.igdetective -i genome.fasta -o out_dir -m 1 -l IGH [-r] [-g vdj]
+
+Outputs (byte-identical to the reference on the same input): genes_V.tsv, genes_D.tsv,
+genes_J.tsv, or rss_<type>.csv with -r  (py/IGDetective.py:227-255,424-436,439-487).
+Extra long options that the reference does not have: --datafiles DIR, --gene_dir NAME,
+--device N, --order reference|canonical.
+"""
+import csv
+import getopt
+import os
+import sys
+
+import numpy as np
+
+from . import datafiles as dfiles
+from .engine import Engine
+from .fasta import fasta_dict, reverse_complement
+from .rss import (D, DL, DR, FWD, GENE_LENGTH, J, REV, SIGNAL_TYPES, V, RssScan, combine_D_RSS,
+                  get_s_fragment_from_RSS)
+from .scoring import align_fragment_to_genes, compute_alignments
+
+PI_CUTOFF = {"strict": {V: 70, J: 70}, "relax": {V: 60, J: 65}}     # py/IGDetective.py:31
+MAXK_CUTOFF = {V: 15, J: 11}                                         # :32
+ALIGNMENT_EXTENSION = {V: REV, J: FWD, D: None}                      # :30
+
+D_HEADER = ['reference contig', 'strand', 'left heptamer index', 'left nonamer index',
+            'left heptamer', 'left nonamer', 'right heptamer index', 'right nonamer index',
+            'right heptamer', 'right nonamer', 'start of gene', 'end of gene', 'gene sequence']
+VJ_HEADER = ['reference contig', 'strand', 'heptamer index', 'nonamer index', 'heptamer', 'nonamer',
+             'start of gene', 'end of gene', 'best aligned human gene', 'alignment direction',
+             'alignment PI', 'longest common k-mer', 'gene sequence']
+RSS_HEADER = ['7-mer index', '9-mer index', '7-mer', '9-mer', 'reference contig', 'strand']
+
+
+def _kmer(seq, i, k, strand):
+    s = seq[i:i + k]
+    return (s if strand == FWD else reverse_complement(s)).upper()
+
+
+def rss_rows(rss_idx, parent_seq):
+    """write_rss_to_file, py/IGDetective.py:227-251."""
+    rows = [RSS_HEADER]
+    for strand in (FWD, REV):
+        for contig in parent_seq:
+            for h, n in rss_idx[strand][contig]:
+                rows.append([h, n, _kmer(parent_seq[contig], h, 7, strand), _kmer(parent_seq[contig], n, 9, strand),
+                             contig, strand])
+    return rows
+
+
+def _write_tsv(path, rows):
+    with open(path, "w", newline="") as f:             # csv 'excel' dialect => CRLF, like the reference
+        csv.writer(f, delimiter="\t").writerows(rows)
+
+
+def d_gene_rows(parent_seq, rss_idx):
+    """extract_genes for D, py/IGDetective.py:366-378."""
+    rows = []
+    for strand in rss_idx:
+        for contig in rss_idx[strand]:
+            s = parent_seq[contig]
+            for e in rss_idx[strand][contig]:
+                lh, ln = _kmer(s, e[0], 7, strand), _kmer(s, e[1], 9, strand)
+                rh, rn = _kmer(s, e[2], 7, strand), _kmer(s, e[3], 9, strand)
+                if strand == FWD:
+                    gs, ge, gene = e[0] + 7, e[2] - 1, s[e[0] + 7:e[2]].upper()
+                else:
+                    gs, ge, gene = e[2] + 7, e[0] - 1, reverse_complement(s[e[2] + 7:e[0]]).upper()
+                rows.append([contig, strand, e[0], e[1], lh, ln, e[2], e[3], rh, rn, gs, ge, gene])
+    return rows
+
+
+def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
+    """Scoring + argmax (:463-477) + extract_genes for V / J (:380-420)."""
+    ids = list(canonical.keys())
+    glist = list(canonical.values())
+    flat = []
+    for strand in (FWD, REV):
+        for contig in fragments[strand]:
+            flat.extend(fragments[strand][contig])
+    # the reference runs the same computation twice ('AFFINE' and 'MAXK', :467-468); once is enough
+    pi_mat, len_mat = align_fragment_to_genes(flat, glist, "AFFINE", gene, engine=engine)
+    winners, k = [], 0
+    for strand in (FWD, REV):
+        for contig in fragments[strand]:
+            for i, frag in enumerate(fragments[strand][contig]):
+                best = int(np.argmax(pi_mat[k]))
+                pi, maxk = pi_mat[k][best], len_mat[k][best]
+                k += 1
+                if pi >= PI_CUTOFF["strict"][gene] or (pi >= PI_CUTOFF["relax"][gene] and maxk >= MAXK_CUTOFF[gene]):
+                    winners.append((strand, contig, i, frag, best, pi, maxk))
+    rows = []
+    if not winners:
+        return rows
+    detail = compute_alignments(engine, [(w[3], w[4]) for w in winners], glist, want_ient=True)   # :388
+    for (strand, contig, i, frag, best, pi, maxk), (aln, direction, _) in zip(winners, detail):
+        r = rss_idx[strand][contig][i]
+        s = parent_seq[contig]
+        start, end = aln.AlignmentRange()
+        if strand == FWD:
+            if gene == V:
+                ge = r[0] - 1
+                gs = r[0] - GENE_LENGTH[gene] + start
+            else:
+                gs = r[0] + 7
+                ge = gs + end
+        else:
+            if gene == V:
+                gs = r[0] + 7
+                ge = gs + GENE_LENGTH[gene] - start - 1
+            else:
+                ge = r[0] - 1
+                gs = r[0] - end
+        rows.append([contig, strand, r[0], r[1], _kmer(s, r[0], 7, strand), _kmer(s, r[1], 9, strand),
+                     gs, ge, ids[best], direction, int(round(pi)), maxk, aln.QuerySeq()])
+    return rows
+
+
+def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False):
+    """The module body of py/IGDetective.py:439-487 as a function.
+    Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only."""
+    scan = RssScan(engine, input_seq_dict, order=order)
+    info = {st: {sd: scan.contigwise(st, sd) for sd in (FWD, REV)} for st in SIGNAL_TYPES}
+    info[D] = {sd: combine_D_RSS(info[DL][sd], info[DR][sd], input_seq_dict, sd) for sd in (FWD, REV)}
+    if rss_only:
+        return info, None
+    frags = {g: {sd: get_s_fragment_from_RSS(g, sd, info, input_seq_dict) for sd in (FWD, REV)} for g in (V, J)}
+    rows = {D: d_gene_rows(input_seq_dict, info[D])}
+    for gene in (V, J):
+        rows[gene] = vj_gene_rows(engine, input_seq_dict, gene, info[gene], frags[gene], canonical_genes[gene])
+    return info, rows
+
+
+def run(input_path, output_path, locus="IGH", rss_only=False, engine=None, datafiles=None,
+        gene_dir="combined_reference_genes", order="reference", device=0):
+    own = engine is None
+    if own:
+        engine = Engine(device)
+    try:
+        engine.set_motifs(dfiles.load_motifs(datafiles))
+        print("Finding immunoglobulin genes for locus " + locus + "...")
+        input_seq_dict = fasta_dict(input_path)
+        canonical = {g: dfiles.load_canonical_genes(locus, g, gene_dir, datafiles) for g in (V, J)}
+        os.makedirs(output_path, exist_ok=True)
+        print("Finding candidate RSS...", end=" ")
+        info, rows = detect(engine, input_seq_dict, canonical, order, rss_only)
+        print("Done")
+        if rss_only:
+            for st in SIGNAL_TYPES:
+                _write_tsv("{}/rss_{}.csv".format(output_path, st), rss_rows(info[st], input_seq_dict))
+            return
+        print("Aligning candidate genes...", end=" ")
+        print("Done")
+        for gene in (V, D, J):
+            _write_tsv("{}/genes_{}.tsv".format(output_path, gene), [D_HEADER if gene == D else VJ_HEADER] + rows[gene])
+        print("Please see {}/ for gene predictions".format(output_path))
+    finally:
+        if own:
+            engine.close()
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    options = "hi:o:m:rg:l:"
+    long_options = ["help", "input_file=", "output_directory=", "multi_process=", "rss_only", "genes_type=",
+                    "locus=", "datafiles=", "gene_dir=", "device=", "order="]
+    try:
+        arguments, _ = getopt.getopt(argv, options, long_options)
+    except getopt.error as err:
+        print(str(err))
+        sys.exit(0)
+    inp = out = None
+    locus, rss_mode, datafiles, gene_dir, device, order = "IGH", False, None, "combined_reference_genes", 0, "reference"
+    for a, v in arguments:
+        if a in ("-h", "--help"):
+            print(__doc__)
+            return
+        elif a in ("-i", "--input_file"):
+            inp = str(v)
+        elif a in ("-o", "--output_directory"):
+            out = str(v)
+        elif a in ("-l", "--locus"):
+            if v not in ["IGH", "IGK", "IGL", "TRA", "TRB", "TRG"]:
+                print("Incorrect locus argument: " + v)
+                sys.exit(1)
+            locus = v
+        elif a in ("-m", "--multi_process"):
+            int(v)                       # accepted for compatibility; the GPU path does not fork
+        elif a in ("-r", "--rss_only"):
+            rss_mode = True
+        elif a == "--datafiles":
+            datafiles = v
+        elif a == "--gene_dir":
+            gene_dir = v
+        elif a == "--device":
+            device = int(v)
+        elif a == "--order":
+            order = v
+    if inp is None:
+        raise NameError("no input file was given")
+    if out is None:
+        out = ".".join(inp.split(".")[:-1])
+    run(inp, out, locus, rss_mode, None, datafiles, gene_dir, order, device)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,135 @@
+"""RSS stage behind the reference's function seams (py/IGDetective.py:138-300).
+
+One GPU pass (Engine.scan_rss) evaluates both strands and the four signal types; the functions
+below serve its result in the reference's own shapes:
+  get_contigwise_rss(sig_type, strand, parent_seq) -> {contig: [(hept_idx, nona_idx), ...]}   (:180)
+  combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len)                   (:210)
+  get_s_fragment_from_RSS(gene, strand, ...)                                                  (:268)
+"""
+import numpy as np
+
+from .engine import SIGNAL_INDEX, SIGNAL_NAMES
+from .fasta import reverse_complement
+from .order import rank_map
+
+V, D, J, DR, DL = "V", "D", "J", "D_right", "D_left"
+FWD, REV = "+", "-"
+SIGNAL_TYPES = [V, J, DL, DR]                        # :119-125 with the default GENE_TYPES_TOFIND
+# InitializeVariables (:36-51) assigns locals only, so every locus runs with these
+SPACER_LENGTH = {V: 23, DL: 12, DR: 12, J: 23}
+GENE_LENGTH = {V: 350, J: 70, D: 150}
+HEPT_FIRST = {V: True, DR: True, J: False, DL: False}
+
+
+class RssScan:
+    """Result of one scan of `parent_seq` ({contig id: str}) on an Engine."""
+
+    def __init__(self, engine, parent_seq, spacers=None, order="reference"):
+        if order not in ("reference", "canonical"):
+            raise ValueError("order must be 'reference' or 'canonical'")
+        self.engine = engine
+        self.seqs = parent_seq
+        self.ids = list(parent_seq.keys())
+        self.lens = [len(parent_seq[c]) for c in self.ids]
+        self.spacers = dict(spacers or SPACER_LENGTH)
+        self.order = order
+        engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
+        self.hits = engine.scan_rss(self.spacers)
+        self._kmers = {}
+        self._cache = {}
+
+    def _kmer_hits(self, k):
+        if k not in self._kmers:
+            self._kmers[k] = self.engine.scan_kmers(k)
+        return self._kmers[k]
+
+    def _first_set(self, sig_type, strand, ci):
+        """Ascending scanned-strand indices of the 5' k-mer set of find_valid_rss (:153-160)."""
+        k = 7 if HEPT_FIRST[sig_type] else 9
+        kh = self._kmer_hits(k)
+        bit = 1 << (SIGNAL_INDEX[sig_type] + (4 if strand == REV else 0))
+        sel = kh[(kh["contig"] == ci) & ((kh["flags"] & bit) != 0)]["pos"].astype(np.int64)
+        if strand == REV:
+            sel = (self.lens[ci] - sel - k)[::-1]
+        return sel.tolist()
+
+    def contigwise(self, sig_type, strand):
+        key = (sig_type, strand)
+        if key in self._cache:
+            return self._cache[key]
+        t, s = SIGNAL_INDEX[sig_type], (0 if strand == FWD else 1)
+        h = self.hits[(self.hits["sig_type"] == t) & (self.hits["strand"] == s)]
+        res = {}
+        for ci, cid in enumerate(self.ids):
+            hc = h[h["contig"] == ci]                  # already ascending in scan-order index
+            tuples = [(int(a), int(b)) for a, b in zip(hc["hept"], hc["nona"])]
+            if self.order == "reference" and len(tuples) > 1:
+                k = 7 if HEPT_FIRST[sig_type] else 9
+                L = self.lens[ci]
+                rank = rank_map(self._first_set(sig_type, strand, ci))
+
+                def scan_index(tp):
+                    first = tp[0] if HEPT_FIRST[sig_type] else tp[1]
+                    return first if strand == FWD else L - first - k
+                tuples.sort(key=lambda tp: rank[scan_index(tp)])
+            res[cid] = tuples
+        self._cache[key] = res
+        return res
+
+
+def get_contigwise_rss(sig_type, strand, parent_seq, scan=None, engine=None, order="reference"):
+    """Drop-in for py/IGDetective.py:180.  Pass a shared RssScan to serve all eight
+    (sig_type, strand) calls of :443 from one GPU pass."""
+    if scan is None:
+        if engine is None:
+            raise ValueError("get_contigwise_rss needs an Engine or an RssScan")
+        scan = RssScan(engine, parent_seq, order=order)
+    return scan.contigwise(sig_type, strand)
+
+
+def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GENE_LENGTH[D]):
+    """py/IGDetective.py:210-224: every (dr, dl) with left < right and right-(left+7) <= Dgene_len,
+    dr-outer / dl-inner in the given list orders.  Vectorised per dr; same output."""
+    res = {c: [] for c in input_seq_dict.keys()}
+    for c in input_seq_dict:
+        dls, drs = D_left_idx[c], D_right_idx[c]
+        if not dls or not drs:
+            continue
+        dl0 = np.fromiter((x[0] for x in dls), np.int64, len(dls))
+        for dr in drs:
+            if strand == FWD:
+                ok = (dr[0] - (dl0 + 7) <= Dgene_len) & (dl0 < dr[0])
+            else:
+                ok = (dl0 - (dr[0] + 7) <= Dgene_len) & (dr[0] < dl0)
+            for i in np.nonzero(ok)[0]:
+                dl = dls[i]
+                res[c].append((dl[0], dl[1], dr[0], dr[1]))
+    return res
+
+
+def extract_s_fragment(index, extract_dir, length, parent_seq):
+    """py/IGDetective.py:260-266 -- plain Python slicing, including its negative-start behaviour."""
+    if extract_dir == FWD:
+        return parent_seq[index:index + length]
+    return parent_seq[index - length:index]
+
+
+def get_s_fragment_from_RSS(gene, strand, input_rss_info, input_seq_dict):
+    """py/IGDetective.py:268-300 (the globals it reads are parameters here)."""
+    out = {c: [] for c in input_rss_info[gene][strand]}
+    for c in input_rss_info[gene][strand]:
+        s = input_seq_dict[c]
+        frs = []
+        for r in input_rss_info[gene][strand][c]:
+            if (gene == V and strand == FWD) or (gene == J and strand == REV):
+                frs.append(extract_s_fragment(r[0], REV, GENE_LENGTH[gene], s))
+            elif gene in (V, J):
+                frs.append(extract_s_fragment(r[0] + 7, FWD, GENE_LENGTH[gene], s))
+            else:
+                index = r[0] + 7 if strand == FWD else r[2] + 7
+                glen = (r[2] if strand == FWD else r[0]) - index
+                frs.append(extract_s_fragment(index, FWD, glen, s))
+        if strand == REV:
+            frs = [reverse_complement(x) for x in frs]
+        out[c] = frs
+    return out

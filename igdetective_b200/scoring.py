@@ -1,0 +1,173 @@
+"""Scoring stage behind the reference's function seams.
+
+  ComputeAlignment(seq_A, seq_B, ext)                      py/IGDetective.py:307-317
+  align_fragment_to_genes(fragments, canon_genes, ...)     py/IGDetective.py:319-360
+  BioAlign                                                 py/extract_aligned_genes.py:9-56
+  ComputeAlignment(aligner, query_list, strand_list, genes) py/extract_aligned_genes.py:85-105
+
+The GPU returns, per (target, query) pair, the integers BioAlign derives from BioPython's first
+optimal alignment; this module turns them into the reference's return values (float64 PI etc.)."""
+import numpy as np
+
+from .fasta import reverse_complement
+
+
+class BioAlignView:
+    """The observable surface of BioAlign (extract_aligned_genes.py:9-56) over GPU results."""
+
+    def __init__(self, target, matches, start, end, ient=None):
+        self._target = target
+        self._matches = int(matches)
+        self.gene_range = (int(start), int(end))
+        self._ient = None if ient is None else int(ient)
+
+    def NumMatches(self):
+        return self._matches - 1            # the reference starts counting at -1 (:16,33-38)
+
+    def __len__(self):
+        return self.gene_range[1] - self.gene_range[0]
+
+    def PI(self):
+        return self.NumMatches() / len(self) * 100
+
+    def AlignmentRange(self):
+        return self.gene_range
+
+    def QuerySeq(self):
+        if self._ient is None:
+            raise RuntimeError("alignment was computed without ient")
+        return self._target[self.gene_range[0]:self._ient].upper()
+
+
+def pi_from(matches, start, end):
+    """float64 PI exactly as BioAlign.PI(): (matches-1) / len * 100, evaluated left to right."""
+    return (np.asarray(matches, np.int64) - 1) / (np.asarray(end, np.int64) - np.asarray(start, np.int64)) * 100
+
+
+def compute_alignments(engine, pairs, genes, want_ient=False):
+    """IGDetective.ComputeAlignment for many (fragment, gene index) pairs in one GPU batch.
+    Returns a list of (BioAlignView, direction, matches-1): direction '+' iff the forward
+    orientation has strictly more matches (:314-317)."""
+    targets, pt, pq = [], [], []
+    index = {}
+    for frag, g in pairs:
+        q = str(frag).upper()
+        if q not in index:
+            index[q] = len(targets)
+            targets.append(q)
+            targets.append(reverse_complement(q))
+        pt += [index[q], index[q] + 1]
+        pq += [g, g]
+    r = engine.align(targets, genes, pt, pq, want_ient=want_ient)
+    out = []
+    for k in range(len(pairs)):
+        f, b = 2 * k, 2 * k + 1
+        pick, d = (f, "+") if r["matches"][f] - 1 > r["matches"][b] - 1 else (b, "-")
+        view = BioAlignView(targets[pt[pick]], r["matches"][pick], r["start"][pick], r["end"][pick],
+                            r["ient"][pick] if want_ient else None)
+        out.append((view, d, int(r["matches"][pick]) - 1))
+    return out
+
+
+def ComputeAlignment(seq_A, seq_B, extend_alignment=None, engine=None):
+    """Drop-in for py/IGDetective.py:307 (one pair)."""
+    return compute_alignments(engine, [(seq_A, 0)], [str(seq_B)], want_ient=True)[0]
+
+
+def align_fragment_to_genes(fragments, canon_genes, scoring_scheme=None, gene=None, engine=None):
+    """Drop-in for py/IGDetective.py:319-360 -> (pi_mat, alig_len_mat), float64 [F, G].
+    `scoring_scheme` is ignored, as in the reference (set_aligner, :303-304)."""
+    genes = [str(g) for g in canon_genes]
+    F, G = len(fragments), len(genes)
+    if F == 0 or G == 0:
+        return np.zeros((F, G)), np.zeros((F, G))
+    targets, tindex = [], {}
+
+    def tid(s):
+        if s not in tindex:
+            tindex[s] = len(targets)
+            targets.append(s)
+            targets.append(reverse_complement(s))
+        return tindex[s]
+    pt = np.zeros((F, G, 2), np.int32)
+    for i, f in enumerate(fragments):
+        q = str(f).upper()
+        if len(q):
+            t = tid(q)
+            pt[i, :, 0] = t
+            pt[i, :, 1] = t + 1
+        else:                                    # empty fragment -> 'A' * len(gene) (:339-340)
+            for j, g in enumerate(genes):
+                t = tid("A" * len(g))
+                pt[i, j, 0] = t
+                pt[i, j, 1] = t + 1
+    pq = np.broadcast_to(np.arange(G, dtype=np.int32)[None, :, None], (F, G, 2))
+    r = engine.align(targets, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
+    m = r["matches"].reshape(F, G, 2)
+    st = r["start"].reshape(F, G, 2)
+    en = r["end"].reshape(F, G, 2)
+    fwd = (m[:, :, 0] - 1) > (m[:, :, 1] - 1)
+    pick = np.where(fwd, 0, 1)[:, :, None]
+    mm = np.take_along_axis(m, pick, 2)[:, :, 0]
+    ss = np.take_along_axis(st, pick, 2)[:, :, 0]
+    ee = np.take_along_axis(en, pick, 2)[:, :, 0]
+    return pi_from(mm, ss, ee), (ee - ss).astype(np.float64)
+
+
+class Alignment:
+    """extract_aligned_genes.Alignment (:58-70)."""
+
+    def __init__(self):
+        self.gene_seq, self.gene_id, self.pi = "", "", 0
+
+    def Initiate(self, gene_seq, gene_id, pi):
+        self.gene_seq, self.gene_id, self.pi = gene_seq, gene_id, pi
+
+    def Empty(self):
+        return self.gene_seq == "" or self.gene_seq[0] == " "
+
+
+def window_alignments(engine, windows, genes):
+    """extract_aligned_genes.ComputeAlignment (:85-105) for many windows in one GPU batch.
+    windows: raw-case strings; genes: [(id, SEQ)].  For each window the scan order is
+    [window, RC(window)] x genes, keeping the LAST maximum of PI (>=, from 0).
+    Returns [(Alignment, strand)]."""
+    G = len(genes)
+    targets = []
+    for w in windows:
+        targets.append(w)
+        targets.append(reverse_complement(w))
+    W = len(windows)
+    out = []
+    if W == 0 or G == 0:
+        return [(Alignment(), "") for _ in windows]
+    pt = np.repeat(np.arange(2 * W, dtype=np.int32), G)
+    pq = np.tile(np.arange(G, dtype=np.int32), 2 * W)
+    r = engine.align(targets, [g[1] for g in genes], pt, pq)
+    pi = pi_from(r["matches"], r["start"], r["end"]).reshape(W, 2 * G)
+    # last index attaining the maximum, provided the maximum is >= 0 (best_pi starts at 0)
+    best = 2 * G - 1 - np.argmax(pi[:, ::-1], axis=1)
+    need = []
+    for w in range(W):
+        if pi[w, best[w]] >= 0:
+            need.append((w, int(best[w])))
+    detail = {}
+    if need:
+        dt = [2 * w + b // G for w, b in need]
+        dq = [b % G for w, b in need]
+        d = engine.align(targets, [g[1] for g in genes], dt, dq, want_ient=True)
+        for i, (w, b) in enumerate(need):
+            detail[w] = (b, d["start"][i], d["end"][i], d["ient"][i])
+    for w in range(W):
+        a = Alignment()
+        if w not in detail:
+            out.append((a, ""))
+            continue
+        b, s, e, ie = detail[w]
+        if e - s == 0:
+            out.append((a, ""))
+            continue
+        seq = targets[2 * w + b // G][int(s):int(ie)].upper()
+        a.Initiate(seq, genes[b % G][0], float(pi[w, b]))
+        out.append((a, "+-"[b // G]))
+    return out

@@ -1,0 +1,46 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+DATAFILES = os.path.join(GOLDEN, "datafiles")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _oracle_built():
+    """The oracle's C part is compiled on demand (gcc only)."""
+    import subprocess
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+
+
+@pytest.fixture(scope="session")
+def motifs():
+    from oracle import igd_oracle
+    return igd_oracle.load_motifs_text(os.path.join(DATAFILES, "motif_sets.txt"))
+
+
+@pytest.fixture(scope="session")
+def engine(motifs):
+    """One Engine per session; creating it fails loudly when the CUDA library or a B200 is missing."""
+    from igdetective_b200.engine import Engine
+    e = Engine(0, motifs)
+    yield e
+    e.close()
+
+
+def golden_input(name):
+    return os.path.join(GOLDEN, "inputs", name + ".fa.gz")
+
+
+def canonical(gene_dir, locus="IGH"):
+    from oracle import igd_oracle
+    return {g: igd_oracle.fasta_dict(os.path.join(DATAFILES, gene_dir, "%s%s.fa.gz" % (locus, g)), upper=True)
+            for g in ("V", "J")}

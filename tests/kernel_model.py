@@ -1,0 +1,106 @@
+"""Pure-Python models of what the CUDA kernels compute, used by the CPU tests to check the
+ALGORITHMS (heptamer-gated forward-only scan; key/payload Gotoh) against the oracle before any GPU
+time is spent.  Test infrastructure only."""
+import numpy as np
+
+SIG = ["V", "D_left", "D_right", "J"]
+HEPT_FIRST = {"V": True, "D_right": True, "J": False, "D_left": False}
+_COMP = str.maketrans("ACGT", "TGCA")
+
+
+def _rc(s):
+    return s.translate(_COMP)[::-1]
+
+
+def scan_model(seq, motifs, spacers):
+    """rss_scan.cu's formulation: forward coordinates only, reverse strand through RC'd motif
+    sets, pairing gated on heptamer hits.  Returns {(type, strand): set of (hept, nona)}."""
+    s = seq.upper()
+    L = len(s)
+    H = {t: {"+": motifs[t]["7"], "-": {_rc(m) for m in motifs[t]["7"]}} for t in SIG}
+    N = {t: {"+": motifs[t]["9"], "-": {_rc(m) for m in motifs[t]["9"]}} for t in SIG}
+
+    def hept(x, t, sd):
+        return 0 <= x <= L - 7 and s[x:x + 7] in H[t][sd]
+
+    def nona(x, t, sd):
+        return 0 <= x <= L - 9 and s[x:x + 9] in N[t][sd]
+    out = {(t, sd): set() for t in SIG for sd in "+-"}
+    for q in range(L - 6):
+        for t in SIG:
+            sp = spacers[t]
+            cand = (sp, sp - 1, sp + 1)
+            if hept(q, t, "+"):
+                if HEPT_FIRST[t]:
+                    for s1 in cand:
+                        if nona(q + 7 + s1, t, "+"):
+                            out[(t, "+")].add((q, q + 7 + s1)); break
+                else:
+                    if nona(q - 9 - sp, t, "+"):
+                        out[(t, "+")].add((q, q - 9 - sp))
+                    if not hept(q + 1, t, "+") and nona(q - 9 - (sp - 1), t, "+"):
+                        out[(t, "+")].add((q, q - 9 - (sp - 1)))
+                    if not hept(q - 1, t, "+") and not hept(q - 2, t, "+") and nona(q - 9 - (sp + 1), t, "+"):
+                        out[(t, "+")].add((q, q - 9 - (sp + 1)))
+            if hept(q, t, "-"):
+                if HEPT_FIRST[t]:
+                    for s1 in cand:
+                        if nona(q - s1 - 9, t, "-"):
+                            out[(t, "-")].add((q, q - s1 - 9)); break
+                else:
+                    if nona(q + 7 + sp, t, "-"):
+                        out[(t, "-")].add((q, q + 7 + sp))
+                    if not hept(q - 1, t, "-") and nona(q + 7 + (sp - 1), t, "-"):
+                        out[(t, "-")].add((q, q + 7 + (sp - 1)))
+                    if not hept(q + 1, t, "-") and not hept(q + 2, t, "-") and nona(q + 7 + (sp + 1), t, "-"):
+                        out[(t, "-")].add((q, q + 7 + (sp + 1)))
+    return out
+
+
+NEG = -(1 << 26)
+
+
+def gotoh_model(A, B, sc, pay_mode=0):
+    """gotoh.cu's recurrence: integer keys 4*score+priority, payload selected by the same compare.
+    sc: dict with the ten igd_scoring fields.  Returns (score, matches, lead_or_trail, intIx)."""
+    A = A.encode("latin-1") if isinstance(A, str) else A
+    B = B.encode("latin-1") if isinstance(B, str) else B
+    nA, nB = len(A), len(B)
+    up = lambda c: c - 32 if 97 <= c <= 122 else c
+    m4, x4 = 4 * sc["match"], 4 * sc["mismatch"]
+    to4, te4 = 4 * sc["target_internal_open"], 4 * sc["target_internal_extend"]
+    qio4, qie4 = 4 * sc["query_internal_open"], 4 * sc["query_internal_extend"]
+    qeo4, qee4 = 4 * sc["query_end_open"], 4 * sc["query_end_extend"]
+    u_int, u_trail = 1 << 10, ((1 << 20) if pay_mode == 1 else 0)
+    lead = (lambda i: i << 20) if pay_mode == 0 else (lambda i: 0)
+    # column state, indexed by row i (0..nA): D key/pay, Iy key/pay for column j-1
+    Dk = [2] + [(qeo4 + qee4 * (i - 1)) | 1 for i in range(1, nA + 1)]
+    Dp = [0] + [lead(i) for i in range(1, nA + 1)]
+    Yk = [NEG] * (nA + 1)
+    Yp = [0] * (nA + 1)
+    for j in range(1, nB + 1):
+        last = j == nB
+        qo4, qe4 = (qeo4, qee4 + 1) if last else (qio4, qie4 + 1)
+        ux = u_trail if last else u_int
+        nDk, nDp, nYk, nYp = [0] * (nA + 1), [0] * (nA + 1), [0] * (nA + 1), [0] * (nA + 1)
+        nDk[0], nDp[0], nYk[0], nYp[0] = to4 + te4 * (j - 1), 0, to4 + te4 * (j - 1), 0
+        xk, xp = NEG, 0
+        for i in range(1, nA + 1):
+            a, b = A[i - 1], B[j - 1]
+            mk = ((Dk[i - 1] & ~3) | 2) + (m4 if a == b else x4)
+            mp = Dp[i - 1] + (1 if up(a) == up(b) else 0)
+            c1, c2 = nDk[i - 1] + qo4, xk + qe4
+            nxk = max(c1, c2) & ~3
+            nxp = (nDp[i - 1] if c1 >= c2 else xp) + ux
+            e1, e2 = Dk[i] + to4, Yk[i] + te4
+            nyk = max(e1, e2) & ~3
+            nyp = Dp[i] if e1 >= e2 else Yp[i]
+            xk1 = nxk | 1
+            bk, bp = (mk, mp) if mk >= xk1 else (xk1, nxp)
+            if not bk >= nyk:
+                bk, bp = nyk, nyp
+            nDk[i], nDp[i], nYk[i], nYp[i] = bk, bp, nyk, nyp
+            xk, xp = nxk, nxp
+        Dk, Dp, Yk, Yp = nDk, nDp, nYk, nYp
+    k, p = Dk[nA], Dp[nA]
+    return k >> 2, p & 1023, (p >> 20) & 1023, (p >> 10) & 1023

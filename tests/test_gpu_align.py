@@ -1,0 +1,146 @@
+"""Alignment parity: CUDA Gotoh (through the C ABI) vs the oracle's BioPython restatement.  Bit-exact."""
+import numpy as np
+import pytest
+
+import synth
+from conftest import canonical
+from oracle import igd_oracle as O
+
+pytestmark = pytest.mark.gpu
+KEYS = ("score", "matches", "start", "end", "ient")
+
+
+def compare(engine, targets, queries, pt, pq):
+    got = engine.align(targets, queries, pt, pq, want_ient=True)
+    want = O.align_stats(targets, queries, pt, pq, threads=8)
+    for k, wk in zip(KEYS, ("score", "matches", "start", "end", "ient")):
+        w = want[wk].astype(np.int64)
+        bad = np.nonzero(got[k] != w)[0]
+        assert bad.size == 0, (k, bad[:5], got[k][bad[:5]], w[bad[:5]],
+                               [(targets[pt[i]], queries[pq[i]]) for i in bad[:1]])
+
+
+def rand_seq(rng, n, alphabet="ACGT"):
+    return "".join(alphabet[i] for i in rng.integers(0, len(alphabet), n))
+
+
+def test_align_small_exhaustive_lengths(engine):
+    rng = np.random.default_rng(1)
+    targets = [rand_seq(rng, n) for n in list(range(1, 40)) + [71, 72, 73, 191, 192, 193]]
+    queries = [rand_seq(rng, n) for n in list(range(1, 30)) + [50, 63]]
+    pt, pq = np.meshgrid(np.arange(len(targets)), np.arange(len(queries)), indexing="ij")
+    compare(engine, targets, queries, pt.ravel(), pq.ravel())
+
+
+def test_align_bucket_edges(engine):
+    rng = np.random.default_rng(2)
+    lens = [351, 352, 353, 511, 512, 513, 799, 800, 801, 1022, 1023]
+    targets = [rand_seq(rng, n) for n in lens]
+    queries = [rand_seq(rng, n) for n in (1, 38, 294, 325, 700, 1023)]
+    # related pairs too: a query embedded in the target
+    for n in lens:
+        q = queries[2]
+        t = rand_seq(rng, max(0, n - len(q)) // 2) + synth.mutate(rng, q, 0.1, 0.02)
+        targets.append((t + rand_seq(rng, n))[:n])
+    pt, pq = np.meshgrid(np.arange(len(targets)), np.arange(len(queries)), indexing="ij")
+    compare(engine, targets, queries, pt.ravel(), pq.ravel())
+
+
+def test_align_v_fragments_vs_gene_set(engine):
+    """350-nt fragments (true, mutated, background, 'A'*len) x the IGHV set, both orientations"""
+    rng = np.random.default_rng(3)
+    genes = list(canonical("combined_reference_genes")["V"].values())
+    frags = []
+    for i in range(24):
+        g = genes[rng.integers(len(genes))]
+        if i % 3 == 0:
+            f = rand_seq(rng, 350)
+        else:
+            m = synth.mutate(rng, g, rng.uniform(0.02, 0.25), rng.uniform(0, 0.02))
+            f = (rand_seq(rng, 350) + m)[-350:]
+        frags.append(f)
+        frags.append(O.revcomp(f))
+    frags.append("A" * 296)
+    frags.append("ACGT" * 80 + "NNNNNNNNNN" + "Y" * 5)
+    gsel = list(rng.choice(len(genes), 120, replace=False))
+    queries = [genes[i] for i in gsel]
+    pt, pq = np.meshgrid(np.arange(len(frags)), np.arange(len(queries)), indexing="ij")
+    compare(engine, frags, queries, pt.ravel(), pq.ravel())
+
+
+def test_align_j_fragments(engine):
+    rng = np.random.default_rng(4)
+    genes = list(canonical("combined_reference_genes")["J"].values())
+    frags = []
+    for i in range(64):
+        g = genes[rng.integers(len(genes))]
+        f = (synth.mutate(rng, g, 0.1, 0.02) + rand_seq(rng, 70))[:70] if i % 2 else rand_seq(rng, int(rng.integers(1, 71)))
+        frags.append(f)
+    pt, pq = np.meshgrid(np.arange(len(frags)), np.arange(len(genes)), indexing="ij")
+    compare(engine, frags, genes, pt.ravel(), pq.ravel())
+
+
+def test_align_windows_raw_case(engine):
+    """800-nt raw-case windows (scoring B): lower-case letters mismatch in the DP but count as matches"""
+    rng = np.random.default_rng(5)
+    genes = list(canonical("combined_reference_genes")["V"].values())
+    wins = []
+    for i in range(10):
+        g = genes[rng.integers(len(genes))]
+        w = rand_seq(rng, 250) + synth.mutate(rng, g, 0.08, 0.01) + rand_seq(rng, 400)
+        w = w[:800]
+        if i % 2:
+            a = int(rng.integers(0, 600))
+            w = w[:a] + w[a:a + 150].lower() + w[a + 150:]
+        if i == 9:
+            w = w.lower()                       # fully soft-masked: every path ties, pure tie-break test
+        wins.append(w)
+        wins.append(O.revcomp(w))
+    gsel = list(rng.choice(len(genes), 60, replace=False))
+    queries = [genes[i] for i in gsel]
+    pt, pq = np.meshgrid(np.arange(len(wins)), np.arange(len(queries)), indexing="ij")
+    compare(engine, wins, queries, pt.ravel(), pq.ravel())
+
+
+def test_align_low_complexity_ties(engine):
+    """homopolymers / repeats maximise co-optimal paths: the M > Ix > Iy preference decides everything"""
+    targets = ["A" * 50, "AC" * 40, "A" * 20 + "C" * 20, "ACGT" * 30, "T" * 7, "G"]
+    queries = ["A" * 10, "AC" * 7, "CA" * 7, "AAAC", "C", "ACGT" * 5, "T" * 30]
+    pt, pq = np.meshgrid(np.arange(len(targets)), np.arange(len(queries)), indexing="ij")
+    compare(engine, targets, queries, pt.ravel(), pq.ravel())
+
+
+def test_align_empty_target_and_errors(engine):
+    from igdetective_b200._lib import IgdError
+    r = engine.align(["", "ACGT"], ["ACGTAC"], [0, 1], [0, 0], want_ient=True)
+    assert (r["score"][0], r["matches"][0], r["start"][0], r["end"][0], r["ient"][0]) == (-7, 0, 0, 6, 0)
+    with pytest.raises(IgdError):
+        engine.align(["A" * 1024], ["ACGT"], [0], [0])
+    with pytest.raises(IgdError):
+        engine.align(["ACGT"], [""], [0], [0])
+    with pytest.raises(IgdError):
+        engine.align(["ACGT"], ["ACGT"], [0], [0], scoring=dict(match=2, mismatch=0, target_internal_open=-2,
+                     target_internal_extend=-1, target_end_open=0, target_end_extend=0, query_internal_open=-2,
+                     query_internal_extend=-1, query_end_open=0, query_end_extend=0))
+
+
+def test_align_other_schemes(engine):
+    rng = np.random.default_rng(6)
+    targets = [rand_seq(rng, int(rng.integers(1, 120))) for _ in range(40)]
+    queries = [rand_seq(rng, int(rng.integers(1, 60))) for _ in range(20)]
+    pt, pq = [a.ravel() for a in np.meshgrid(np.arange(40), np.arange(20), indexing="ij")]
+    for sc in (dict(match=1, mismatch=-1, to=-3, te=-1, qo=-3, qe=-1, qeo=-3, qee=-1),
+               dict(match=5, mismatch=-4, to=-10, te=-1, qo=-8, qe=-2, qeo=0, qee=0),
+               dict(match=1, mismatch=0, to=0, te=0, qo=0, qe=0, qeo=0, qee=0)):
+        gsc = dict(match=sc["match"], mismatch=sc["mismatch"], target_internal_open=sc["to"],
+                   target_internal_extend=sc["te"], target_end_open=sc["to"], target_end_extend=sc["te"],
+                   query_internal_open=sc["qo"], query_internal_extend=sc["qe"],
+                   query_end_open=sc["qeo"], query_end_extend=sc["qee"])
+        osc = dict(match=sc["match"], mismatch=sc["mismatch"], t_int_open=sc["to"], t_int_ext=sc["te"],
+                   t_left_open=sc["to"], t_left_ext=sc["te"], t_right_open=sc["to"], t_right_ext=sc["te"],
+                   q_int_open=sc["qo"], q_int_ext=sc["qe"], q_left_open=sc["qeo"], q_left_ext=sc["qee"],
+                   q_right_open=sc["qeo"], q_right_ext=sc["qee"])
+        got = engine.align(targets, queries, pt, pq, scoring=gsc, want_ient=True)
+        want = O.align_stats(targets, queries, pt, pq, scoring=osc, threads=8)
+        for k in KEYS:
+            assert np.array_equal(got[k], want[k].astype(np.int64)), (sc, k)

@@ -1,0 +1,139 @@
+"""RSS scan parity: CUDA path (through the C ABI) vs the oracle.  Integer/index work: bit-exact."""
+import numpy as np
+import pytest
+
+import synth
+from conftest import golden_input
+from oracle import igd_oracle as O
+
+pytestmark = pytest.mark.gpu
+SIG = synth.SIG
+
+
+def oracle_hits(seqs, motifs):
+    """{(contig index, type, strand): sorted list of (hept, nona)}"""
+    out = {}
+    ids = list(seqs.keys())
+    for t in SIG:
+        for sd in "+-":
+            r = O.get_contigwise_rss(t, sd, seqs, motifs, order="canonical")
+            for ci, c in enumerate(ids):
+                out[(ci, t, sd)] = sorted(r[c])
+    return out
+
+
+def gpu_hits(engine, seqs):
+    engine.load_contigs(seqs)
+    h = engine.scan_rss(O.SPACER_LENGTH)
+    out = {(ci, t, sd): [] for ci in range(len(seqs)) for t in SIG for sd in "+-"}
+    for r in h:
+        out[(int(r["contig"]), SIG[r["sig_type"]], "+-"[r["strand"]])].append((int(r["hept"]), int(r["nona"])))
+    return {k: sorted(v) for k, v in out.items()}, h
+
+
+def check(engine, seqs, motifs):
+    want = oracle_hits(seqs, motifs)
+    got, raw = gpu_hits(engine, seqs)
+    assert want.keys() == got.keys()
+    for k in want:
+        assert got[k] == want[k], k
+    return raw
+
+
+@pytest.mark.parametrize("name", ["cow", "human", "mouse"])
+def test_scan_examples(engine, motifs, name):
+    seqs = O.fasta_dict(golden_input(name))
+    raw = check(engine, seqs, motifs)
+    assert len(raw) > 50
+
+
+def test_kmer_hits_examples(engine, motifs):
+    seqs = O.fasta_dict(golden_input("cow"))
+    (cid, s), = seqs.items()
+    engine.load_contigs(seqs)
+    for k in (7, 9):
+        kh = engine.scan_kmers(k)
+        assert np.all(np.diff(kh["pos"]) > 0)
+        for ti, t in enumerate(SIG):
+            fw = O.find_valid_motif_idx(s, motifs[t][str(k)], k)
+            assert kh["pos"][(kh["flags"] >> ti) & 1 == 1].tolist() == fw
+            rv = O.find_valid_motif_idx(O.revcomp(s), motifs[t][str(k)], k)
+            got = sorted((len(s) - kh["pos"][(kh["flags"] >> (4 + ti)) & 1 == 1] - k).tolist())
+            assert got == rv
+
+
+def _strs(contigs):
+    return {"c%d" % i: c.tobytes().decode() for i, c in enumerate(contigs)}
+
+
+def test_scan_synthetic_ragged(engine, motifs):
+    """many contigs of awkward lengths: empty, shorter than a k-mer, around chunk / tile boundaries"""
+    lengths = [0, 1, 6, 7, 8, 9, 39, 40, 41, 63, 64, 65, 127, 128, 129, 1000, 16383, 16384, 16385,
+               16384 * 2 + 17, 50_000, 3, 70_001]
+    contigs, _ = synth.assembly(11, lengths, motifs, plant_every=300, n_runs=1, soft_mask=0.3)
+    check(engine, _strs(contigs), motifs)
+
+
+def test_scan_edge_planted(engine, motifs):
+    """RSS units flush with contig starts / ends and straddling chunk and tile boundaries"""
+    rng = np.random.default_rng(5)
+    sets = {x: (sorted(motifs[x]["7"]), sorted(motifs[x]["9"])) for x in SIG}
+    contigs = []
+    for L in (64 * 256 * 2 + 100, 5000, 1000, 200):
+        buf = synth.background(rng, L)
+        spots = [0, 1, L, 64 * 256, 64 * 256 * 2, 64, 128, 4096] + list(rng.integers(0, L, 20))
+        for sp in spots:
+            t = SIG[rng.integers(4)]
+            u = np.frombuffer(synth.rss_unit(rng, motifs, t, sets).encode(), np.uint8)
+            if rng.integers(2):
+                u = synth.revcomp_bytes(u)
+            for p in (sp - len(u), sp - len(u) // 2, sp - 3, sp):
+                p = int(min(max(p, 0), L - len(u)))
+                if rng.random() < 0.5:
+                    buf[p:p + len(u)] = u
+        contigs.append(buf)
+    check(engine, _strs(contigs), motifs)
+
+
+def test_scan_invalid_letters(engine, motifs):
+    """N / IUPAC letters inside heptamers, nonamers and spacers; lower-case everywhere"""
+    rng = np.random.default_rng(9)
+    contigs, _ = synth.assembly(9, [40_000], motifs, plant_every=120)
+    buf = contigs[0]
+    for p in rng.integers(0, len(buf), 600):
+        buf[p] = ord("NRYKMnry"[rng.integers(8)])
+    buf[1000:9000] |= 0x20
+    check(engine, _strs([buf]), motifs)
+
+
+def test_scan_reverse_complement_symmetry(engine, motifs):
+    """size-independent property: scanning RC(contig) mirrors every hit onto the other strand"""
+    contigs, _ = synth.assembly(21, [3_000_000], motifs, plant_every=5000, n_runs=2, soft_mask=0.2)
+    a = contigs[0]
+    L = len(a)
+    engine.load_contigs([a.tobytes()])
+    h1 = engine.scan_rss(O.SPACER_LENGTH)
+    engine.load_contigs([synth.revcomp_bytes(a).tobytes()])
+    h2 = engine.scan_rss(O.SPACER_LENGTH)
+    s1 = {(int(r["sig_type"]), int(r["strand"]), int(r["hept"]), int(r["nona"])) for r in h1}
+    s2 = {(int(r["sig_type"]), 1 - int(r["strand"]), L - int(r["hept"]) - 7, L - int(r["nona"]) - 9) for r in h2}
+    assert len(s1) == len(h1) and len(s1) > 500
+    assert s1 == s2
+
+
+def test_scan_sharding_invariance(engine, motifs):
+    """hits do not depend on which contigs share a load (what multi-GPU sharding relies on)"""
+    lengths = [200_000, 1_000, 64_000, 333_333, 5_000, 90_001]
+    contigs, _ = synth.assembly(31, lengths, motifs, plant_every=2000, n_runs=1)
+    bs = [c.tobytes() for c in contigs]
+    engine.load_contigs(bs)
+    whole = engine.scan_rss(O.SPACER_LENGTH)
+    parts = []
+    for idx in ([0, 2, 4], [1, 3, 5]):
+        engine.load_contigs([bs[i] for i in idx])
+        h = engine.scan_rss(O.SPACER_LENGTH).copy()
+        h["contig"] = np.asarray(idx, np.uint32)[h["contig"]]
+        parts.append(h)
+    merged = np.concatenate(parts)
+    key = lambda h: sorted(map(tuple, h[["contig", "sig_type", "strand", "hept", "nona", "spacer"]].tolist()))
+    assert key(merged) == key(whole)

@@ -1,0 +1,91 @@
+"""The algorithms the CUDA kernels implement, modelled in Python, against the oracle (CPU only)."""
+import numpy as np
+import pytest
+
+from oracle import igd_oracle as O
+import kernel_model as KM
+
+SC = dict(match=2, mismatch=0, target_internal_open=-2, target_internal_extend=-1,
+          target_end_open=-2, target_end_extend=-1, query_internal_open=-2, query_internal_extend=-1,
+          query_end_open=0, query_end_extend=0)
+
+
+def _plant(rng, motifs, L, n_plant):
+    s = list(rng.choice(list("ACGT"), L, p=[0.295, 0.205, 0.205, 0.295]))
+    for _ in range(n_plant):
+        t = KM.SIG[rng.integers(4)]
+        h = sorted(motifs[t]["7"])[rng.integers(len(motifs[t]["7"]))]
+        n = sorted(motifs[t]["9"])[rng.integers(len(motifs[t]["9"]))]
+        sp = O.SPACER_LENGTH[t] + int(rng.integers(-1, 2))
+        spacer = "".join(rng.choice(list("ACGT"), sp))
+        unit = h + spacer + n if KM.HEPT_FIRST[t] else n + spacer + h
+        if rng.integers(2):
+            unit = O.revcomp(unit)
+        p = int(rng.integers(0, L - len(unit)))
+        s[p:p + len(unit)] = list(unit)
+    s = "".join(s)
+    # soft-masking, an N run and a stray IUPAC code
+    a = int(rng.integers(0, L - 50))
+    s = s[:a] + s[a:a + 40].lower() + s[a + 40:]
+    b = int(rng.integers(0, L - 30))
+    s = s[:b] + "N" * 17 + s[b + 17:]
+    c = int(rng.integers(0, L))
+    return s[:c] + "R" + s[c + 1:]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_scan_model_equals_oracle(motifs, seed):
+    rng = np.random.default_rng(seed)
+    seq = _plant(rng, motifs, 3000, 40)
+    model = KM.scan_model("".join(ch if ch.upper() in "ACGT" else "#" for ch in seq), motifs, O.SPACER_LENGTH)
+    for t in KM.SIG:
+        for sd in "+-":
+            want = O.get_contigwise_rss(t, sd, {"c": seq}, motifs, order="canonical")["c"]
+            assert len(set(want)) == len(want)
+            assert set(want) == model[(t, sd)], (t, sd)
+
+
+def _pairs(rng, n):
+    out = []
+    for _ in range(n):
+        nb = int(rng.integers(1, 40))
+        g = "".join(rng.choice(list("ACGT"), nb))
+        kind = rng.integers(3)
+        if kind == 0:
+            a = "".join(rng.choice(list("ACGT"), int(rng.integers(1, 60))))
+        else:
+            mut = list(g)
+            for _ in range(int(rng.integers(0, 6))):
+                p = int(rng.integers(0, len(mut) + 1))
+                op = rng.integers(3)
+                if op == 0 and mut:
+                    mut[min(p, len(mut) - 1)] = "ACGT"[rng.integers(4)]
+                elif op == 1:
+                    mut.insert(p, "ACGT"[rng.integers(4)])
+                elif mut:
+                    del mut[min(p, len(mut) - 1)]
+            a = "".join(rng.choice(list("ACGT"), int(rng.integers(0, 15)))) + "".join(mut) + \
+                "".join(rng.choice(list("ACGT"), int(rng.integers(0, 15))))
+        if kind == 2:
+            a = "".join(ch.lower() if rng.random() < 0.3 else ch for ch in a)
+        if not a:
+            a = "A"
+        out.append((a, g))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_gotoh_model_equals_oracle(seed):
+    rng = np.random.default_rng(100 + seed)
+    pairs = _pairs(rng, 120)
+    st = O.align_stats([p[0] for p in pairs], [p[1] for p in pairs], range(len(pairs)), range(len(pairs)))
+    for k, (a, g) in enumerate(pairs):
+        score, m, lead, intx = KM.gotoh_model(a, g, SC, 0)
+        _, m2, trail, intx2 = KM.gotoh_model(a, g, SC, 1)
+        s = st[k]
+        assert score == int(s["score"]), (a, g)
+        assert (m, m2) == (int(s["matches"]),) * 2, (a, g)
+        assert lead == int(s["start"]) == int(s["lead"]), (a, g)
+        assert lead + len(g) + intx == int(s["end"]), (a, g)
+        assert intx == intx2
+        assert len(a) - trail == int(s["ient"]), (a, g)
