@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the RSS scan + V/D/J scoring hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mbases M]
+
+Workload (BASELINE.json configs[1]): one synthetic 100 Mb contig per GPU, seed 2 (+rank): i.i.d.
+background, 300 V + 30 D + 12 J mutated genes with their RSSs in 3 clusters, 20 N runs, 45 %
+soft-masked; scored against combined_reference_genes IGHV (490) / IGHJ (13).
+One step = one pass of the hot path: RSS scan of both strands for the 4 signal types, D pairing,
+fragment extraction, scoring of every V / J candidate against every gene in both orientations,
+argmax + threshold + the winners' detail pass -> the rows of genes_{V,D,J}.tsv.
+  value : Gb scanned per second over the whole step, contigs resident in HBM (packed)
+  e2e   : the same through the public API from HOST buffers (pinned ASCII contig H2D + pack
+          inside the timed region, hits and alignment results read back)
+The reference arm (--impl reference) times the CPU oracle port of the same step on a bounded,
+proportional sample (the reference itself needs BioPython, which is not installable here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+DATA = os.path.join(ROOT, "tests", "golden", "datafiles")
+METRIC, UNIT = "rss_scan_and_vdj_scoring_throughput", "Gb_scanned_per_s"
+
+
+def load_data():
+    from igdetective_b200 import datafiles
+    motifs = datafiles.load_motifs(DATA)
+    canon = {g: datafiles.load_canonical_genes("IGH", g, "combined_reference_genes", DATA) for g in ("V", "J")}
+    return motifs, canon
+
+
+def make_workload(seed, n_bases, motifs, canon):
+    import synth
+    rng = np.random.default_rng(seed)
+    contigs, truth = synth.assembly(seed, [n_bases], motifs, canon["V"], canon["J"], n_runs=20, soft_mask=0.45,
+                                    clusters=[(0, 100, 10, 4)] * 3)
+    return contigs[0], truth
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return None
+        reasons = []
+        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
+            if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "samples": len(sm),
+                "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def gpu_arm(a):
+    import torch
+    import torch.distributed as dist
+    from igdetective_b200 import igdetective
+    from igdetective_b200.engine import Engine
+    from igdetective_b200.rss import SPACER_LENGTH
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    motifs, canon = load_data()
+    n_bases = int(a.mbases * 1e6)
+    contig, truth = make_workload(2 + rank, n_bases, motifs, canon)
+    # host side of the public API: the contig as the reference holds it (a str) and as pinned bytes
+    pinned = torch.empty(n_bases, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = contig
+    seqs = {"synthetic_%d" % rank: contig.tobytes().decode("latin-1")}
+    off = np.array([0, n_bases], np.uint64)
+    eng = Engine(local, motifs)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        eng.sync()
+        if world > 1:
+            dist.barrier()
+
+    stats = {}
+
+    def step(e2e):
+        if e2e:
+            eng.load_contigs((pinned.data_ptr(), off), list(seqs))
+        info, rows = igdetective.detect(eng, seqs, canon, order="canonical", load=False)
+        stats["rows"] = {g: len(r) for g, r in rows.items()}
+        stats["rss"] = {st: sum(len(v) for sd in info[st] for v in info[st][sd].values()) for st in info}
+        return rows
+
+    def timed(e2e, k):
+        """K steps, each bracketed by barrier + synchronize; L2 flushed between steps outside the clock."""
+        total, scan_ms, align_ms, cells, launches = 0.0, [], 0.0, 0, 0
+        h0, d0 = eng.h2d_bytes, eng.d2h_bytes
+        for _ in range(k):
+            flush.zero_()
+            barrier()
+            l0 = eng.timing()["total_launches"]
+            t0 = time.perf_counter()
+            step(e2e)
+            eng.sync()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            total += dt
+            launches += eng.timing()["total_launches"] - l0
+        return total, (eng.h2d_bytes - h0) / k, (eng.d2h_bytes - d0) / k, launches / k
+
+    eng.load_contigs((pinned.data_ptr(), off), list(seqs))
+    for _ in range(a.warmup):
+        step(False)
+    clocks = Clocks(local) if rank == 0 else None
+    t_dev, _, _, launches = timed(False, a.steps)
+    # per-kernel device times of the last resident step: CUDA events on the library's stream
+    eng.load_contigs((pinned.data_ptr(), off), list(seqs))
+    flush.zero_(); barrier()
+    eng.scan_rss_count(SPACER_LENGTH)
+    tm = eng.timing()
+    scan_ms = tm["scan_ms"]
+    scan_samples = []
+    for _ in range(max(3, a.steps)):
+        flush.zero_(); barrier()
+        eng.scan_rss_count(SPACER_LENGTH)
+        scan_samples.append(eng.timing()["scan_ms"])
+    scan_ms = float(np.mean(scan_samples))
+    kstat = kernel_stats(eng, seqs, canon, igdetective)
+    t_e2e, h2d, d2h, _ = timed(True, a.steps)
+    clk = clocks.stop() if clocks else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    total_bases = n_bases * world
+    alg_bytes = (n_bases + 3) // 4
+    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
+    sm_hz = (clk or {}).get("sm_mhz", 1965.0) * 1e6
+    int_peak = 148 * 64 * sm_hz / 1e12            # ALU-pipe lane-ops/s (T), 64 lanes/clk/SM
+    line = {
+        "metric": METRIC, "value": total_bases / (t_dev / a.steps) / 1e9, "unit": UNIT,
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic %.0f Mb single contig per GPU, planted RSS + mutated V/D/J, "
+                               "both strands, 4 signal types, scored vs combined_reference_genes IGHV(490)/IGHJ(13)"
+                               % a.mbases,
+                   "order": "canonical", "l2": "flushed (256 MiB write) between steps, outside the timed regions",
+                   "rows": stats.get("rows"), "rss": stats.get("rss")},
+        "e2e": {"value": total_bases / (t_e2e / a.steps) / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / a.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "scan": {"kernel_ms": scan_ms, "gb_per_s_both_strands": n_bases / (scan_ms * 1e-3) / 1e9,
+                 "hits": kstat["hits"]},
+        "align": {"kernel_ms": kstat["align_ms"], "gcups": kstat["gcups"], "pairs": kstat["pairs"],
+                  "cells": kstat["cells"]},
+        "kernel_share_of_step": {"rss_scan": scan_ms / (1e3 * t_dev / a.steps),
+                                 "gotoh": kstat["align_ms"] / (1e3 * t_dev / a.steps)},
+        "roofline": {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
+        "roofline_align": {"kernel": "gotoh_kernel", "bound": "int32 ALU pipe", "gcups": kstat["gcups"],
+                           "alu_ops_per_cell": kstat["ops_per_cell"],
+                           "achieved": kstat["gcups"] * kstat["ops_per_cell"] / 1e3, "peak": int_peak,
+                           "unit": "T lane-ops/s", "frac": kstat["gcups"] * kstat["ops_per_cell"] / 1e3 / int_peak},
+    }
+    if not a.no_cpu:
+        line["cpu_baseline"] = cpu_sample(contig, seqs, motifs, canon, kstat["fragments"], a)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+ALU_OPS_PER_CELL = 23.0     # SASS count of the <32,11> inner loop, see DESIGN.md
+
+
+def kernel_stats(eng, seqs, canon, igdetective):
+    """One resident step with the library's own CUDA-event timings pulled after each call."""
+    from igdetective_b200.rss import (D, DL, DR, FWD, J, REV, SIGNAL_TYPES, V, RssScan, combine_D_RSS,
+                                      get_s_fragment_from_RSS)
+    from igdetective_b200.scoring import align_fragment_to_genes
+    scan = RssScan(eng, seqs, order="canonical", load=False)
+    info = {st: {sd: scan.contigwise(st, sd) for sd in (FWD, REV)} for st in SIGNAL_TYPES}
+    frags = {g: {sd: get_s_fragment_from_RSS(g, sd, info, seqs) for sd in (FWD, REV)} for g in (V, J)}
+    ms, cells, pairs, flat_all = 0.0, 0, 0, {}
+    for g in (V, J):
+        flat = [f for sd in (FWD, REV) for c in frags[g][sd] for f in frags[g][sd][c]]
+        flat_all[g] = flat
+        align_fragment_to_genes(flat, list(canon[g].values()), engine=eng)
+        t = eng.timing()
+        ms += t["align_ms"]; cells += t["align_cells"]; pairs += 2 * len(flat) * len(canon[g])
+    return {"hits": int(len(scan.hits)), "align_ms": ms, "cells": int(cells), "pairs": int(pairs),
+            "gcups": cells / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "ops_per_cell": ALU_OPS_PER_CELL,
+            "fragments": flat_all}
+
+
+# --------------------------------------------------------------------------------------- CPU arms
+def _scan_piece(args):
+    """The reference's scan loops, literally (py/IGDetective.py:138-177), on one piece of the contig."""
+    from oracle import igd_oracle as O
+    piece, motifs = args
+    n = 0
+    for st in O.SIGNAL_TYPES:
+        for sd in "+-":
+            r = O.get_contigwise_rss(st, sd, {"p": piece}, motifs, order="reference", scan=O.find_valid_motif_idx_py)
+            n += len(r["p"])
+    return n
+
+
+def cpu_step(sample_seq, motifs, frag_sample, canon, cores):
+    """Oracle port of one step on a sample: pure-Python scan loops over `sample_seq` (split over
+    `cores` processes) + scoring of `frag_sample` = {gene type: fragments} against all genes."""
+    import multiprocessing as mp
+    from oracle import igd_oracle as O
+    t0 = time.perf_counter()
+    n = max(1, cores)
+    sz = (len(sample_seq) + n - 1) // n
+    pieces = [sample_seq[max(0, i * sz - 40):(i + 1) * sz] for i in range(n)]
+    with mp.get_context("fork").Pool(n) as pool:
+        pool.map(_scan_piece, [(p, motifs) for p in pieces])
+    t_scan = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cells = 0
+    for g, frs in frag_sample.items():
+        if frs:
+            glist = list(canon[g].values())
+            O.align_fragment_to_genes(frs, glist, threads=cores)
+            cells += 2 * sum(max(len(f), 1) for f in frs) * sum(len(x) for x in glist)
+    t_score = time.perf_counter() - t0
+    return t_scan, t_score, cells
+
+
+def cpu_sample(contig, seqs, motifs, canon, fragments, a, frac=None):
+    """Bounded proportional sample of the workload: `frac` of the contig and of the candidates."""
+    cores = len(os.sched_getaffinity(0))
+    n = len(contig)
+    frac = frac or min(1.0, 2.0e6 / n)
+    s_len = int(n * frac)
+    sample_seq = next(iter(seqs.values()))[:s_len]
+    fs = {g: fr[:max(1, int(round(len(fr) * frac)))] for g, fr in fragments.items()}
+    t_scan, t_score, cells = cpu_step(sample_seq, motifs, fs, canon, cores)
+    return {"value": s_len / (t_scan + t_score) / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%.2f%% of the step: pure-Python reference scan loops over the first %d bases split over "
+                      "%d processes (%.2fs) + C oracle aligner, %d threads, on %s of the V/J candidates x all genes "
+                      "x 2 orientations (%.2fs, %.1f MCUPS)" % (100 * frac, s_len, cores, t_scan, cores,
+                      {g: len(f) for g, f in fs.items()}, t_score, cells / max(t_score, 1e-9) / 1e6),
+            "scan_mb_per_s": s_len / t_scan / 1e6, "align_mcups": cells / max(t_score, 1e-9) / 1e6}
+
+
+def reference_arm(a):
+    """CPU-only: the oracle port of the step on a bounded proportional sample, all host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from oracle import igd_oracle as O
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    motifs, canon = load_data()
+    n_bases = int(a.mbases * 1e6)
+    contig, truth = make_workload(2, n_bases, motifs, canon)
+    seqs = {"synthetic_0": contig.tobytes().decode("latin-1")}
+    frac = min(1.0, 2.0e6 / n_bases)
+    # candidates of the whole workload (untimed set-up; vectorised oracle scan), then a proportional share
+    rss = {g: {sd: O.get_contigwise_rss(g, sd, seqs, motifs, order="canonical") for sd in "+-"} for g in ("V", "J")}
+    fragments = {g: [f for sd in "+-" for c in seqs for f in O.s_fragments(g, sd, rss, seqs)[c]] for g in ("V", "J")}
+    cores = len(os.sched_getaffinity(0))
+    res = None
+    t_all = 0.0
+    for i in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        res = cpu_sample(contig, seqs, motifs, canon, fragments, a, frac)
+        if i >= a.warmup:
+            t_all += time.perf_counter() - t0
+    s_len = int(n_bases * frac)
+    val = s_len * a.steps / t_all / 1e9
+    res["value"] = val
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", a.gpus)),
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: synthetic %.0f Mb single contig, bounded proportional sample (%.2f%% "
+                               "of the contig and of the V/J candidates per step)" % (a.mbases, 100 * frac)},
+        "cpu_baseline": res,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--mbases", type=float, default=100.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)

@@ -142,6 +142,16 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
             if (f) any[ki >> 5] |= 1u << (ki & 31);
         }
     }
+    // does the bit-sliced consensus prefilter of rss_scan.cu cover every heptamer of these tables?
+    bool covered = true;
+    for (unsigned nat = 0; nat < 16384u && covered; ++nat) {
+        if (!flags7[nat] && !flags7[revcomp_index(nat, 7)]) continue;
+        static const int want[7] = {1, 0, 1, -1, 2, 3, 2};           // C A C . G T G
+        int m = 0;
+        for (int i = 0; i < 7; ++i) m += (int)((nat >> (2 * (6 - i))) & 3u) == want[i];
+        covered = m >= 4;
+    }
+    h->consensus_prefilter = covered;
     IGD_CUDA(cudaMemcpyAsync(h->d_lut7, l7.data(), 16384, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_lut9, l9.data(), 262144, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_any7, a7.data(), 2048, cudaMemcpyHostToDevice, h->stream));

@@ -18,7 +18,7 @@
 // least one all-invalid pad chunk, so no k-mer window or RSS can straddle two contigs; the array
 // is padded with invalid chunks to a whole number of tiles plus one trailing halo chunk.
 constexpr int IGD_CHUNK_BASES = 64;
-constexpr int IGD_TILE_CHUNKS = 256;                  // chunks per scan tile = threads per CTA
+constexpr int IGD_TILE_CHUNKS = 512;                  // chunks per scan tile = threads per CTA
 constexpr int IGD_STAGE_CHUNKS = IGD_TILE_CHUNKS + 2; // one halo chunk each side (RSS span <= 40 bases)
 
 struct igd_handle {
@@ -33,6 +33,7 @@ struct igd_handle {
     uint32_t *d_any9 = nullptr;   // 262144-bit bitmap: lut9 != 0
     uint32_t *d_any7 = nullptr;   // 16384-bit bitmap: lut7 != 0
     bool motifs_set = false;
+    bool consensus_prefilter = false;   // every heptamer flag entry matches CAC.GTG in >= 4 of 6 positions
 
     // contigs
     uint4 *d_planes = nullptr;

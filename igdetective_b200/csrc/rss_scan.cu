@@ -14,19 +14,27 @@
 //   strand -, nonamer first              :  nonamer n=q+7+s' selects q iff (q-1 | q+1,q+2) miss
 // with s' tried in the order s, s-1, s+1 (:162-168).
 //
-// Data movement: a persistent CTA walks tiles of 256 chunks (16 Kbases, 4 KB of planes); each
+// Data movement: a persistent CTA walks tiles of 512 chunks (32 Kbases, 8 KB of planes); each
 // tile plus one halo chunk per side arrives in shared memory by one TMA bulk copy
 // (cp.async.bulk + mbarrier, 3 stages in flight), so every base is read from HBM once
-// (0.25 B/base).  Phase A tests all 64 heptamer windows of a thread's chunk; survivors
-// (~1 % of positions) go to a shared-memory queue and phase B evaluates them with all lanes busy.
+// (0.25 B/base).
+// Phase A, one 64-base chunk per thread, is bit-parallel on the planes: every heptamer of the
+// shipped motif file (both strands) agrees with the consensus CAC.GTG in at least 4 of its 6
+// fixed positions, so a bit-sliced population count of the six letter-match planes, thresholded
+// at 4, passes every possible heptamer hit and only ~3.8 % of random positions (igd_set_motifs
+// verifies that property for the tables it is given; tables that break it use the exhaustive
+// variant of the same kernel).  Survivors are looked up in the exact 7-mer flag table in shared
+// memory; real heptamer hits (~1 % of positions) go to a shared-memory queue.
+// Phase B pairs the queued heptamers with all lanes busy.
 #include "common.cuh"
 
 namespace {
 
 constexpr int NSTAGE = 3;
-constexpr int STAGE_BYTES = IGD_STAGE_CHUNKS * 16;          // 4128
-constexpr int STAGE_STRIDE = 4224;                          // 128-byte aligned
+constexpr int STAGE_BYTES = IGD_STAGE_CHUNKS * 16;          // 8224
+constexpr int STAGE_STRIDE = 8320;                          // 128-byte aligned
 constexpr int QCAP = 2048;
+constexpr int INVSUM_WORDS = IGD_TILE_CHUNKS / 32 + 1;
 
 struct ScanParams {
     const uint4 *planes;
@@ -65,6 +73,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
     return ok != 0;
 }
 
+struct TileCtx {
+    const uint32_t *sw;            // stage words: record r = {lo0, lo1, hi0, hi1} at sw[4r..4r+3]
+    const uint8_t *s_lut7;
+    const uint32_t *s_invsum;      // validity summary bits of the stage's chunks
+    unsigned long long g0;         // global base index of stage position 0
+};
+
 // 32 consecutive positions of one bit-plane starting at stage position p (plane = 0 lo, 2 hi)
 __device__ __forceinline__ uint32_t win32(const uint32_t *sw, int p, int plane)
 {
@@ -74,31 +89,21 @@ __device__ __forceinline__ uint32_t win32(const uint32_t *sw, int p, int plane)
     return __funnelshift_r(a, b, p & 31);
 }
 
-// true iff no base of [g, g+k) is marked invalid (g = global base index in the chunk array)
-__device__ __forceinline__ bool window_valid(const ScanParams &P, unsigned long long g, int k)
+// true iff no base of stage window [x, x+k) is marked invalid
+__device__ __forceinline__ bool window_valid(const ScanParams &P, const TileCtx &T, int x, int k)
 {
-    const unsigned long long c0 = g >> 6, c1 = (g + k - 1) >> 6;
-    const int b0 = (int)(g & 63);
-    if ((__ldg(&P.invsum[c0 >> 5]) >> (c0 & 31)) & 1u) {
-        const unsigned long long m = __ldg(&P.inv[c0]);
+    const int c0 = x >> 6, c1 = (x + k - 1) >> 6, b0 = x & 63;
+    if ((T.s_invsum[c0 >> 5] >> (c0 & 31)) & 1u) {
+        const unsigned long long m = __ldg(&P.inv[(T.g0 >> 6) + c0]);
         const int n0 = (b0 + k > 64) ? 64 - b0 : k;
-        const unsigned long long mask = ((n0 == 64) ? ~0ull : ((1ull << n0) - 1ull)) << b0;
-        if (m & mask) return false;
+        if (m & (((1ull << n0) - 1ull) << b0)) return false;
     }
-    if (c1 != c0 && ((__ldg(&P.invsum[c1 >> 5]) >> (c1 & 31)) & 1u)) {
-        const unsigned long long m = __ldg(&P.inv[c1]);
-        const int n1 = b0 + k - 64;
-        if (m & ((1ull << n1) - 1ull)) return false;
+    if (c1 != c0 && ((T.s_invsum[c1 >> 5] >> (c1 & 31)) & 1u)) {
+        const unsigned long long m = __ldg(&P.inv[(T.g0 >> 6) + c1]);
+        if (m & ((1ull << (b0 + k - 64)) - 1ull)) return false;
     }
     return true;
 }
-
-struct TileCtx {
-    const uint32_t *sw;            // stage words
-    const uint8_t *s_lut7;
-    const uint32_t *s_any9;
-    unsigned long long g0;         // global base index of stage position 0
-};
 
 // heptamer flags at stage position x (0 if the window holds an invalid base)
 __device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const TileCtx &T, int x)
@@ -106,17 +111,22 @@ __device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const TileCt
     const unsigned lo = win32(T.sw, x, 0) & 127u, hi = win32(T.sw, x, 2) & 127u;
     const unsigned f = T.s_lut7[(hi << 7) | lo];
     if (!f) return 0;
-    return window_valid(P, T.g0 + x, 7) ? f : 0;
+    return window_valid(P, T, x, 7) ? f : 0;
 }
 
-// nonamer at stage position x carries flag `bit`?
-__device__ __forceinline__ bool nona_has(const ScanParams &P, const TileCtx &T, int x, unsigned bit)
+// flags of the three nonamers starting at x, x+1, x+2 (the spacers s+1, s, s-1 or s-1, s, s+1 of
+// one heptamer), masked by `bit`, validity included: bit i of the result = nonamer x+i qualifies
+__device__ __forceinline__ unsigned nona3(const ScanParams &P, const TileCtx &T, int x, unsigned bit)
 {
-    const unsigned lo = win32(T.sw, x, 0) & 511u, hi = win32(T.sw, x, 2) & 511u;
-    const unsigned idx = (hi << 9) | lo;
-    if (!((T.s_any9[idx >> 5] >> (idx & 31)) & 1u)) return false;
-    if (!(__ldg(&P.lut9[idx]) & bit)) return false;
-    return window_valid(P, T.g0 + x, 9);
+    const unsigned lo = win32(T.sw, x, 0), hi = win32(T.sw, x, 2);
+    unsigned r = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const unsigned idx = (((hi >> i) & 511u) << 9) | ((lo >> i) & 511u);
+        if ((__ldg(&P.any9[idx >> 5]) >> (idx & 31)) & 1u)
+            if ((__ldg(&P.lut9[idx]) & bit) && window_valid(P, T, x + i, 9)) r |= 1u << i;
+    }
+    return r;
 }
 
 __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq, int t, int strand, int d)
@@ -126,32 +136,25 @@ __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq,
 }
 
 // all RSSs whose heptamer starts at stage position q; f = LUT flags of that heptamer
-__device__ void eval_heptamer(const ScanParams &P, const TileCtx &T, int q, unsigned f)
+__device__ __noinline__ void eval_heptamer(const ScanParams &P, const TileCtx &T, int q, unsigned f)
 {
-    if (!window_valid(P, T.g0 + q, 7)) return;
+    if (!window_valid(P, T, q, 7)) return;
     const unsigned long long gq = T.g0 + q;
-    // neighbouring heptamer flags, fetched lazily (only nonamer-first types with s' != s need them)
     unsigned hm2 = 0, hm1 = 0, hp1 = 0, hp2 = 0; bool have_nb = false;
-#pragma unroll
+#pragma unroll 1
     for (int t = 0; t < 4; ++t) {
         const unsigned bF = 1u << t, bR = 16u << t;
         if (!(f & (bF | bR))) continue;
         const int s = P.sp[t];
         const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
         if (hept_first) {
-            if (f & bF) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int s1 = s + (d == 0 ? 0 : (d == 1 ? -1 : 1));
-                    if (nona_has(P, T, q + 7 + s1, bF)) { emit(P, gq, t, 0, d); break; }
-                }
+            if (f & bF) {              // nonamers at q+7+{s-1, s, s+1} = bits 0,1,2; priority s, s-1, s+1
+                const unsigned n = nona3(P, T, q + 7 + s - 1, bF);
+                if (n) emit(P, gq, t, 0, (n & 2u) ? 0 : ((n & 1u) ? 1 : 2));
             }
-            if (f & bR) {
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int s1 = s + (d == 0 ? 0 : (d == 1 ? -1 : 1));
-                    if (nona_has(P, T, q - s1 - 9, bR)) { emit(P, gq, t, 1, d); break; }
-                }
+            if (f & bR) {              // nonamers at q-9-{s+1, s, s-1} = bits 0,1,2
+                const unsigned n = nona3(P, T, q - 9 - s - 1, bR);
+                if (n) emit(P, gq, t, 1, (n & 2u) ? 0 : ((n & 4u) ? 1 : 2));
             }
         } else {
             if (!have_nb) {
@@ -159,31 +162,53 @@ __device__ void eval_heptamer(const ScanParams &P, const TileCtx &T, int q, unsi
                 hp1 = hept_flags(P, T, q + 1); hp2 = hept_flags(P, T, q + 2);
                 have_nb = true;
             }
-            if (f & bF) {
-                // nonamer p = q-9-s' looks for its heptamer at p+9+s, then +s-1, then +s+1
-                if (nona_has(P, T, q - 9 - s, bF)) emit(P, gq, t, 0, 0);
-                if (!(hp1 & bF) && nona_has(P, T, q - 9 - (s - 1), bF)) emit(P, gq, t, 0, 1);
-                if (!(hm1 & bF) && !(hm2 & bF) && nona_has(P, T, q - 9 - (s + 1), bF)) emit(P, gq, t, 0, 2);
+            if (f & bF) {              // nonamer p = q-9-s' ranks its heptamers p+9+s, +s-1, +s+1
+                const unsigned n = nona3(P, T, q - 9 - s - 1, bF);     // bits: s+1, s, s-1
+                if (n & 2u) emit(P, gq, t, 0, 0);
+                if ((n & 4u) && !(hp1 & bF)) emit(P, gq, t, 0, 1);
+                if ((n & 1u) && !(hm1 & bF) && !(hm2 & bF)) emit(P, gq, t, 0, 2);
             }
-            if (f & bR) {
-                // reverse strand: nonamer n = q+7+s'; its ranked heptamer candidates are n-s-7, +1, -1
-                if (nona_has(P, T, q + 7 + s, bR)) emit(P, gq, t, 1, 0);
-                if (!(hm1 & bR) && nona_has(P, T, q + 7 + (s - 1), bR)) emit(P, gq, t, 1, 1);
-                if (!(hp1 & bR) && !(hp2 & bR) && nona_has(P, T, q + 7 + (s + 1), bR)) emit(P, gq, t, 1, 2);
+            if (f & bR) {              // reverse strand: nonamer n = q+7+s' ranks heptamers n-s-7, +1, -1
+                const unsigned n = nona3(P, T, q + 7 + s - 1, bR);     // bits: s-1, s, s+1
+                if (n & 2u) emit(P, gq, t, 1, 0);
+                if ((n & 1u) && !(hm1 & bR)) emit(P, gq, t, 1, 1);
+                if ((n & 4u) && !(hp1 & bR) && !(hp2 & bR)) emit(P, gq, t, 1, 2);
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(IGD_TILE_CHUNKS)
+// positions of word (w, next) whose 7-mer matches CAC.GTG in at least 4 of the 6 fixed positions.
+// A/C/G/T = letter indicator planes of the word, nA.. = of the following word.
+struct Ind { uint32_t a, c, g, t; };
+__device__ __forceinline__ Ind indicators(uint32_t lo, uint32_t hi)
+{
+    Ind r; r.a = ~(lo | hi); r.c = lo & ~hi; r.g = hi & ~lo; r.t = lo & hi; return r;
+}
+__device__ __forceinline__ uint32_t consensus_ge4(const Ind &w, const Ind &n)
+{
+    const uint32_t m0 = w.c;
+    const uint32_t m1 = __funnelshift_r(w.a, n.a, 1);
+    const uint32_t m2 = __funnelshift_r(w.c, n.c, 2);
+    const uint32_t m4 = __funnelshift_r(w.g, n.g, 4);
+    const uint32_t m5 = __funnelshift_r(w.t, n.t, 5);
+    const uint32_t m6 = __funnelshift_r(w.g, n.g, 6);
+    const uint32_t s1 = m0 ^ m1 ^ m2, c1 = (m0 & m1) | (m2 & (m0 | m1));
+    const uint32_t s2 = m4 ^ m5 ^ m6, c2 = (m4 & m5) | (m6 & (m4 | m5));
+    const uint32_t c3 = s1 & s2;
+    return (c1 & c2) | (c3 & (c1 | c2));          // ones + 2*twos >= 4  <=>  at least two carries
+}
+
+template <bool PREFILTER>
+__global__ void __launch_bounds__(IGD_TILE_CHUNKS, 2)
 rss_scan_kernel(const ScanParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_stage = smem;                                           // NSTAGE * STAGE_STRIDE
     uint8_t *s_lut7 = smem + NSTAGE * STAGE_STRIDE;                          // 16384
-    uint32_t *s_any9 = (uint32_t *)(s_lut7 + 16384);                         // 32768
-    uint32_t *s_queue = s_any9 + 8192;                                       // QCAP
-    uint64_t *s_bar = (uint64_t *)(s_queue + QCAP);                          // NSTAGE
+    uint32_t *s_queue = (uint32_t *)(s_lut7 + 16384);                        // QCAP
+    uint32_t *s_invsum = s_queue + QCAP;                                     // INVSUM_WORDS (+pad)
+    uint64_t *s_bar = (uint64_t *)(s_invsum + 32);                           // NSTAGE
     unsigned *s_qn = (unsigned *)(s_bar + NSTAGE);
 
     const int tid = threadIdx.x;
@@ -196,7 +221,6 @@ rss_scan_kernel(const ScanParams P)
     __syncthreads();
 
     const unsigned long long tile0 = blockIdx.x, stride = gridDim.x;
-    // prologue: tiles of iterations 0 .. NSTAGE-2
     if (tid == 0) {
         for (int i = 0; i < NSTAGE - 1; ++i) {
             const unsigned long long tile = tile0 + (unsigned long long)i * stride;
@@ -206,12 +230,9 @@ rss_scan_kernel(const ScanParams P)
             }
         }
     }
-    // motif tables -> shared memory (L2-resident after the first CTA)
-    {
+    {   // exact 7-mer flag table -> shared memory (L2-resident after the first CTA)
         const uint4 *src7 = (const uint4 *)P.lut7; uint4 *dst7 = (uint4 *)s_lut7;
         for (int i = tid; i < 16384 / 16; i += IGD_TILE_CHUNKS) dst7[i] = __ldg(&src7[i]);
-        const uint4 *src9 = (const uint4 *)P.any9; uint4 *dst9 = (uint4 *)s_any9;
-        for (int i = tid; i < 32768 / 16; i += IGD_TILE_CHUNKS) dst9[i] = __ldg(&src9[i]);
     }
     __syncthreads();
 
@@ -219,8 +240,7 @@ rss_scan_kernel(const ScanParams P)
     for (unsigned long long tile = tile0; tile < P.n_tiles; tile += stride, ++it) {
         const int stage = it % NSTAGE;
         const unsigned parity = (it / NSTAGE) & 1u;
-        if (tid == 0) {
-            // refill the stage consumed in the previous iteration
+        if (tid == 0) {                                   // refill the stage consumed last iteration
             const unsigned long long nxt = tile + (unsigned long long)(NSTAGE - 1) * stride;
             if (nxt < P.n_tiles) {
                 const int ns = (it + NSTAGE - 1) % NSTAGE;
@@ -228,32 +248,41 @@ rss_scan_kernel(const ScanParams P)
                 bulk_g2s(s_stage + ns * STAGE_STRIDE, P.planes + nxt * IGD_TILE_CHUNKS, STAGE_BYTES, &s_bar[ns]);
             }
         }
+        if (tid < INVSUM_WORDS) s_invsum[tid] = __ldg(&P.invsum[tile * (IGD_TILE_CHUNKS / 32) + tid]);
         while (!mbar_try_wait(&s_bar[stage], parity)) { }
 
         const uint32_t *sw = (const uint32_t *)(s_stage + stage * STAGE_STRIDE);
         TileCtx T;
-        T.sw = sw; T.s_lut7 = s_lut7; T.s_any9 = s_any9;
-        T.g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);   // stage record 0 = chunk tile*256
+        T.sw = sw; T.s_lut7 = s_lut7; T.s_invsum = s_invsum;
+        T.g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);   // stage record 0 = chunk tile*512
 
-        // ---- phase A: heptamer membership of the 64 windows starting in this thread's chunk
+        // ---- phase A: heptamer candidates of the 64 windows starting in this thread's chunk
         {
             const uint4 r = ((const uint4 *)sw)[tid + 1];
             const uint4 n = ((const uint4 *)sw)[tid + 2];
+            uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
+            if (PREFILTER) {
+                const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
+                cand0 = consensus_ge4(i0, i1);
+                cand1 = consensus_ge4(i1, i2);
+            }
             const int p0 = (tid + 1) * 64;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const uint32_t l0 = half ? r.y : r.x, l1 = half ? n.x : r.y;
                 const uint32_t h0 = half ? r.w : r.z, h1 = half ? n.z : r.w;
-#pragma unroll 8
-                for (int b = 0; b < 32; ++b) {
+                uint32_t m = half ? cand1 : cand0;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
                     const unsigned lo = __funnelshift_r(l0, l1, b) & 127u;
                     const unsigned hi = __funnelshift_r(h0, h1, b) & 127u;
                     const unsigned f = s_lut7[(hi << 7) | lo];
                     if (f) {
                         const unsigned slot = atomicAdd(s_qn, 1u);
-                        const unsigned e = (unsigned)(p0 + half * 32 + b) | (f << 16);
-                        if (slot < QCAP) s_queue[slot] = e;
-                        else eval_heptamer(P, T, p0 + half * 32 + b, f);
+                        const int q = p0 + half * 32 + b;
+                        if (slot < QCAP) s_queue[slot] = (unsigned)q | (f << 16);
+                        else eval_heptamer(P, T, q, f);
                     }
                 }
             }
@@ -267,11 +296,8 @@ rss_scan_kernel(const ScanParams P)
                 eval_heptamer(P, T, (int)(e & 0xffffu), e >> 16);
             }
         }
-        __syncthreads();
+        __syncthreads();          // all reads of this stage, the queue and s_invsum are done
         if (tid == 0) *s_qn = 0;
-        // the next iteration's refill targets this stage only after the barrier above; the
-        // queue counter reset is ordered before any push by the mbarrier wait + program order
-        __syncthreads();
     }
 }
 
@@ -323,7 +349,7 @@ kmer_scan_kernel(const KmerParams P)
 
 } // namespace
 
-static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + 32768 + QCAP * 4 + NSTAGE * 8 + 16;
+static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + QCAP * 4 + 32 * 4 + NSTAGE * 8 + 16;
 
 int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
 {
@@ -333,18 +359,15 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
     P.n_tiles = h->n_tiles;
     for (int i = 0; i < 4; ++i) P.sp[i] = spacer[i];
     P.hits = h->d_hits; P.cap = h->hit_cap; P.count = h->d_count;
-    static bool attr_done = false;
-    if (!attr_done) {
-        IGD_CUDA(cudaFuncSetAttribute(rss_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
-        attr_done = true;
-    }
+    auto kernel = h->consensus_prefilter ? rss_scan_kernel<true> : rss_scan_kernel<false>;
+    IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
     int per_sm = 0;
-    IGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rss_scan_kernel, IGD_TILE_CHUNKS, kScanSmem));
+    IGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IGD_TILE_CHUNKS, kScanSmem));
     if (per_sm < 1) per_sm = 1;
     unsigned long long blocks = (unsigned long long)h->sm_count * per_sm;
     if (blocks > h->n_tiles) blocks = h->n_tiles;
     if (blocks < 1) blocks = 1;
-    rss_scan_kernel<<<(unsigned)blocks, IGD_TILE_CHUNKS, kScanSmem, h->stream>>>(P);
+    kernel<<<(unsigned)blocks, IGD_TILE_CHUNKS, kScanSmem, h->stream>>>(P);
     h->timing.total_launches++;
     IGD_CUDA(cudaGetLastError());
     return IGD_OK;

@@ -55,6 +55,8 @@ class Engine:
         self.device = int(device)
         self.contig_ids = []
         self.contig_lens = np.zeros(0, np.int64)
+        self.h2d_bytes = 0          # bytes handed to the C ABI as inputs / read back as results
+        self.d2h_bytes = 0
         if motifs is not None:
             self.set_motifs(motifs)
 
@@ -99,6 +101,7 @@ class Engine:
         self.contig_ids = list(ids) if ids is not None else list(range(n))
         self.contig_lens = np.diff(off.astype(np.int64))
         _lib.check(self._lib.igd_load_contigs(self._h, ptr, off.ctypes.data, n))
+        self.h2d_bytes += int(off[-1] - off[0]) + off.nbytes
         return n
 
     def scan_rss(self, spacers):
@@ -111,6 +114,7 @@ class Engine:
         _lib.check(self._lib.igd_scan(self._h, sp.ctypes.data, ctypes.byref(n)))
         out = np.zeros(n.value, _lib.HIT_DTYPE)
         _lib.check(self._lib.igd_fetch_hits(self._h, out.ctypes.data, n.value))
+        self.d2h_bytes += 8 + 8 * n.value       # count + one packed 64-bit key per hit cross the bus
         return out
 
     def scan_rss_count(self, spacers):
@@ -125,6 +129,7 @@ class Engine:
         _lib.check(self._lib.igd_scan_kmers(self._h, int(k), ctypes.byref(n)))
         out = np.zeros(n.value, _lib.KMER_HIT_DTYPE)
         _lib.check(self._lib.igd_fetch_kmer_hits(self._h, out.ctypes.data, n.value))
+        self.d2h_bytes += 8 + 8 * n.value
         return out
 
     # ---- alignment --------------------------------------------------------------------------
@@ -152,6 +157,8 @@ class Engine:
             res["end"].ctypes.data, ient.ctypes.data if want_ient else None))
         if want_ient:
             res["ient"] = ient
+        self.h2d_bytes += tb.nbytes + to.nbytes + qb.nbytes + qo.nbytes + 3 * pt.nbytes
+        self.d2h_bytes += (4 if want_ient else 2) * 4 * n
         return res
 
     def sync(self):

@@ -119,10 +119,10 @@ def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
     return rows
 
 
-def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False):
+def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False, load=True):
     """The module body of py/IGDetective.py:439-487 as a function.
     Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only."""
-    scan = RssScan(engine, input_seq_dict, order=order)
+    scan = RssScan(engine, input_seq_dict, order=order, load=load)
     info = {st: {sd: scan.contigwise(st, sd) for sd in (FWD, REV)} for st in SIGNAL_TYPES}
     info[D] = {sd: combine_D_RSS(info[DL][sd], info[DR][sd], input_seq_dict, sd) for sd in (FWD, REV)}
     if rss_only:

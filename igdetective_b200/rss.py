@@ -24,7 +24,7 @@ HEPT_FIRST = {V: True, DR: True, J: False, DL: False}
 class RssScan:
     """Result of one scan of `parent_seq` ({contig id: str}) on an Engine."""
 
-    def __init__(self, engine, parent_seq, spacers=None, order="reference"):
+    def __init__(self, engine, parent_seq, spacers=None, order="reference", load=True):
         if order not in ("reference", "canonical"):
             raise ValueError("order must be 'reference' or 'canonical'")
         self.engine = engine
@@ -33,7 +33,8 @@ class RssScan:
         self.lens = [len(parent_seq[c]) for c in self.ids]
         self.spacers = dict(spacers or SPACER_LENGTH)
         self.order = order
-        engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
+        if load:                       # load=False: the caller already put these contigs on the engine
+            engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
         self.hits = engine.scan_rss(self.spacers)
         self._kmers = {}
         self._cache = {}

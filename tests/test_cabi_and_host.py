@@ -1,0 +1,106 @@
+"""CPU-only checks: the C ABI library loads and exports what include/igd_b200.h declares, fails
+loudly without a GPU, and the host-side glue (order replay, D pairing, tables, FASTA) is right."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import DATAFILES, ROOT, golden_input
+from oracle import igd_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    from igdetective_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "igd_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(igd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from igdetective_b200._lib import IgdError
+    from igdetective_b200.engine import Engine
+    with pytest.raises(IgdError):
+        Engine(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "igdetective_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, fn)).read()
+                assert "oracle" not in src.replace("igd_oracle_unused", ""), fn
+
+
+def test_motif_flag_tables(motifs):
+    from igdetective_b200.engine import SIGNAL_INDEX, motif_flag_tables
+    f7, f9 = motif_flag_tables(motifs)
+    for name, t in SIGNAL_INDEX.items():
+        assert int(((f7 >> t) & 1).sum()) == len(motifs[name]["7"])
+        assert int(((f9 >> t) & 1).sum()) == len(motifs[name]["9"])
+    v = 0
+    for c in "CACAGTG":
+        v = v * 4 + "ACGT".index(c)
+    assert f7[v] & 1
+
+
+def test_datafiles_loader_matches_oracle(motifs):
+    from igdetective_b200 import datafiles
+    assert datafiles.load_motifs(DATAFILES) == motifs
+    g = datafiles.load_canonical_genes("IGH", "J", "combined_reference_genes", DATAFILES)
+    assert g == O.fasta_dict(os.path.join(DATAFILES, "combined_reference_genes", "IGHJ.fa.gz"), upper=True)
+    assert all(s == s.upper() for s in g.values())
+
+
+def test_reference_set_order_replay():
+    from igdetective_b200.order import reference_set_order
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 263, 5000):
+        asc = sorted(set(rng.integers(0, 3_000_000, n).tolist()))
+        assert reference_set_order(asc) == O.reference_set_order(asc)
+        assert sorted(reference_set_order(asc)) == asc
+
+
+def test_combine_d_rss_equals_reference_loops():
+    from igdetective_b200.rss import combine_D_RSS
+    rng = np.random.default_rng(1)
+    seqs = {"a": "x", "b": "y", "c": "z"}
+    for strand in "+-":
+        dl = {c: [(int(p), int(p) - 21) for p in rng.integers(0, 3000, 60)] for c in seqs}
+        dr = {c: [(int(p), int(p) + 19) for p in rng.integers(0, 3000, 50)] for c in seqs}
+        dl["c"], dr["b"] = [], []
+        assert combine_D_RSS(dl, dr, seqs, strand) == O.combine_D_RSS(dl, dr, seqs, strand)
+
+
+def test_fragment_slicing_quirks():
+    """negative slice start near the contig start gives an empty fragment, not a truncated one"""
+    from igdetective_b200.rss import get_s_fragment_from_RSS
+    s = "".join("ACGT"[i % 4] for i in range(1000))
+    seqs = {"c": s}
+    info = {"V": {"+": {"c": [(100, 130), (400, 430)]}, "-": {"c": [(900, 870)]}},
+            "J": {"+": {"c": [(990, 950)]}, "-": {"c": [(30, 60), (500, 530)]}}}
+    for g in "VJ":
+        for sd in "+-":
+            assert get_s_fragment_from_RSS(g, sd, info, seqs) == O.s_fragments(g, sd, info, seqs)
+    assert get_s_fragment_from_RSS("V", "+", info, seqs)["c"][0] == ""
+    assert len(get_s_fragment_from_RSS("J", "+", info, seqs)["c"][0]) == 3
+
+
+def test_fasta_reader_and_translate():
+    from igdetective_b200.extract_aligned_genes import translate
+    from igdetective_b200.fasta import fasta_dict, read_fasta, reverse_complement
+    p = golden_input("cow")
+    assert read_fasta(p) == O.read_fasta(p)
+    assert list(fasta_dict(p)) == ["KT723008.1|Bos"]
+    assert reverse_complement("ACGTNacgtRy") == O.revcomp("ACGTNacgtRy") == "rYacgtNACGT"
+    for s in ("ATGGCCTAA", "atggcNtga", "ATGNNNAC", "GCNTAR", ""):
+        assert translate(s) == O.translate(s)
+    assert translate("ATGGCCTAA") == "MA*" and translate("GCN") == "A" and translate("TAR") == "*"
