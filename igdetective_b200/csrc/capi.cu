@@ -363,12 +363,32 @@ int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity)
 
 // ---- alignment ------------------------------------------------------------------------------------
 
+// Can every intermediate DP value of an nA x nB pair be held in the packed kernel's 12-bit score
+// field, with the sentinel (-2000) below everything reachable and one extension short of wrapping?
+static bool packed_scheme_ok(const igd_scoring *sc)
+{
+    const int g[] = {sc->target_internal_open, sc->target_internal_extend, sc->query_internal_open,
+                     sc->query_internal_extend, sc->query_end_open, sc->query_end_extend};
+    for (int v : g) if (v > 0 || v < -40) return false;
+    return sc->match >= -40 && sc->match <= 40 && sc->mismatch >= -40 && sc->mismatch <= 40;
+}
+static bool packed_pair_ok(const igd_scoring *sc, int nA, int nB)
+{
+    if (nA > 511 || nB > 511) return false;                       // 9-bit matches / internal-Ix fields
+    const int hi = std::max(0, sc->match) * std::min(nA, nB);
+    // every state is at least as good as "row 0 along the query, then straight down" (pure gaps)
+    const int lo = sc->target_internal_open + sc->target_internal_extend * (nB - 1)
+                 + std::min(sc->query_internal_open, sc->query_end_open)
+                 + std::min(sc->query_internal_extend, sc->query_end_extend) * (nA - 1);
+    return hi <= 1900 && lo - 8 * 40 >= -1900;
+}
+
 int igd_align_batch(igd_handle *h,
                     const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
                     const int32_t *pair_t, const int32_t *pair_q, int64_t n_pairs,
                     const igd_scoring *sc,
-                    int32_t *score, int32_t *matches, int32_t *start, int32_t *end, int32_t *ient)
+                    int32_t *score, int32_t *matches, int32_t *alen, int32_t *start, int32_t *ient)
 {
     if (!h || !tgt_off || !qry_off || !sc || n_tgt < 0 || n_qry < 0 || n_pairs < 0 || (n_pairs && (!pair_t || !pair_q || !score))) {
         igd_set_error("bad arguments to igd_align_batch"); return IGD_ERR_ARG;
@@ -388,13 +408,15 @@ int igd_align_batch(igd_handle *h,
     h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
     if (n_pairs == 0) return IGD_OK;
 
-    // validate, bucket by target length, detect lower-case letters
+    // validate, bucket by target length and kernel, detect lower-case letters
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
     bool mixed = false;
     for (size_t i = 0; i < tbytes && !mixed; ++i) mixed = (unsigned)(tgt[i] - 'a') < 26u;
     for (size_t i = 0; i < qbytes && !mixed; ++i) mixed = (unsigned)(qry[i] - 'a') < 26u;
+    const bool detail = start || ient;
+    const bool packed_ok = !detail && packed_scheme_ok(sc);
     constexpr int NB = 6;
-    std::vector<int32_t> work[NB];
+    std::vector<int32_t> work[2][NB];                  // [packed?][bucket]
     std::vector<int64_t> trivial;                      // empty target: closed form
     uint64_t cells = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -407,7 +429,8 @@ int igd_align_batch(igd_handle *h,
             return IGD_ERR_TOO_LONG;
         }
         if (nA == 0) { trivial.push_back(p); continue; }
-        work[igd_align_bucket_of(nA)].push_back((int32_t)p);
+        const int b = igd_align_bucket_of(nA);
+        work[(packed_ok && b <= 3 && packed_pair_ok(sc, nA, nB)) ? 1 : 0][b].push_back((int32_t)p);
         cells += (uint64_t)nA * (uint64_t)nB;
     }
     int rc;
@@ -427,30 +450,31 @@ int igd_align_batch(igd_handle *h,
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PT], pair_t, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PQ], pair_q, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     std::vector<int32_t> flat; flat.reserve((size_t)n_pairs);
-    size_t woff[NB + 1]; woff[0] = 0;
-    for (int b = 0; b < NB; ++b) { flat.insert(flat.end(), work[b].begin(), work[b].end()); woff[b + 1] = flat.size(); }
+    size_t woff[2][NB];
+    for (int k = 0; k < 2; ++k)
+        for (int b = 0; b < NB; ++b) { woff[k][b] = flat.size(); flat.insert(flat.end(), work[k][b].begin(), work[k][b].end()); }
     if (!flat.empty())
         IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_WORK], flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, h->stream));
 
     std::vector<int32_t> h_score((size_t)n_pairs), h_pay((size_t)n_pairs);
     const int passes = ient ? 2 : 1;
-    std::vector<int32_t> trail;
     for (int pass = 0; pass < passes; ++pass) {
-        IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, NB * sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 2 * NB * sizeof(unsigned long long), h->stream));
         IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
-        for (int b = 0; b < NB; ++b) {
-            if (work[b].empty()) continue;
-            igd_align_job job;
-            job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
-            job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
-            job.d_pair_t = (const int32_t *)h->d_scratch[S_PT]; job.d_pair_q = (const int32_t *)h->d_scratch[S_PQ];
-            job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[b];
-            job.n_work = (int32_t)work[b].size();
-            job.bucket = b; job.mixed_case = mixed; job.pay_mode = pass; job.sc = *sc;
-            job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
-            job.d_counter = (unsigned int *)(h->d_count + 8 + b);
-            if ((rc = igd_launch_gotoh(h, job))) return rc;
-        }
+        for (int k = 0; k < 2; ++k)
+            for (int b = 0; b < NB; ++b) {
+                if (work[k][b].empty()) continue;
+                igd_align_job job;
+                job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
+                job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
+                job.d_pair_t = (const int32_t *)h->d_scratch[S_PT]; job.d_pair_q = (const int32_t *)h->d_scratch[S_PQ];
+                job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[k][b];
+                job.n_work = (int32_t)work[k][b].size();
+                job.bucket = b; job.mixed_case = mixed; job.packed = (k == 1); job.pay_mode = pass; job.sc = *sc;
+                job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
+                job.d_counter = (unsigned int *)(h->d_count + 8 + k * NB + b);
+                if ((rc = igd_launch_gotoh(h, job))) return rc;
+            }
         IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
         IGD_CUDA(cudaMemcpyAsync(h_score.data(), h->d_scratch[S_SCORE], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
         IGD_CUDA(cudaMemcpyAsync(h_pay.data(), h->d_scratch[S_PAY], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -465,11 +489,10 @@ int igd_align_batch(igd_handle *h,
             if (nA == 0) continue;
             const uint32_t pay = (uint32_t)h_pay[p];
             if (pass == 0) {
-                const int lead = (int)(pay >> 20) & 1023, intx = (int)(pay >> 10) & 1023;
                 score[p] = h_score[p];
                 if (matches) matches[p] = (int)(pay & 1023);
-                if (start) start[p] = lead;
-                if (end) end[p] = lead + nB + intx;
+                if (alen) alen[p] = nB + ((int)(pay >> 10) & 1023);
+                if (start) start[p] = (int)(pay >> 20) & 1023;
             } else {
                 ient[p] = nA - ((int)(pay >> 20) & 1023);
             }
@@ -481,8 +504,8 @@ int igd_align_batch(igd_handle *h,
         const int nB = qry_off[q + 1] - qry_off[q];
         score[p] = sc->target_end_open + sc->target_end_extend * (nB - 1);
         if (matches) matches[p] = 0;
+        if (alen) alen[p] = nB;
         if (start) start[p] = 0;
-        if (end) end[p] = nB;
         if (ient) ient[p] = 0;
     }
     return IGD_OK;

@@ -164,6 +164,135 @@ gotoh_kernel(const GotohParams P)
     }
 }
 
+// ---- packed variant: one 32-bit word per state ------------------------------------------------
+// word = score << 20 | priority << 18 | internal-Ix-moves << 9 | matches.  Candidates that tie on
+// (score, priority) always descend from the same state and so carry the same payload, hence a
+// single integer max selects score, tie-break and payload at once: 12 integer instructions per
+// cell instead of 27.  Only (score, matches, alignment length) come out; lead / ient need the
+// two-register kernel above.  The host routes a pair here only if every field provably fits
+// (target <= 511 rows, query <= 511 columns, score bounds inside +-1900, see capi.cu).
+constexpr int PK_S = 1 << 20, PK_PR = 1 << 18, PK_PRMASK = 3 << 18, PK_UI = 1 << 9;
+constexpr int PK_NEG = -2000 * PK_S;
+
+struct PackedParams {
+    const uint8_t *tgt; const int32_t *tgt_off;
+    const uint8_t *qry; const int32_t *qry_off;
+    const int32_t *pair_t; const int32_t *pair_q;
+    const int32_t *work; int32_t n_work;
+    int inc_match, inc_mismatch;  // score * S + 2 * PR (+1 match for inc_match)
+    int to, te;                   // target gap open / extend, * S
+    int qio, qie, qeo, qee;       // query internal / end gap open / extend, * S
+    int32_t *out_score; uint32_t *out_pay;
+    unsigned int *counter;
+};
+
+template <int G, int C, bool MIXED>
+__global__ void __launch_bounds__(GT_THREADS)
+gotoh_packed_kernel(const PackedParams P)
+{
+    constexpr int GROUPS_PER_WARP = 32 / G;
+    const unsigned lane = threadIdx.x & 31u;
+    const int l = lane % G;
+    const int grp = lane / G;
+
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(P.counter, (unsigned)GROUPS_PER_WARP);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)P.n_work) break;
+        const bool have = base + grp < (unsigned)P.n_work;
+        int pair = 0, nA = 0, nB = 0;
+        const uint8_t *A = P.tgt, *B = P.qry;
+        if (have) {
+            pair = P.work[base + grp];
+            const int t = P.pair_t[pair], q = P.pair_q[pair];
+            const int a0 = P.tgt_off[t], b0 = P.qry_off[q];
+            nA = P.tgt_off[t + 1] - a0; nB = P.qry_off[q + 1] - b0;
+            A += a0; B += b0;
+        }
+        int steps = have ? nB + G - 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+
+        unsigned a[C];
+        int D[C], Y[C];                                       // D(i, j-1) with priority, Iy(i, j-1) clean
+        const int i0 = l * C;
+#pragma unroll
+        for (int r = 0; r < C; ++r) {
+            const int i = i0 + r + 1;
+            const unsigned ch = (have && i <= nA) ? A[i - 1] : 0u;
+            a[r] = MIXED ? (ch | (up8(ch) << 8)) : ch;
+            D[r] = P.qeo + P.qee * (i - 1) + PK_PR;           // D(i,0) = Ix(i,0), priority 1
+            Y[r] = PK_NEG;
+        }
+        int diag = (l == 0) ? 0 : (P.qeo + P.qee * (i0 - 1));   // clean D(i0, 0)
+        int botD = PK_NEG, botX = PK_NEG;
+
+        for (int t = 0; t < steps; ++t) {
+            int upD = __shfl_up_sync(0xffffffffu, botD, 1, G);
+            int upX = __shfl_up_sync(0xffffffffu, botX, 1, G);
+            const int j = t - l + 1;
+            if (j >= 1 && j <= nB) {
+                if (l == 0) { upD = P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j), priority 0
+                const unsigned braw = B[j - 1];
+                const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
+                const bool lastcol = (j == nB);
+                const int qo = lastcol ? P.qeo : P.qio;
+                const int qe = lastcol ? P.qee : P.qie;
+                const int xfix = PK_PR + (lastcol ? 0 : PK_UI);   // priority 1 (+1 internal Ix move)
+                const int nextdiag = upD & ~PK_PRMASK;
+                int dc = diag, uD = upD, uX = upX;
+#pragma unroll
+                for (int r = 0; r < C; ++r) {
+                    int inc;
+                    if (MIXED) {
+                        const unsigned x = a[r] ^ b;
+                        inc = (x & 0xffu) == 0u ? P.inc_match : ((x & 0xff00u) == 0u ? P.inc_mismatch + 1 : P.inc_mismatch);
+                    } else {
+                        inc = (a[r] == b) ? P.inc_match : P.inc_mismatch;
+                    }
+                    const int m = dc + inc;                                            // M(i,j), priority 2
+                    const int x = __viaddmax_s32(uD, qo, uX + qe);                     // Ix(i,j) raw
+                    const int xs = (x & ~PK_PRMASK) + xfix;                            // priority 1, move counted
+                    const int y = __viaddmax_s32(D[r], P.to, Y[r] + P.te) & ~PK_PRMASK; // Iy(i,j), priority 0
+                    const int d = __vimax3_s32(m, xs, y);
+                    dc = D[r] & ~PK_PRMASK;
+                    D[r] = d; Y[r] = y;
+                    uD = d; uX = xs;
+                }
+                botD = uD; botX = uX;
+                diag = (l == 0) ? (P.to + P.te * (j - 1)) : nextdiag;
+            }
+        }
+        if (have && nA >= 1) {
+            const int ls = (nA - 1) / C, rs = (nA - 1) % C;
+            if (l == ls) {
+                int k = 0;
+#pragma unroll
+                for (int r = 0; r < C; ++r) if (r == rs) k = D[r];
+                P.out_score[pair] = k >> 20;
+                P.out_pay[pair] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & 511u) << 10);   // same layout as the wide kernel
+            }
+        }
+    }
+}
+
+template <int G, int C>
+int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
+{
+    const unsigned warps_needed = (unsigned)((P.n_work + (32 / G) - 1) / (32 / G));
+    unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);
+    const unsigned cap = (unsigned)h->sm_count * 4u;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (mixed) gotoh_packed_kernel<G, C, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    else       gotoh_packed_kernel<G, C, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    h->timing.total_launches++;
+    h->timing.align_launches++;
+    IGD_CUDA(cudaGetLastError());
+    return IGD_OK;
+}
+
 template <int G, int C>
 int launch(igd_handle *h, const GotohParams &P, bool mixed)
 {
@@ -197,8 +326,30 @@ int igd_align_bucket_of(int target_len)
     return -1;
 }
 
+static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
+{
+    PackedParams P;
+    P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
+    P.pair_t = job.d_pair_t; P.pair_q = job.d_pair_q; P.work = job.d_work; P.n_work = job.n_work;
+    P.inc_match = job.sc.match * PK_S + 2 * PK_PR + 1;
+    P.inc_mismatch = job.sc.mismatch * PK_S + 2 * PK_PR;
+    P.to = job.sc.target_internal_open * PK_S; P.te = job.sc.target_internal_extend * PK_S;
+    P.qio = job.sc.query_internal_open * PK_S; P.qie = job.sc.query_internal_extend * PK_S;
+    P.qeo = job.sc.query_end_open * PK_S; P.qee = job.sc.query_end_extend * PK_S;
+    P.out_score = job.d_score; P.out_pay = job.d_pay; P.counter = job.d_counter;
+    switch (job.bucket) {
+    case 0: return launch_packed<8, 9>(h, P, job.mixed_case);
+    case 1: return launch_packed<32, 6>(h, P, job.mixed_case);
+    case 2: return launch_packed<32, 11>(h, P, job.mixed_case);
+    case 3: return launch_packed<32, 16>(h, P, job.mixed_case);
+    }
+    igd_set_error("bad packed align bucket %d", job.bucket);
+    return IGD_ERR_ARG;
+}
+
 int igd_launch_gotoh(igd_handle *h, const igd_align_job &job)
 {
+    if (job.packed) return launch_gotoh_packed(h, job);
     GotohParams P;
     P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
     P.pair_t = job.d_pair_t; P.pair_q = job.d_pair_q; P.work = job.d_work; P.n_work = job.n_work;

@@ -133,9 +133,10 @@ class Engine:
         return out
 
     # ---- alignment --------------------------------------------------------------------------
-    def align(self, targets, queries, pair_t, pair_q, scoring=None, want_ient=False):
+    def align(self, targets, queries, pair_t, pair_q, scoring=None, detail=False):
         """targets / queries: list[str|bytes] or (uint8 buffer, int32 offsets).  Returns a dict of int32
-        arrays: score, matches (TRUE count), start, end and, if want_ient, ient."""
+        arrays: score, matches (TRUE count), alen (= end - start) and, with detail=True, also start, end
+        and ient (QuerySeq = target[start:ient]); detail costs the slower two-pass kernel."""
         tb, to = targets if isinstance(targets, tuple) else concat(targets)
         qb, qo = queries if isinstance(queries, tuple) else concat(queries)
         tb = np.ascontiguousarray(tb, np.uint8)
@@ -147,18 +148,18 @@ class Engine:
         n = len(pt)
         assert len(pq) == n
         sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
-        res = {k: np.zeros(n, np.int32) for k in ("score", "matches", "start", "end")}
-        ient = np.zeros(n, np.int32) if want_ient else None
+        res = {k: np.zeros(n, np.int32) for k in (("score", "matches", "alen", "start", "ient") if detail
+                                                   else ("score", "matches", "alen"))}
         _lib.check(self._lib.igd_align_batch(
             self._h, tb.ctypes.data if tb.size else None, to.ctypes.data, len(to) - 1,
             qb.ctypes.data if qb.size else None, qo.ctypes.data, len(qo) - 1,
             pt.ctypes.data, pq.ctypes.data, n, ctypes.byref(sc),
-            res["score"].ctypes.data, res["matches"].ctypes.data, res["start"].ctypes.data,
-            res["end"].ctypes.data, ient.ctypes.data if want_ient else None))
-        if want_ient:
-            res["ient"] = ient
+            res["score"].ctypes.data, res["matches"].ctypes.data, res["alen"].ctypes.data,
+            res["start"].ctypes.data if detail else None, res["ient"].ctypes.data if detail else None))
+        if detail:
+            res["end"] = res["start"] + res["alen"]
         self.h2d_bytes += tb.nbytes + to.nbytes + qb.nbytes + qo.nbytes + 3 * pt.nbytes
-        self.d2h_bytes += (4 if want_ient else 2) * 4 * n
+        self.d2h_bytes += (4 if detail else 2) * 4 * n
         return res
 
     def sync(self):

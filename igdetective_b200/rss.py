@@ -90,21 +90,29 @@ def get_contigwise_rss(sig_type, strand, parent_seq, scan=None, engine=None, ord
 
 def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GENE_LENGTH[D]):
     """py/IGDetective.py:210-224: every (dr, dl) with left < right and right-(left+7) <= Dgene_len,
-    dr-outer / dl-inner in the given list orders.  Vectorised per dr; same output."""
+    dr-outer / dl-inner in the given list orders.  The reference's double loop is replaced by one
+    sorted search per contig; the output (content and order) is the same."""
     res = {c: [] for c in input_seq_dict.keys()}
     for c in input_seq_dict:
         dls, drs = D_left_idx[c], D_right_idx[c]
         if not dls or not drs:
             continue
         dl0 = np.fromiter((x[0] for x in dls), np.int64, len(dls))
-        for dr in drs:
-            if strand == FWD:
-                ok = (dr[0] - (dl0 + 7) <= Dgene_len) & (dl0 < dr[0])
-            else:
-                ok = (dl0 - (dr[0] + 7) <= Dgene_len) & (dr[0] < dl0)
-            for i in np.nonzero(ok)[0]:
+        dr0 = np.fromiter((x[0] for x in drs), np.int64, len(drs))
+        order = np.argsort(dl0, kind="stable")
+        sdl = dl0[order]
+        if strand == FWD:        # left = dl, right = dr:  dr-157 <= dl <= dr-1
+            lo = np.searchsorted(sdl, dr0 - (Dgene_len + 7), "left")
+            hi = np.searchsorted(sdl, dr0 - 1, "right")
+        else:                    # left = dr, right = dl:  dr+1 <= dl <= dr+157
+            lo = np.searchsorted(sdl, dr0 + 1, "left")
+            hi = np.searchsorted(sdl, dr0 + (Dgene_len + 7), "right")
+        out = res[c]
+        for k in np.nonzero(hi > lo)[0]:
+            dr = drs[k]
+            for i in np.sort(order[lo[k]:hi[k]]):      # dl-inner order = position in the dl list
                 dl = dls[i]
-                res[c].append((dl[0], dl[1], dr[0], dr[1]))
+                out.append((dl[0], dl[1], dr[0], dr[1]))
     return res
 
 

@@ -39,9 +39,9 @@ class BioAlignView:
         return self._target[self.gene_range[0]:self._ient].upper()
 
 
-def pi_from(matches, start, end):
+def pi_from(matches, alen):
     """float64 PI exactly as BioAlign.PI(): (matches-1) / len * 100, evaluated left to right."""
-    return (np.asarray(matches, np.int64) - 1) / (np.asarray(end, np.int64) - np.asarray(start, np.int64)) * 100
+    return (np.asarray(matches, np.int64) - 1) / np.asarray(alen, np.int64) * 100
 
 
 def compute_alignments(engine, pairs, genes, want_ient=False):
@@ -58,13 +58,12 @@ def compute_alignments(engine, pairs, genes, want_ient=False):
             targets.append(reverse_complement(q))
         pt += [index[q], index[q] + 1]
         pq += [g, g]
-    r = engine.align(targets, genes, pt, pq, want_ient=want_ient)
+    r = engine.align(targets, genes, pt, pq, detail=True)
     out = []
     for k in range(len(pairs)):
         f, b = 2 * k, 2 * k + 1
         pick, d = (f, "+") if r["matches"][f] - 1 > r["matches"][b] - 1 else (b, "-")
-        view = BioAlignView(targets[pt[pick]], r["matches"][pick], r["start"][pick], r["end"][pick],
-                            r["ient"][pick] if want_ient else None)
+        view = BioAlignView(targets[pt[pick]], r["matches"][pick], r["start"][pick], r["end"][pick], r["ient"][pick])
         out.append((view, d, int(r["matches"][pick]) - 1))
     return out
 
@@ -104,14 +103,12 @@ def align_fragment_to_genes(fragments, canon_genes, scoring_scheme=None, gene=No
     pq = np.broadcast_to(np.arange(G, dtype=np.int32)[None, :, None], (F, G, 2))
     r = engine.align(targets, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
     m = r["matches"].reshape(F, G, 2)
-    st = r["start"].reshape(F, G, 2)
-    en = r["end"].reshape(F, G, 2)
+    ln = r["alen"].reshape(F, G, 2)
     fwd = (m[:, :, 0] - 1) > (m[:, :, 1] - 1)
     pick = np.where(fwd, 0, 1)[:, :, None]
     mm = np.take_along_axis(m, pick, 2)[:, :, 0]
-    ss = np.take_along_axis(st, pick, 2)[:, :, 0]
-    ee = np.take_along_axis(en, pick, 2)[:, :, 0]
-    return pi_from(mm, ss, ee), (ee - ss).astype(np.float64)
+    ll = np.take_along_axis(ln, pick, 2)[:, :, 0]
+    return pi_from(mm, ll), ll.astype(np.float64)
 
 
 class Alignment:
@@ -144,7 +141,7 @@ def window_alignments(engine, windows, genes):
     pt = np.repeat(np.arange(2 * W, dtype=np.int32), G)
     pq = np.tile(np.arange(G, dtype=np.int32), 2 * W)
     r = engine.align(targets, [g[1] for g in genes], pt, pq)
-    pi = pi_from(r["matches"], r["start"], r["end"]).reshape(W, 2 * G)
+    pi = pi_from(r["matches"], r["alen"]).reshape(W, 2 * G)
     # last index attaining the maximum, provided the maximum is >= 0 (best_pi starts at 0)
     best = 2 * G - 1 - np.argmax(pi[:, ::-1], axis=1)
     need = []
@@ -155,7 +152,7 @@ def window_alignments(engine, windows, genes):
     if need:
         dt = [2 * w + b // G for w, b in need]
         dq = [b % G for w, b in need]
-        d = engine.align(targets, [g[1] for g in genes], dt, dq, want_ient=True)
+        d = engine.align(targets, [g[1] for g in genes], dt, dq, detail=True)
         for i, (w, b) in enumerate(need):
             detail[w] = (b, d["start"][i], d["end"][i], d["ient"][i])
     for w in range(W):

@@ -138,16 +138,19 @@ int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity);
  *   score   optimal global score
  *   matches number of equal (upper-cased) columns inside the gene range
  *           -- the TRUE count; BioAlign.NumMatches() returns matches-1
+ *   alen    len(BioAlign) == AlignmentRange()[1] - AlignmentRange()[0]
  *   start   BioAlign.AlignmentRange()[0]  (columns before the first gene letter)
- *   end     BioAlign.AlignmentRange()[1]  (len(BioAlign) == end - start)
- *   ient    BioAlign.QuerySeq() == upper(target[start:ient]); costs a second DP pass
+ *   ient    BioAlign.QuerySeq() == upper(target[start:ient])
+ * With start == ient == NULL every pair whose fields provably fit runs in the
+ * packed single-register kernel (about twice as fast); asking for start uses
+ * the two-register kernel, asking for ient adds a second pass of it.
  */
 int igd_align_batch(igd_handle *h,
                     const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
                     const int32_t *pair_t, const int32_t *pair_q, int64_t n_pairs,
                     const igd_scoring *sc,
-                    int32_t *score, int32_t *matches, int32_t *start, int32_t *end, int32_t *ient);
+                    int32_t *score, int32_t *matches, int32_t *alen, int32_t *start, int32_t *ient);
 
 #ifdef __cplusplus
 }

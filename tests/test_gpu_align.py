@@ -11,13 +11,17 @@ KEYS = ("score", "matches", "start", "end", "ient")
 
 
 def compare(engine, targets, queries, pt, pq):
-    got = engine.align(targets, queries, pt, pq, want_ient=True)
+    """both kernels: detail=True -> two-register kernel (all fields), detail=False -> packed kernel
+    wherever the pair qualifies (score, matches, alignment length)"""
     want = O.align_stats(targets, queries, pt, pq, threads=8)
-    for k, wk in zip(KEYS, ("score", "matches", "start", "end", "ient")):
-        w = want[wk].astype(np.int64)
-        bad = np.nonzero(got[k] != w)[0]
-        assert bad.size == 0, (k, bad[:5], got[k][bad[:5]], w[bad[:5]],
-                               [(targets[pt[i]], queries[pq[i]]) for i in bad[:1]])
+    w = {k: want[k].astype(np.int64) for k in KEYS}
+    w["alen"] = w["end"] - w["start"]
+    for detail, keys in ((True, KEYS + ("alen",)), (False, ("score", "matches", "alen"))):
+        got = engine.align(targets, queries, pt, pq, detail=detail)
+        for k in keys:
+            bad = np.nonzero(got[k] != w[k])[0]
+            assert bad.size == 0, (detail, k, bad[:5], got[k][bad[:5]], w[k][bad[:5]],
+                                   [(targets[pt[i]], queries[pq[i]]) for i in bad[:1]])
 
 
 def rand_seq(rng, n, alphabet="ACGT"):
@@ -112,7 +116,7 @@ def test_align_low_complexity_ties(engine):
 
 def test_align_empty_target_and_errors(engine):
     from igdetective_b200._lib import IgdError
-    r = engine.align(["", "ACGT"], ["ACGTAC"], [0, 1], [0, 0], want_ient=True)
+    r = engine.align(["", "ACGT"], ["ACGTAC"], [0, 1], [0, 0], detail=True)
     assert (r["score"][0], r["matches"][0], r["start"][0], r["end"][0], r["ient"][0]) == (-7, 0, 0, 6, 0)
     with pytest.raises(IgdError):
         engine.align(["A" * 1024], ["ACGT"], [0], [0])
@@ -140,7 +144,11 @@ def test_align_other_schemes(engine):
                    t_left_open=sc["to"], t_left_ext=sc["te"], t_right_open=sc["to"], t_right_ext=sc["te"],
                    q_int_open=sc["qo"], q_int_ext=sc["qe"], q_left_open=sc["qeo"], q_left_ext=sc["qee"],
                    q_right_open=sc["qeo"], q_right_ext=sc["qee"])
-        got = engine.align(targets, queries, pt, pq, scoring=gsc, want_ient=True)
         want = O.align_stats(targets, queries, pt, pq, scoring=osc, threads=8)
+        got = engine.align(targets, queries, pt, pq, scoring=gsc, detail=True)
         for k in KEYS:
             assert np.array_equal(got[k], want[k].astype(np.int64)), (sc, k)
+        fast = engine.align(targets, queries, pt, pq, scoring=gsc)
+        assert np.array_equal(fast["score"], want["score"].astype(np.int64)), sc
+        assert np.array_equal(fast["matches"], want["matches"]), sc
+        assert np.array_equal(fast["alen"], want["end"] - want["start"]), sc
