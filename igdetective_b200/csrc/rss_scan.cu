@@ -14,27 +14,32 @@
 //   strand -, nonamer first              :  nonamer n=q+7+s' selects q iff (q-1 | q+1,q+2) miss
 // with s' tried in the order s, s-1, s+1 (:162-168).
 //
-// Data movement: a persistent CTA walks tiles of 512 chunks (32 Kbases, 8 KB of planes); each
-// tile plus one halo chunk per side arrives in shared memory by one TMA bulk copy
-// (cp.async.bulk + mbarrier, 3 stages in flight), so every base is read from HBM once
-// (0.25 B/base).
-// Phase A, one 64-base chunk per thread, is bit-parallel on the planes: every heptamer of the
+// Data movement: a persistent CTA (8 warps) walks tiles of 512 chunks (32 Kbases, 8 KB of
+// planes); each tile plus one halo chunk per side arrives in shared memory by one TMA bulk copy
+// (cp.async.bulk + mbarrier; 3 stages, full/empty barrier pairs), so every base is read from
+// HBM once (0.25 B/base).  There is no CTA-wide barrier in the loop: each warp owns two rows of
+// 32 chunks per tile and releases the stage as soon as it has read them.
+// Phase A, one 64-base chunk per lane, is bit-parallel on the planes: every heptamer of the
 // shipped motif file (both strands) agrees with the consensus CAC.GTG in at least 4 of its 6
 // fixed positions, so a bit-sliced population count of the six letter-match planes, thresholded
 // at 4, passes every possible heptamer hit and only ~3.8 % of random positions (igd_set_motifs
 // verifies that property for the tables it is given; tables that break it use the exhaustive
-// variant of the same kernel).  Survivors are looked up in the exact 7-mer flag table in shared
-// memory; real heptamer hits (~1 % of positions) go to a shared-memory queue.
-// Phase B pairs the queued heptamers with all lanes busy.
+// instance of the same kernel).  Survivors are looked up in the exact 7-mer flag table in shared
+// memory; real heptamer hits (~1 % of positions) are compacted into a per-warp queue.
+// Phase B runs whenever a warp has 32 queued hits, so all lanes are busy: it re-reads the few
+// words it needs through L2 (the stage may already be recycled) and pairs heptamer and nonamers.
 #include "common.cuh"
 
 namespace {
 
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int ROWS_PER_WARP = IGD_TILE_CHUNKS / 32 / SCAN_WARPS;      // 2
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = IGD_STAGE_CHUNKS * 16;          // 8224
 constexpr int STAGE_STRIDE = 8320;                          // 128-byte aligned
-constexpr int QCAP = 2048;
-constexpr int INVSUM_WORDS = IGD_TILE_CHUNKS / 32 + 1;
+constexpr int WQCAP = 128;                                  // per-warp hit queue (flushes in rounds of 32)
+constexpr int IQCAP = 288;                                  // per-warp (hit, window) items: < 32 waiting + 32 hits x 8 windows
 
 struct ScanParams {
     const uint4 *planes;
@@ -45,6 +50,9 @@ struct ScanParams {
     const uint32_t *any9;
     unsigned long long n_tiles;
     int sp[4];
+    int nwin;                      // distinct (side, spacer) nonamer windows, <= 8
+    int woff[8];                   // first candidate nonamer start relative to the heptamer start
+    unsigned wmask[8];             // heptamer flag bits whose nonamers live in that window
     unsigned long long *hits;
     unsigned long long cap;
     unsigned long long *count;
@@ -60,6 +68,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -73,60 +85,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
     return ok != 0;
 }
 
-struct TileCtx {
-    const uint32_t *sw;            // stage words: record r = {lo0, lo1, hi0, hi1} at sw[4r..4r+3]
-    const uint8_t *s_lut7;
-    const uint32_t *s_invsum;      // validity summary bits of the stage's chunks
-    unsigned long long g0;         // global base index of stage position 0
-};
+// ---- phase B helpers: everything addressed by global base index g, read through L1/L2 ---------
 
-// 32 consecutive positions of one bit-plane starting at stage position p (plane = 0 lo, 2 hi)
-__device__ __forceinline__ uint32_t win32(const uint32_t *sw, int p, int plane)
+// 32 consecutive positions of both bit-planes starting at global position g: two 16-byte record
+// loads (through L1/L2), then a funnel shift per plane
+__device__ __forceinline__ void gwin32x2(const ScanParams &P, unsigned long long g, unsigned &lo, unsigned &hi)
 {
-    const int b0 = p >> 5, b1 = b0 + 1;
-    const uint32_t a = sw[4 * (b0 >> 1) + (b0 & 1) + plane];
-    const uint32_t b = sw[4 * (b1 >> 1) + (b1 & 1) + plane];
-    return __funnelshift_r(a, b, p & 31);
+    const unsigned rec = (unsigned)(g >> 6);                 // < 2^32 chunks
+    const uint4 r0 = __ldg(&P.planes[rec]);
+    const uint4 r1 = __ldg(&P.planes[rec + 1]);
+    const bool up = (g >> 5) & 1ull;
+    const unsigned sh = (unsigned)g & 31u;
+    lo = __funnelshift_r(up ? r0.y : r0.x, up ? r1.x : r0.y, sh);
+    hi = __funnelshift_r(up ? r0.w : r0.z, up ? r1.z : r0.w, sh);
 }
 
-// true iff no base of stage window [x, x+k) is marked invalid
-__device__ __forceinline__ bool window_valid(const ScanParams &P, const TileCtx &T, int x, int k)
+// true iff no base of [g, g+k) is marked invalid
+__device__ __forceinline__ bool window_valid(const ScanParams &P, unsigned long long g, int k)
 {
-    const int c0 = x >> 6, c1 = (x + k - 1) >> 6, b0 = x & 63;
-    if ((T.s_invsum[c0 >> 5] >> (c0 & 31)) & 1u) {
-        const unsigned long long m = __ldg(&P.inv[(T.g0 >> 6) + c0]);
+    const unsigned long long c0 = g >> 6, c1 = (g + k - 1) >> 6;
+    const int b0 = (int)(g & 63);
+    if ((__ldg(&P.invsum[c0 >> 5]) >> (c0 & 31)) & 1u) {
+        const unsigned long long m = __ldg(&P.inv[c0]);
         const int n0 = (b0 + k > 64) ? 64 - b0 : k;
         if (m & (((1ull << n0) - 1ull) << b0)) return false;
     }
-    if (c1 != c0 && ((T.s_invsum[c1 >> 5] >> (c1 & 31)) & 1u)) {
-        const unsigned long long m = __ldg(&P.inv[(T.g0 >> 6) + c1]);
+    if (c1 != c0 && ((__ldg(&P.invsum[c1 >> 5]) >> (c1 & 31)) & 1u)) {
+        const unsigned long long m = __ldg(&P.inv[c1]);
         if (m & ((1ull << (b0 + k - 64)) - 1ull)) return false;
     }
     return true;
 }
 
-// heptamer flags at stage position x (0 if the window holds an invalid base)
-__device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const TileCtx &T, int x)
+// heptamer flags at g (0 if the window holds an invalid base)
+__device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const uint8_t *s_lut7, unsigned long long g)
 {
-    const unsigned lo = win32(T.sw, x, 0) & 127u, hi = win32(T.sw, x, 2) & 127u;
-    const unsigned f = T.s_lut7[(hi << 7) | lo];
+    unsigned lo, hi;
+    gwin32x2(P, g, lo, hi);
+    const unsigned f = s_lut7[((hi & 127u) << 7) | (lo & 127u)];
     if (!f) return 0;
-    return window_valid(P, T, x, 7) ? f : 0;
-}
-
-// flags of the three nonamers starting at x, x+1, x+2 (the spacers s+1, s, s-1 or s-1, s, s+1 of
-// one heptamer), masked by `bit`, validity included: bit i of the result = nonamer x+i qualifies
-__device__ __forceinline__ unsigned nona3(const ScanParams &P, const TileCtx &T, int x, unsigned bit)
-{
-    const unsigned lo = win32(T.sw, x, 0), hi = win32(T.sw, x, 2);
-    unsigned r = 0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const unsigned idx = (((hi >> i) & 511u) << 9) | ((lo >> i) & 511u);
-        if ((__ldg(&P.any9[idx >> 5]) >> (idx & 31)) & 1u)
-            if ((__ldg(&P.lut9[idx]) & bit) && window_valid(P, T, x + i, 9)) r |= 1u << i;
-    }
-    return r;
+    return window_valid(P, g, 7) ? f : 0;
 }
 
 __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq, int t, int strand, int d)
@@ -135,51 +133,108 @@ __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq,
     if (i < P.cap) P.hits[i] = (gq << 8) | ((unsigned long long)t << 4) | ((unsigned long long)strand << 3) | (unsigned long long)d;
 }
 
-// all RSSs whose heptamer starts at stage position q; f = LUT flags of that heptamer
-__device__ __noinline__ void eval_heptamer(const ScanParams &P, const TileCtx &T, int q, unsigned f)
+// Rare path: window w of heptamer gq (flags f) has at least one nonamer carrying a wanted flag.
+// nf[i] = 9-mer flags at window position i (i = 0,1,2 ascending).  Applies the reference's ranking.
+__device__ __noinline__ void resolve_window(const ScanParams &P, const uint8_t *s_lut7, unsigned long long gq,
+                                            unsigned fm, int w, unsigned nf0, unsigned nf1, unsigned nf2)
 {
-    if (!window_valid(P, T, q, 7)) return;
-    const unsigned long long gq = T.g0 + q;
+    if (!window_valid(P, gq, 7)) return;
+    const unsigned long long x = gq + (long long)P.woff[w];
+    if (nf0 && !window_valid(P, x, 9)) nf0 = 0;
+    if (nf1 && !window_valid(P, x + 1, 9)) nf1 = 0;
+    if (nf2 && !window_valid(P, x + 2, 9)) nf2 = 0;
+    const bool right = P.woff[w] > 0;
     unsigned hm2 = 0, hm1 = 0, hp1 = 0, hp2 = 0; bool have_nb = false;
-#pragma unroll 1
-    for (int t = 0; t < 4; ++t) {
-        const unsigned bF = 1u << t, bR = 16u << t;
-        if (!(f & (bF | bR))) continue;
-        const int s = P.sp[t];
+    while (fm) {
+        const int fb = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const unsigned bit = 1u << fb;
+        const unsigned n = ((nf0 & bit) ? 1u : 0u) | ((nf1 & bit) ? 2u : 0u) | ((nf2 & bit) ? 4u : 0u);
+        if (!n) continue;
+        const int t = fb & 3, strand = fb >> 2;
         const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
-        if (hept_first) {
-            if (f & bF) {              // nonamers at q+7+{s-1, s, s+1} = bits 0,1,2; priority s, s-1, s+1
-                const unsigned n = nona3(P, T, q + 7 + s - 1, bF);
-                if (n) emit(P, gq, t, 0, (n & 2u) ? 0 : ((n & 1u) ? 1 : 2));
-            }
-            if (f & bR) {              // nonamers at q-9-{s+1, s, s-1} = bits 0,1,2
-                const unsigned n = nona3(P, T, q - 9 - s - 1, bR);
-                if (n) emit(P, gq, t, 1, (n & 2u) ? 0 : ((n & 4u) ? 1 : 2));
-            }
-        } else {
-            if (!have_nb) {
-                hm2 = hept_flags(P, T, q - 2); hm1 = hept_flags(P, T, q - 1);
-                hp1 = hept_flags(P, T, q + 1); hp2 = hept_flags(P, T, q + 2);
+        // window positions ascend; on the right they are spacers s-1, s, s+1, on the left s+1, s, s-1
+        const unsigned bm = right ? 1u : 4u, bp = right ? 4u : 1u;
+        if (hept_first) {                                      // the heptamer picks: s, then s-1, then s+1
+            emit(P, gq, t, strand, (n & 2u) ? 0 : ((n & bm) ? 1 : 2));
+        } else {                                               // each nonamer picks its best-ranked heptamer
+            if (!have_nb && (n & 5u)) {
+                hm2 = hept_flags(P, s_lut7, gq - 2); hm1 = hept_flags(P, s_lut7, gq - 1);
+                hp1 = hept_flags(P, s_lut7, gq + 1); hp2 = hept_flags(P, s_lut7, gq + 2);
                 have_nb = true;
             }
-            if (f & bF) {              // nonamer p = q-9-s' ranks its heptamers p+9+s, +s-1, +s+1
-                const unsigned n = nona3(P, T, q - 9 - s - 1, bF);     // bits: s+1, s, s-1
-                if (n & 2u) emit(P, gq, t, 0, 0);
-                if ((n & 4u) && !(hp1 & bF)) emit(P, gq, t, 0, 1);
-                if ((n & 1u) && !(hm1 & bF) && !(hm2 & bF)) emit(P, gq, t, 0, 2);
-            }
-            if (f & bR) {              // reverse strand: nonamer n = q+7+s' ranks heptamers n-s-7, +1, -1
-                const unsigned n = nona3(P, T, q + 7 + s - 1, bR);     // bits: s-1, s, s+1
-                if (n & 2u) emit(P, gq, t, 1, 0);
-                if ((n & 1u) && !(hm1 & bR)) emit(P, gq, t, 1, 1);
-                if ((n & 4u) && !(hp1 & bR) && !(hp2 & bR)) emit(P, gq, t, 1, 2);
+            if (n & 2u) emit(P, gq, t, strand, 0);
+            if (strand == 0) {      // nonamer p = q-9-s' ranks heptamers p+9+s, +s-1, +s+1
+                if ((n & bm) && !(hp1 & bit)) emit(P, gq, t, 0, 1);
+                if ((n & bp) && !(hm1 & bit) && !(hm2 & bit)) emit(P, gq, t, 0, 2);
+            } else {                // reverse strand: nonamer n = q+7+s' ranks heptamers n-s-7, +1, -1
+                if ((n & bm) && !(hm1 & bit)) emit(P, gq, t, 1, 1);
+                if ((n & bp) && !(hp1 & bit) && !(hp2 & bit)) emit(P, gq, t, 1, 2);
             }
         }
     }
 }
 
-// positions of word (w, next) whose 7-mer matches CAC.GTG in at least 4 of the 6 fixed positions.
-// A/C/G/T = letter indicator planes of the word, nA.. = of the following word.
+// One (heptamer, window) work item: probe the three adjacent 9-mers of window w next to heptamer
+// gq; fm = the heptamer's flag bits served by that window.  Validity is checked on the rare path.
+__device__ __forceinline__ void probe_window(const ScanParams &P, const uint8_t *s_lut7, unsigned long long item)
+{
+    const unsigned long long gq = item & 0xffffffffffffull;
+    const int w = (int)(item >> 48) & 7;
+    const unsigned fm = (unsigned)(item >> 56);
+    unsigned lo, hi;
+    gwin32x2(P, gq + (long long)P.woff[w], lo, hi);
+    unsigned nf[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const unsigned idx = (((hi >> i) & 511u) << 9) | ((lo >> i) & 511u);
+        nf[i] = 0;
+        if ((__ldg(&P.any9[idx >> 5]) >> (idx & 31)) & 1u) nf[i] = __ldg(&P.lut9[idx]);
+    }
+    if ((nf[0] | nf[1] | nf[2]) & fm) resolve_window(P, s_lut7, gq, fm, w, nf[0], nf[1], nf[2]);
+}
+
+// Phase B for one round of up to 32 queued heptamer hits (lane < take holds one): look up the
+// heptamer's flags, expand into one item per window that serves any of them, and probe items 32 at
+// a time so that every lane does useful work.  ni = items waiting in iq (warp-uniform).
+__device__ __noinline__ int phase_b(const ScanParams &P, const uint8_t *s_lut7, unsigned long long *iq, int ni,
+                                   unsigned long long gq, bool active, bool drain)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned f = 0, need = 0;
+    if (active) {
+        unsigned lo, hi;
+        gwin32x2(P, gq, lo, hi);
+        f = s_lut7[((hi & 127u) << 7) | (lo & 127u)];
+        for (int w = 0; w < P.nwin; ++w) need |= (f & P.wmask[w]) ? (1u << w) : 0u;
+    }
+    const int cnt = __popc(need);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+    int off = ni + incl - cnt;
+    while (need) {
+        const int w = __ffs(need) - 1;
+        need &= need - 1;
+        iq[off++] = gq | ((unsigned long long)w << 48) | ((unsigned long long)(f & P.wmask[w]) << 56);
+    }
+    ni += tot;
+    __syncwarp();
+    while (ni >= 32 || (drain && ni > 0)) {
+        const int take = min(ni, 32);
+        ni -= take;
+        if ((int)lane < take) probe_window(P, s_lut7, iq[ni + lane]);
+        __syncwarp();
+    }
+    return ni;
+}
+
+// ---- phase A helpers ---------------------------------------------------------------------------
+// positions of word (w, next) whose 7-mer matches CAC.GTG in at least 4 of the 6 fixed positions
 struct Ind { uint32_t a, c, g, t; };
 __device__ __forceinline__ Ind indicators(uint32_t lo, uint32_t hi)
 {
@@ -199,24 +254,42 @@ __device__ __forceinline__ uint32_t consensus_ge4(const Ind &w, const Ind &n)
     return (c1 & c2) | (c3 & (c1 | c2));          // ones + 2*twos >= 4  <=>  at least two carries
 }
 
+// exact heptamer hits among the candidate positions `m` of one 32-position word
+__device__ __forceinline__ uint32_t lut_filter(uint32_t m, uint32_t l0, uint32_t l1, uint32_t h0, uint32_t h1,
+                                               const uint8_t *s_lut7)
+{
+    uint32_t hit = 0;
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const unsigned lo = __funnelshift_r(l0, l1, b) & 127u;
+        const unsigned hi = __funnelshift_r(h0, h1, b) & 127u;
+        if (s_lut7[(hi << 7) | lo]) hit |= 1u << b;
+    }
+    return hit;
+}
+
 template <bool PREFILTER>
-__global__ void __launch_bounds__(IGD_TILE_CHUNKS, 2)
-rss_scan_kernel(const ScanParams P)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
+rss_scan_kernel(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_stage = smem;                                           // NSTAGE * STAGE_STRIDE
     uint8_t *s_lut7 = smem + NSTAGE * STAGE_STRIDE;                          // 16384
-    uint32_t *s_queue = (uint32_t *)(s_lut7 + 16384);                        // QCAP
-    uint32_t *s_invsum = s_queue + QCAP;                                     // INVSUM_WORDS (+pad)
-    uint64_t *s_bar = (uint64_t *)(s_invsum + 32);                           // NSTAGE
-    unsigned *s_qn = (unsigned *)(s_bar + NSTAGE);
+    unsigned long long *s_wq = (unsigned long long *)(s_lut7 + 16384);       // SCAN_WARPS * WQCAP
+    unsigned long long *s_iq = s_wq + SCAN_WARPS * WQCAP;                    // SCAN_WARPS * IQCAP
+    uint64_t *s_full = (uint64_t *)(s_iq + SCAN_WARPS * IQCAP);              // NSTAGE
+    uint64_t *s_empty = s_full + NSTAGE;                                     // NSTAGE
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        for (int i = 0; i < NSTAGE; ++i) mbar_init(&s_bar[i], 1);
-        *s_qn = 0;
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], SCAN_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    {   // exact 7-mer flag table -> shared memory (L2-resident after the first CTA)
+        const uint4 *src7 = (const uint4 *)P.lut7; uint4 *dst7 = (uint4 *)s_lut7;
+        for (int i = tid; i < 16384 / 16; i += SCAN_THREADS) dst7[i] = __ldg(&src7[i]);
     }
     __syncthreads();
 
@@ -225,79 +298,97 @@ rss_scan_kernel(const ScanParams P)
         for (int i = 0; i < NSTAGE - 1; ++i) {
             const unsigned long long tile = tile0 + (unsigned long long)i * stride;
             if (tile < P.n_tiles) {
-                mbar_expect_tx(&s_bar[i], STAGE_BYTES);
-                bulk_g2s(s_stage + i * STAGE_STRIDE, P.planes + tile * IGD_TILE_CHUNKS, STAGE_BYTES, &s_bar[i]);
+                mbar_expect_tx(&s_full[i], STAGE_BYTES);
+                bulk_g2s(s_stage + i * STAGE_STRIDE, P.planes + tile * IGD_TILE_CHUNKS, STAGE_BYTES, &s_full[i]);
             }
         }
     }
-    {   // exact 7-mer flag table -> shared memory (L2-resident after the first CTA)
-        const uint4 *src7 = (const uint4 *)P.lut7; uint4 *dst7 = (uint4 *)s_lut7;
-        for (int i = tid; i < 16384 / 16; i += IGD_TILE_CHUNKS) dst7[i] = __ldg(&src7[i]);
-    }
-    __syncthreads();
 
+    unsigned long long *wq = s_wq + warp * WQCAP;
+    unsigned long long *iq = s_iq + warp * IQCAP;
+    int nq = 0, ni = 0;                                   // queued hits / items of this warp (warp-uniform)
     unsigned it = 0;
-    for (unsigned long long tile = tile0; tile < P.n_tiles; tile += stride, ++it) {
-        const int stage = it % NSTAGE;
-        const unsigned parity = (it / NSTAGE) & 1u;
-        if (tid == 0) {                                   // refill the stage consumed last iteration
-            const unsigned long long nxt = tile + (unsigned long long)(NSTAGE - 1) * stride;
-            if (nxt < P.n_tiles) {
-                const int ns = (it + NSTAGE - 1) % NSTAGE;
-                mbar_expect_tx(&s_bar[ns], STAGE_BYTES);
-                bulk_g2s(s_stage + ns * STAGE_STRIDE, P.planes + nxt * IGD_TILE_CHUNKS, STAGE_BYTES, &s_bar[ns]);
+    unsigned long long tile = tile0;
+    bool more = tile < P.n_tiles;
+    while (more || nq > 0 || ni > 0) {
+        if (more) {
+            const int stage = it % NSTAGE;
+            const unsigned parity = (it / NSTAGE) & 1u;
+            if (tid == 0) {
+                // producer: refill the stage that was read during iteration it-1, once all warps left it
+                const unsigned long long nxt = tile + (unsigned long long)(NSTAGE - 1) * stride;
+                if (nxt < P.n_tiles) {
+                    const int ns = (it + NSTAGE - 1) % NSTAGE;
+                    if (it >= 1) {
+                        const unsigned ep = ((it - 1) / NSTAGE) & 1u;
+                        while (!mbar_try_wait(&s_empty[ns], ep)) { }
+                    }
+                    mbar_expect_tx(&s_full[ns], STAGE_BYTES);
+                    bulk_g2s(s_stage + ns * STAGE_STRIDE, P.planes + nxt * IGD_TILE_CHUNKS, STAGE_BYTES, &s_full[ns]);
+                }
             }
-        }
-        if (tid < INVSUM_WORDS) s_invsum[tid] = __ldg(&P.invsum[tile * (IGD_TILE_CHUNKS / 32) + tid]);
-        while (!mbar_try_wait(&s_bar[stage], parity)) { }
+            __syncwarp();
+            while (!mbar_try_wait(&s_full[stage], parity)) { }
 
-        const uint32_t *sw = (const uint32_t *)(s_stage + stage * STAGE_STRIDE);
-        TileCtx T;
-        T.sw = sw; T.s_lut7 = s_lut7; T.s_invsum = s_invsum;
-        T.g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);   // stage record 0 = chunk tile*512
-
-        // ---- phase A: heptamer candidates of the 64 windows starting in this thread's chunk
-        {
-            const uint4 r = ((const uint4 *)sw)[tid + 1];
-            const uint4 n = ((const uint4 *)sw)[tid + 2];
-            uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
-            if (PREFILTER) {
-                const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
-                cand0 = consensus_ge4(i0, i1);
-                cand1 = consensus_ge4(i1, i2);
-            }
-            const int p0 = (tid + 1) * 64;
+            const uint4 *rec = (const uint4 *)(s_stage + stage * STAGE_STRIDE);
+            const unsigned long long g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);   // stage record 0
+#pragma unroll 1
+            for (int row = 0; row < ROWS_PER_WARP; ++row) {
+                // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk
+                const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;        // stage record of the chunk
+                uint32_t hit0, hit1;
+                {
+                    const uint4 r = rec[c];
+                    const uint4 n = rec[c + 1];
+                    uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
+                    if (PREFILTER) {
+                        const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
+                        cand0 = consensus_ge4(i0, i1);
+                        cand1 = consensus_ge4(i1, i2);
+                    }
+                    hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
+                    hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
+                }
+                // ---- compaction of the hit positions into the warp queue (nq < 64 on entry; a pass
+                //      queues at most what fits, so pathological densities just take more passes)
+                const unsigned long long gc = g0 + (unsigned long long)c * 64ull;
+                unsigned long long m = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
+                while (__any_sync(0xffffffffu, m != 0ull)) {
+                    const int cnt = __popcll(m);
+                    int incl = cnt;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t l0 = half ? r.y : r.x, l1 = half ? n.x : r.y;
-                const uint32_t h0 = half ? r.w : r.z, h1 = half ? n.z : r.w;
-                uint32_t m = half ? cand1 : cand0;
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const unsigned lo = __funnelshift_r(l0, l1, b) & 127u;
-                    const unsigned hi = __funnelshift_r(h0, h1, b) & 127u;
-                    const unsigned f = s_lut7[(hi << 7) | lo];
-                    if (f) {
-                        const unsigned slot = atomicAdd(s_qn, 1u);
-                        const int q = p0 + half * 32 + b;
-                        if (slot < QCAP) s_queue[slot] = (unsigned)q | (f << 16);
-                        else eval_heptamer(P, T, q, f);
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                    const int space = WQCAP - nq;
+                    int off = incl - cnt;
+                    while (m && off < space) {
+                        const int b = __ffsll((long long)m) - 1;
+                        m &= m - 1;
+                        wq[nq + off] = gc + b;
+                        ++off;
+                    }
+                    nq += min(tot, space);
+                    __syncwarp();
+                    if (nq >= 64) {                       // keep room for the next chunk; full rounds only
+                        nq -= 32;
+                        ni = phase_b(P, s_lut7, iq, ni, wq[nq + lane], true, false);
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);      // this warp no longer needs the stage
+            tile += stride; ++it;
+            more = tile < P.n_tiles;
         }
-        __syncthreads();
-        // ---- phase B: pair the queued heptamers
-        {
-            const unsigned n = min(*s_qn, (unsigned)QCAP);
-            for (unsigned i = tid; i < n; i += IGD_TILE_CHUNKS) {
-                const unsigned e = s_queue[i];
-                eval_heptamer(P, T, (int)(e & 0xffffu), e >> 16);
-            }
+        // ---- phase B: 32 queued heptamers at a time so that every lane is busy (the tail is partial)
+        if (nq >= 32 || !more) {
+            const int take = min(nq, 32);
+            nq -= take;
+            ni = phase_b(P, s_lut7, iq, ni, lane < take ? wq[nq + lane] : 0ull, lane < take, !more && nq == 0);
         }
-        __syncthreads();          // all reads of this stage, the queue and s_invsum are done
-        if (tid == 0) *s_qn = 0;
     }
 }
 
@@ -349,7 +440,7 @@ kmer_scan_kernel(const KmerParams P)
 
 } // namespace
 
-static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + QCAP * 4 + 32 * 4 + NSTAGE * 8 + 16;
+static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + SCAN_WARPS * (WQCAP + IQCAP) * 8 + 2 * NSTAGE * 8 + 16;
 
 int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
 {
@@ -358,16 +449,30 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
     P.lut7 = h->d_lut7; P.lut9 = h->d_lut9; P.any9 = h->d_any9;
     P.n_tiles = h->n_tiles;
     for (int i = 0; i < 4; ++i) P.sp[i] = spacer[i];
+    // one window per distinct (side, spacer): right of the heptamer for (heptamer-first, +) and
+    // (nonamer-first, -), left of it for the other two combinations
+    P.nwin = 0;
+    for (int side = 0; side < 2; ++side)
+        for (int t = 0; t < 4; ++t) {
+            const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
+            const unsigned bit = side == 0 ? (hept_first ? (1u << t) : (16u << t)) : (hept_first ? (16u << t) : (1u << t));
+            const int off = side == 0 ? 7 + spacer[t] - 1 : -9 - spacer[t] - 1;
+            int w = 0;
+            while (w < P.nwin && P.woff[w] != off) ++w;
+            if (w == P.nwin) { P.woff[w] = off; P.wmask[w] = 0; P.nwin++; }
+            P.wmask[w] |= bit;
+        }
+    for (int w = P.nwin; w < 8; ++w) { P.woff[w] = 0; P.wmask[w] = 0; }
     P.hits = h->d_hits; P.cap = h->hit_cap; P.count = h->d_count;
     auto kernel = h->consensus_prefilter ? rss_scan_kernel<true> : rss_scan_kernel<false>;
     IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
     int per_sm = 0;
-    IGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, IGD_TILE_CHUNKS, kScanSmem));
+    IGD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SCAN_THREADS, kScanSmem));
     if (per_sm < 1) per_sm = 1;
     unsigned long long blocks = (unsigned long long)h->sm_count * per_sm;
     if (blocks > h->n_tiles) blocks = h->n_tiles;
     if (blocks < 1) blocks = 1;
-    kernel<<<(unsigned)blocks, IGD_TILE_CHUNKS, kScanSmem, h->stream>>>(P);
+    kernel<<<(unsigned)blocks, SCAN_THREADS, kScanSmem, h->stream>>>(P);
     h->timing.total_launches++;
     IGD_CUDA(cudaGetLastError());
     return IGD_OK;
