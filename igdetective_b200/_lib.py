@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libigd_b200.so")
+LIB_PATH = os.environ.get("IGD_B200_LIB") or os.path.join(_HERE, "libigd_b200.so")
 
 IGD_OK, IGD_ERR_CUDA, IGD_ERR_ARG, IGD_ERR_STATE = 0, -1, -2, -3
 IGD_ERR_TOO_LONG, IGD_ERR_UNSUPPORTED, IGD_ERR_CAPACITY = -4, -5, -6

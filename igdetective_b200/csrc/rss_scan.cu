@@ -270,7 +270,7 @@ __device__ __forceinline__ uint32_t lut_filter(uint32_t m, uint32_t l0, uint32_t
 }
 
 template <bool PREFILTER>
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
 rss_scan_kernel(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];

@@ -60,19 +60,25 @@ class RssScan:
             return self._cache[key]
         t, s = SIGNAL_INDEX[sig_type], (0 if strand == FWD else 1)
         h = self.hits[(self.hits["sig_type"] == t) & (self.hits["strand"] == s)]
+        # hits arrive sorted by (contig, type, strand, scan-order index): one split per contig
+        cuts = np.searchsorted(h["contig"], np.arange(len(self.ids) + 1))
+        hept, nona = h["hept"].tolist(), h["nona"].tolist()
         res = {}
         for ci, cid in enumerate(self.ids):
-            hc = h[h["contig"] == ci]                  # already ascending in scan-order index
-            tuples = [(int(a), int(b)) for a, b in zip(hc["hept"], hc["nona"])]
+            lo, hi = cuts[ci], cuts[ci + 1]
+            if lo == hi:
+                res[cid] = []
+                continue
+            tuples = list(zip(hept[lo:hi], nona[lo:hi]))
             if self.order == "reference" and len(tuples) > 1:
                 k = 7 if HEPT_FIRST[sig_type] else 9
                 L = self.lens[ci]
                 rank = rank_map(self._first_set(sig_type, strand, ci))
-
-                def scan_index(tp):
-                    first = tp[0] if HEPT_FIRST[sig_type] else tp[1]
-                    return first if strand == FWD else L - first - k
-                tuples.sort(key=lambda tp: rank[scan_index(tp)])
+                first = 0 if HEPT_FIRST[sig_type] else 1
+                if strand == FWD:
+                    tuples.sort(key=lambda tp: rank[tp[first]])
+                else:
+                    tuples.sort(key=lambda tp: rank[L - tp[first] - k])
             res[cid] = tuples
         self._cache[key] = res
         return res

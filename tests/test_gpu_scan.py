@@ -137,3 +137,71 @@ def test_scan_sharding_invariance(engine, motifs):
     merged = np.concatenate(parts)
     key = lambda h: sorted(map(tuple, h[["contig", "sig_type", "strand", "hept", "nona", "spacer"]].tolist()))
     assert key(merged) == key(whole)
+
+
+def test_scan_fragmented_assembly(engine, motifs):
+    """config 5 in miniature: thousands of short, skewed-length contigs with RSS units at their edges;
+    every contig up to 20 kb is checked against the oracle, the rest through bounds and ordering"""
+    rng = np.random.default_rng(55)
+    n = 6000
+    lengths = np.minimum((1000 * (1 - rng.random(n)) ** (-1 / 1.1)).astype(np.int64), 2_000_000)
+    lengths[:50] = rng.integers(0, 80, 50)                      # a few degenerate ones
+    contigs, _ = synth.assembly(55, lengths.tolist(), motifs, plant_every=4000)
+    sets = {x: (sorted(motifs[x]["7"]), sorted(motifs[x]["9"])) for x in SIG}
+    for c in contigs[::20]:                                      # units flush with both ends
+        for at_end in (False, True):
+            u = np.frombuffer(synth.rss_unit(rng, motifs, SIG[rng.integers(4)], sets).encode(), np.uint8)
+            if rng.integers(2):
+                u = synth.revcomp_bytes(u)
+            if len(c) >= len(u):
+                p = len(c) - len(u) if at_end else 0
+                c[p:p + len(u)] = u
+    engine.load_contigs([c.tobytes() for c in contigs])
+    h = engine.scan_rss(O.SPACER_LENGTH)
+    L = lengths[h["contig"]]
+    assert np.all(h["hept"] >= 0) and np.all(h["hept"] + 7 <= L)
+    assert np.all(h["nona"] >= 0) and np.all(h["nona"] + 9 <= L)
+    key = h["contig"].astype(np.int64) * 16 + h["sig_type"] * 2 + h["strand"]
+    assert np.all(np.diff(key) >= 0)
+    small = [i for i in range(n) if lengths[i] <= 20_000]
+    seqs = {i: contigs[i].tobytes().decode() for i in small}
+    got = {}
+    for r in h:
+        got.setdefault((int(r["contig"]), SIG[r["sig_type"]], "+-"[r["strand"]]), []).append((int(r["hept"]), int(r["nona"])))
+    nchecked = 0
+    for t in SIG:
+        for sd in "+-":
+            want = O.get_contigwise_rss(t, sd, seqs, motifs, order="canonical")
+            for i in small:
+                assert sorted(got.get((i, t, sd), [])) == sorted(want[i]), (i, t, sd)
+                nchecked += len(want[i])
+    assert nchecked > 300
+
+
+def test_scan_large_properties(engine, motifs):
+    """~0.4 Gb in 40 scaffolds: hit set invariant under reverse complement and under resharding
+    (too big for the CPU oracle, so only size-independent properties are checked)"""
+    rng = np.random.default_rng(77)
+    lengths = (rng.uniform(2e6, 2e7, 40)).astype(np.int64).tolist()
+    contigs, _ = synth.assembly(77, lengths, motifs, plant_every=50_000, n_runs=1, soft_mask=0.1)
+    bs = [c.tobytes() for c in contigs]
+    engine.load_contigs(bs)
+    h = engine.scan_rss(O.SPACER_LENGTH)
+    assert len(h) > 10_000
+    full = set(map(tuple, h[["contig", "sig_type", "strand", "hept", "nona"]].tolist()))
+    assert len(full) == len(h)
+    # reverse complement of every contig
+    engine.load_contigs([synth.revcomp_bytes(c).tobytes() for c in contigs])
+    r = engine.scan_rss(O.SPACER_LENGTH)
+    Lr = np.asarray(lengths)[r["contig"]]
+    mirrored = set(zip(r["contig"].tolist(), r["sig_type"].tolist(), (1 - r["strand"]).tolist(),
+                       (Lr - r["hept"] - 7).tolist(), (Lr - r["nona"] - 9).tolist()))
+    assert mirrored == full
+    # two shards
+    parts = set()
+    for idx in (list(range(0, 40, 2)), list(range(1, 40, 2))):
+        engine.load_contigs([bs[i] for i in idx])
+        p = engine.scan_rss(O.SPACER_LENGTH)
+        parts |= set(zip(np.asarray(idx)[p["contig"]].tolist(), p["sig_type"].tolist(), p["strand"].tolist(),
+                         p["hept"].tolist(), p["nona"].tolist()))
+    assert parts == full
