@@ -32,7 +32,7 @@ int igd_reserve(igd_handle *h, int slot, size_t bytes)
     return IGD_OK;
 }
 
-enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY };
+enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS };
 
 extern "C" {
 
@@ -82,7 +82,7 @@ void igd_destroy(igd_handle *h)
     cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any7);
     cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
     cudaFree(h->d_hits); cudaFree(h->d_count);
-    for (int i = 0; i < 12; ++i) cudaFree(h->d_scratch[i]);
+    for (int i = 0; i < 13; ++i) cudaFree(h->d_scratch[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -449,12 +449,37 @@ int igd_align_batch(igd_handle *h,
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, (size_t)(n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PT], pair_t, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PQ], pair_q, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, h->stream));
+    // two-register kernel: flat lists of pair indices per bucket
     std::vector<int32_t> flat; flat.reserve((size_t)n_pairs);
-    size_t woff[2][NB];
-    for (int k = 0; k < 2; ++k)
-        for (int b = 0; b < NB; ++b) { woff[k][b] = flat.size(); flat.insert(flat.end(), work[k][b].begin(), work[k][b].end()); }
+    size_t woff[NB];
+    for (int b = 0; b < NB; ++b) { woff[b] = flat.size(); flat.insert(flat.end(), work[0][b].begin(), work[0][b].end()); }
     if (!flat.empty())
         IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_WORK], flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    // packed kernel: RUNS = one target against consecutive queries with consecutive output slots.
+    // Maximal runs are cut into chunks small enough to balance the persistent warps (>= ~16 items each).
+    std::vector<int4> runs[NB];
+    size_t roff[NB], nruns_total = 0;
+    for (int b = 0; b < NB; ++b) {
+        const std::vector<int32_t> &w = work[1][b];
+        if (w.empty()) continue;
+        const size_t slots = (size_t)h->sm_count * 16 * (b == 0 ? 4 : 1);       // concurrent groups of lanes
+        const int chunk = (int)std::min<size_t>(64, std::max<size_t>(1, w.size() / (slots * 16)));
+        for (size_t i = 0; i < w.size();) {
+            const int32_t p = w[i];
+            int n = 1;
+            while (i + n < w.size() && n < chunk && w[i + n] == p + n && pair_t[p + n] == pair_t[p] && pair_q[p + n] == pair_q[p] + n) ++n;
+            runs[b].push_back(make_int4(pair_t[p], pair_q[p], n, p));
+            i += n;
+        }
+        nruns_total += runs[b].size();
+    }
+    if (nruns_total) {
+        if ((rc = igd_reserve(h, S_RUNS, nruns_total * sizeof(int4)))) return rc;
+        std::vector<int4> allruns; allruns.reserve(nruns_total);
+        for (int b = 0; b < NB; ++b) { roff[b] = allruns.size(); allruns.insert(allruns.end(), runs[b].begin(), runs[b].end()); }
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], allruns.data(), nruns_total * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));          // allruns is a host temporary
+    }
 
     std::vector<int32_t> h_score((size_t)n_pairs), h_pay((size_t)n_pairs);
     const int passes = ient ? 2 : 1;
@@ -468,8 +493,13 @@ int igd_align_batch(igd_handle *h,
                 job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
                 job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
                 job.d_pair_t = (const int32_t *)h->d_scratch[S_PT]; job.d_pair_q = (const int32_t *)h->d_scratch[S_PQ];
-                job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[k][b];
-                job.n_work = (int32_t)work[k][b].size();
+                if (k == 0) {
+                    job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[b]; job.d_runs = nullptr;
+                    job.n_work = (int32_t)work[0][b].size();
+                } else {
+                    job.d_work = nullptr; job.d_runs = (const int4 *)h->d_scratch[S_RUNS] + roff[b];
+                    job.n_work = (int32_t)runs[b].size();
+                }
                 job.bucket = b; job.mixed_case = mixed; job.packed = (k == 1); job.pay_mode = pass; job.sc = *sc;
                 job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
                 job.d_counter = (unsigned int *)(h->d_count + 8 + k * NB + b);

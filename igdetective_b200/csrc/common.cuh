@@ -57,8 +57,8 @@ struct igd_handle {
     int32_t last_spacer[4] = {0, 0, 0, 0};
 
     // generic growable device scratch for the aligner
-    void *d_scratch[12] = {nullptr};
-    size_t scratch_cap[12] = {0};
+    void *d_scratch[13] = {nullptr};
+    size_t scratch_cap[13] = {0};
 
     igd_timing timing = {};
 };
@@ -84,7 +84,8 @@ struct igd_align_job {
     const uint8_t *d_tgt; const int32_t *d_tgt_off;
     const uint8_t *d_qry; const int32_t *d_qry_off;
     const int32_t *d_pair_t; const int32_t *d_pair_q;
-    const int32_t *d_work;      // pair indices of this bucket
+    const int32_t *d_work;      // pair indices of this bucket (two-register kernel)
+    const int4 *d_runs;         // runs of this bucket (packed kernel): {target, first query, count, first output slot}
     int32_t n_work;
     int bucket;                 // kernel shape selector
     bool mixed_case;

@@ -177,15 +177,20 @@ constexpr int PK_NEG = -2000 * PK_S;
 struct PackedParams {
     const uint8_t *tgt; const int32_t *tgt_off;
     const uint8_t *qry; const int32_t *qry_off;
-    const int32_t *pair_t; const int32_t *pair_q;
-    const int32_t *work; int32_t n_work;
+    const int4 *runs; int32_t n_runs;   // {target, first query, number of consecutive queries, first output slot}
     int inc_match, inc_mismatch;  // score * S + 2 * PR (+1 match for inc_match)
     int to, te;                   // target gap open / extend, * S
     int qio, qie, qeo, qee;       // query internal / end gap open / extend, * S
+    int m_clear, m_pr;            // ~PK_PRMASK and PK_PR as run-time values: (x & m_clear) | m_pr is then ONE LOP3
+    int one;                      // run-time 1: x * one + c is an IMAD on the FMA pipe, off the saturated ALU pipe
     int32_t *out_score; uint32_t *out_pay;
     unsigned int *counter;
 };
 
+// A work item is a RUN: one target against nq consecutive queries of the table.  The lanes sweep
+// the concatenated columns of the whole run, so the systolic pipeline fills and drains once per
+// run instead of once per pair; at a gene boundary a lane stores the result (if it owns row nA)
+// and re-initialises its column state while the lanes below are still finishing the previous gene.
 template <int G, int C, bool MIXED>
 __global__ void __launch_bounds__(GT_THREADS)
 gotoh_packed_kernel(const PackedParams P)
@@ -194,23 +199,28 @@ gotoh_packed_kernel(const PackedParams P)
     const unsigned lane = threadIdx.x & 31u;
     const int l = lane % G;
     const int grp = lane / G;
+    const int m_clear = P.m_clear, m_pr = P.m_pr, one = P.one;
 
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(P.counter, (unsigned)GROUPS_PER_WARP);
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= (unsigned)P.n_work) break;
-        const bool have = base + grp < (unsigned)P.n_work;
-        int pair = 0, nA = 0, nB = 0;
+        if (base >= (unsigned)P.n_runs) break;
+        const bool have = base + grp < (unsigned)P.n_runs;
+        int nA = 0, nB = 1, nq = 0, out = 0, q = 0;
         const uint8_t *A = P.tgt, *B = P.qry;
+        int steps = 0;
         if (have) {
-            pair = P.work[base + grp];
-            const int t = P.pair_t[pair], q = P.pair_q[pair];
-            const int a0 = P.tgt_off[t], b0 = P.qry_off[q];
-            nA = P.tgt_off[t + 1] - a0; nB = P.qry_off[q + 1] - b0;
-            A += a0; B += b0;
+            const int4 run = P.runs[base + grp];
+            const int a0 = P.tgt_off[run.x];
+            nA = P.tgt_off[run.x + 1] - a0;
+            A += a0;
+            q = run.y; nq = run.z; out = run.w;
+            const int b0 = P.qry_off[q];
+            nB = P.qry_off[q + 1] - b0;
+            B += b0;
+            steps = P.qry_off[q + nq] - b0 + G - 1;            // all columns of the run + pipeline depth
         }
-        int steps = have ? nB + G - 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
 
@@ -225,21 +235,26 @@ gotoh_packed_kernel(const PackedParams P)
             D[r] = P.qeo + P.qee * (i - 1) + PK_PR;           // D(i,0) = Ix(i,0), priority 1
             Y[r] = PK_NEG;
         }
-        int diag = (l == 0) ? 0 : (P.qeo + P.qee * (i0 - 1));   // clean D(i0, 0)
+        const int diag0 = (l == 0) ? 0 : (P.qeo + P.qee * (i0 - 1));   // clean D(i0, 0)
+        int diag = diag0;
         int botD = PK_NEG, botX = PK_NEG;
+        const int ls = (nA - 1) / C, rs = (nA - 1) % C;       // lane / row that owns target row nA
+        int j = 0;                                            // columns of the current gene already done
+        bool active = have && nA >= 1;
 
         for (int t = 0; t < steps; ++t) {
             int upD = __shfl_up_sync(0xffffffffu, botD, 1, G);
             int upX = __shfl_up_sync(0xffffffffu, botX, 1, G);
-            const int j = t - l + 1;
-            if (j >= 1 && j <= nB) {
+            if (active && t >= l) {
+                ++j;
                 if (l == 0) { upD = P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j), priority 0
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
                 const bool lastcol = (j == nB);
-                const int qo = lastcol ? P.qeo : P.qio;
-                const int qe = lastcol ? P.qee : P.qie;
-                const int xfix = PK_PR + (lastcol ? 0 : PK_UI);   // priority 1 (+1 internal Ix move)
+                // an Ix move in an internal column counts one internal-Ix unit: the unit rides on the
+                // gap score constants, so both candidates carry it into the max
+                const int qo = lastcol ? P.qeo : P.qio + PK_UI;
+                const int qe = lastcol ? P.qee : P.qie + PK_UI;
                 const int nextdiag = upD & ~PK_PRMASK;
                 int dc = diag, uD = upD, uX = upX;
 #pragma unroll
@@ -252,9 +267,9 @@ gotoh_packed_kernel(const PackedParams P)
                         inc = (a[r] == b) ? P.inc_match : P.inc_mismatch;
                     }
                     const int m = dc + inc;                                            // M(i,j), priority 2
-                    const int x = __viaddmax_s32(uD, qo, uX + qe);                     // Ix(i,j) raw
-                    const int xs = (x & ~PK_PRMASK) + xfix;                            // priority 1, move counted
-                    const int y = __viaddmax_s32(D[r], P.to, Y[r] + P.te) & ~PK_PRMASK; // Iy(i,j), priority 0
+                    const int x = __viaddmax_s32(uD, qo, uX * one + qe);               // Ix(i,j) raw
+                    const int xs = (x & m_clear) | m_pr;                               // priority 1 (one LOP3)
+                    const int y = __viaddmax_s32(D[r], P.to, Y[r] * one + P.te) & ~PK_PRMASK; // Iy(i,j), priority 0
                     const int d = __vimax3_s32(m, xs, y);
                     dc = D[r] & ~PK_PRMASK;
                     D[r] = d; Y[r] = y;
@@ -262,16 +277,26 @@ gotoh_packed_kernel(const PackedParams P)
                 }
                 botD = uD; botX = uX;
                 diag = (l == 0) ? (P.to + P.te * (j - 1)) : nextdiag;
-            }
-        }
-        if (have && nA >= 1) {
-            const int ls = (nA - 1) / C, rs = (nA - 1) % C;
-            if (l == ls) {
-                int k = 0;
+                if (lastcol) {                                // this lane is through with the current gene
+                    if (l == ls) {
+                        int k = 0;
 #pragma unroll
-                for (int r = 0; r < C; ++r) if (r == rs) k = D[r];
-                P.out_score[pair] = k >> 20;
-                P.out_pay[pair] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & 511u) << 10);   // same layout as the wide kernel
+                        for (int r = 0; r < C; ++r) if (r == rs) k = D[r];
+                        P.out_score[out] = k >> 20;
+                        P.out_pay[out] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & 511u) << 10);   // wide-kernel layout
+                    }
+                    ++out; ++q;
+                    if (--nq > 0) {
+                        B += nB;
+                        nB = P.qry_off[q + 1] - P.qry_off[q];
+                        j = 0;
+#pragma unroll
+                        for (int r = 0; r < C; ++r) { D[r] = P.qeo + P.qee * (i0 + r) + PK_PR; Y[r] = PK_NEG; }
+                        diag = diag0;
+                    } else {
+                        active = false;
+                    }
+                }
             }
         }
     }
@@ -280,7 +305,7 @@ gotoh_packed_kernel(const PackedParams P)
 template <int G, int C>
 int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
 {
-    const unsigned warps_needed = (unsigned)((P.n_work + (32 / G) - 1) / (32 / G));
+    const unsigned warps_needed = (unsigned)((P.n_runs + (32 / G) - 1) / (32 / G));
     unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);
     const unsigned cap = (unsigned)h->sm_count * 4u;
     if (blocks > cap) blocks = cap;
@@ -330,12 +355,13 @@ static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
 {
     PackedParams P;
     P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
-    P.pair_t = job.d_pair_t; P.pair_q = job.d_pair_q; P.work = job.d_work; P.n_work = job.n_work;
+    P.runs = job.d_runs; P.n_runs = job.n_work;
     P.inc_match = job.sc.match * PK_S + 2 * PK_PR + 1;
     P.inc_mismatch = job.sc.mismatch * PK_S + 2 * PK_PR;
     P.to = job.sc.target_internal_open * PK_S; P.te = job.sc.target_internal_extend * PK_S;
     P.qio = job.sc.query_internal_open * PK_S; P.qie = job.sc.query_internal_extend * PK_S;
     P.qeo = job.sc.query_end_open * PK_S; P.qee = job.sc.query_end_extend * PK_S;
+    P.m_clear = ~PK_PRMASK; P.m_pr = PK_PR; P.one = 1;
     P.out_score = job.d_score; P.out_pay = job.d_pay; P.counter = job.d_counter;
     switch (job.bucket) {
     case 0: return launch_packed<8, 9>(h, P, job.mixed_case);

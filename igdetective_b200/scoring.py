@@ -88,26 +88,27 @@ def align_fragment_to_genes(fragments, canon_genes, scoring_scheme=None, gene=No
             targets.append(s)
             targets.append(reverse_complement(s))
         return tindex[s]
-    pt = np.zeros((F, G, 2), np.int32)
+    # pairs are laid out [fragment][orientation][gene]: every target meets the genes in table order,
+    # which the C ABI turns into runs for the packed kernel
+    pt = np.zeros((F, 2, G), np.int32)
     for i, f in enumerate(fragments):
         q = str(f).upper()
         if len(q):
             t = tid(q)
-            pt[i, :, 0] = t
-            pt[i, :, 1] = t + 1
+            pt[i, 0, :] = t
+            pt[i, 1, :] = t + 1
         else:                                    # empty fragment -> 'A' * len(gene) (:339-340)
             for j, g in enumerate(genes):
                 t = tid("A" * len(g))
-                pt[i, j, 0] = t
-                pt[i, j, 1] = t + 1
-    pq = np.broadcast_to(np.arange(G, dtype=np.int32)[None, :, None], (F, G, 2))
+                pt[i, 0, j] = t
+                pt[i, 1, j] = t + 1
+    pq = np.broadcast_to(np.arange(G, dtype=np.int32)[None, None, :], (F, 2, G))
     r = engine.align(targets, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
-    m = r["matches"].reshape(F, G, 2)
-    ln = r["alen"].reshape(F, G, 2)
-    fwd = (m[:, :, 0] - 1) > (m[:, :, 1] - 1)
-    pick = np.where(fwd, 0, 1)[:, :, None]
-    mm = np.take_along_axis(m, pick, 2)[:, :, 0]
-    ll = np.take_along_axis(ln, pick, 2)[:, :, 0]
+    m = r["matches"].reshape(F, 2, G)
+    ln = r["alen"].reshape(F, 2, G)
+    fwd = (m[:, 0, :] - 1) > (m[:, 1, :] - 1)
+    mm = np.where(fwd, m[:, 0, :], m[:, 1, :])
+    ll = np.where(fwd, ln[:, 0, :], ln[:, 1, :])
     return pi_from(mm, ll), ll.astype(np.float64)
 
 
