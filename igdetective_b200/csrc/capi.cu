@@ -372,15 +372,22 @@ static bool packed_scheme_ok(const igd_scoring *sc)
     for (int v : g) if (v > 0 || v < -40) return false;
     return sc->match >= -40 && sc->match <= 40 && sc->mismatch >= -40 && sc->mismatch <= 40;
 }
-static bool packed_pair_ok(const igd_scoring *sc, int nA, int nB)
+// 0: two-register kernel, 1: packed short layout, 2: packed long layout (see gotoh.cu)
+static int packed_layout_for(const igd_scoring *sc, int nA, int nB)
 {
-    if (nA > 511 || nB > 511) return false;                       // 9-bit matches / internal-Ix fields
+    if (nB > 511) return 0;                                        // 9-bit matches field
     const int hi = std::max(0, sc->match) * std::min(nA, nB);
-    // every state is at least as good as "row 0 along the query, then straight down" (pure gaps)
-    const int lo = sc->target_internal_open + sc->target_internal_extend * (nB - 1)
-                 + std::min(sc->query_internal_open, sc->query_end_open)
-                 + std::min(sc->query_internal_extend, sc->query_end_extend) * (nA - 1);
-    return hi <= 1900 && lo - 8 * 40 >= -1900;
+    // every state is at least as good as "row 0 along the query, then straight down" (pure gaps) ...
+    int lo = sc->target_internal_open + sc->target_internal_extend * (nB - 1)
+           + std::min(sc->query_internal_open, sc->query_end_open)
+           + std::min(sc->query_internal_extend, sc->query_end_extend) * (nA - 1);
+    // ... and with free query end gaps also as good as "free lead, then the diagonal" (or row 0 first)
+    if (sc->query_end_open == 0 && sc->query_end_extend == 0)
+        lo = std::max(lo, sc->target_internal_open + sc->target_internal_extend * (nB - 1)
+                          + std::min(0, sc->mismatch) * std::min(nA, nB));
+    if (nA <= 511 && hi <= 1900 && lo - 8 * 40 >= -1900) return 1;
+    if (nA <= 1023 && hi <= 900 && lo - 2 * 40 >= -820) return 2;
+    return 0;
 }
 
 int igd_align_batch(igd_handle *h,
@@ -416,7 +423,7 @@ int igd_align_batch(igd_handle *h,
     const bool detail = start || ient;
     const bool packed_ok = !detail && packed_scheme_ok(sc);
     constexpr int NB = 6;
-    std::vector<int32_t> work[2][NB];                  // [packed?][bucket]
+    std::vector<int32_t> work[3][NB];                  // [kernel: 0 two-register, 1 packed short, 2 packed long][bucket]
     std::vector<int64_t> trivial;                      // empty target: closed form
     uint64_t cells = 0;
     for (int64_t p = 0; p < n_pairs; ++p) {
@@ -430,7 +437,9 @@ int igd_align_batch(igd_handle *h,
         }
         if (nA == 0) { trivial.push_back(p); continue; }
         const int b = igd_align_bucket_of(nA);
-        work[(packed_ok && b <= 3 && packed_pair_ok(sc, nA, nB)) ? 1 : 0][b].push_back((int32_t)p);
+        int k = packed_ok ? packed_layout_for(sc, nA, nB) : 0;
+        if ((k == 1 && b > 3) || (k == 2 && b < 4)) k = 0;      // packed kernels exist for shapes 0-3 (short) and 4-5 (long)
+        work[k][b].push_back((int32_t)p);
         cells += (uint64_t)nA * (uint64_t)nB;
     }
     int rc;
@@ -457,10 +466,10 @@ int igd_align_batch(igd_handle *h,
         IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_WORK], flat.data(), flat.size() * 4, cudaMemcpyHostToDevice, h->stream));
     // packed kernel: RUNS = one target against consecutive queries with consecutive output slots.
     // Maximal runs are cut into chunks small enough to balance the persistent warps (>= ~16 items each).
-    std::vector<int4> runs[NB];
+    std::vector<int4> runs[NB];                        // a bucket belongs to one packed layout (0-3 short, 4-5 long)
     size_t roff[NB], nruns_total = 0;
     for (int b = 0; b < NB; ++b) {
-        const std::vector<int32_t> &w = work[1][b];
+        const std::vector<int32_t> &w = work[b <= 3 ? 1 : 2][b];
         if (w.empty()) continue;
         const size_t slots = (size_t)h->sm_count * 16 * (b == 0 ? 4 : 1);       // concurrent groups of lanes
         const int chunk = (int)std::min<size_t>(64, std::max<size_t>(1, w.size() / (slots * 16)));
@@ -484,9 +493,9 @@ int igd_align_batch(igd_handle *h,
     std::vector<int32_t> h_score((size_t)n_pairs), h_pay((size_t)n_pairs);
     const int passes = ient ? 2 : 1;
     for (int pass = 0; pass < passes; ++pass) {
-        IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 2 * NB * sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
         IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < 3; ++k)
             for (int b = 0; b < NB; ++b) {
                 if (work[k][b].empty()) continue;
                 igd_align_job job;
@@ -500,7 +509,7 @@ int igd_align_batch(igd_handle *h,
                     job.d_work = nullptr; job.d_runs = (const int4 *)h->d_scratch[S_RUNS] + roff[b];
                     job.n_work = (int32_t)runs[b].size();
                 }
-                job.bucket = b; job.mixed_case = mixed; job.packed = (k == 1); job.pay_mode = pass; job.sc = *sc;
+                job.bucket = b; job.mixed_case = mixed; job.packed = k; job.pay_mode = pass; job.sc = *sc;
                 job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
                 job.d_counter = (unsigned int *)(h->d_count + 8 + k * NB + b);
                 if ((rc = igd_launch_gotoh(h, job))) return rc;

@@ -89,7 +89,7 @@ struct igd_align_job {
     int32_t n_work;
     int bucket;                 // kernel shape selector
     bool mixed_case;
-    bool packed;                // single-register kernel: (score, matches, internal Ix) only
+    int packed;                 // 0: two-register kernel; 1 / 2: single-register kernel, short / long field layout
     int pay_mode;               // 0: (matches, internal Ix, lead)   1: (matches, internal Ix, trailing Ix)
     igd_scoring sc;
     int32_t *d_score; uint32_t *d_pay;

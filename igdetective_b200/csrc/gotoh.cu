@@ -171,8 +171,16 @@ gotoh_kernel(const GotohParams P)
 // cell instead of 27.  Only (score, matches, alignment length) come out; lead / ient need the
 // two-register kernel above.  The host routes a pair here only if every field provably fits
 // (target <= 511 rows, query <= 511 columns, score bounds inside +-1900, see capi.cu).
-constexpr int PK_S = 1 << 20, PK_PR = 1 << 18, PK_PRMASK = 3 << 18, PK_UI = 1 << 9;
-constexpr int PK_NEG = -2000 * PK_S;
+// Two field layouts (LONG = false / true):
+//   short: score 12 bits | priority 2 | internal Ix 9 | matches 9   target <= 511, query <= 511, |score| <= 1900
+//   long : score 11 bits | priority 2 | internal Ix 10 | matches 9  target <= 1023, query <= 511, |score| <= 900
+template <bool LONG> struct PK {
+    static constexpr int S = LONG ? (1 << 21) : (1 << 20);
+    static constexpr int PR = S >> 2, PRMASK = 3 * PR, UI = 1 << 9;
+    static constexpr int NEG = (LONG ? -900 : -2000) * S;
+    static constexpr int SHIFT = LONG ? 21 : 20;
+    static constexpr unsigned IXMASK = LONG ? 1023u : 511u;
+};
 
 struct PackedParams {
     const uint8_t *tgt; const int32_t *tgt_off;
@@ -191,10 +199,11 @@ struct PackedParams {
 // the concatenated columns of the whole run, so the systolic pipeline fills and drains once per
 // run instead of once per pair; at a gene boundary a lane stores the result (if it owns row nA)
 // and re-initialises its column state while the lanes below are still finishing the previous gene.
-template <int G, int C, bool MIXED>
+template <int G, int C, bool MIXED, bool LONG>
 __global__ void __launch_bounds__(GT_THREADS)
 gotoh_packed_kernel(const PackedParams P)
 {
+    constexpr int PK_PR = PK<LONG>::PR, PK_PRMASK = PK<LONG>::PRMASK, PK_UI = PK<LONG>::UI, PK_NEG = PK<LONG>::NEG;
     constexpr int GROUPS_PER_WARP = 32 / G;
     const unsigned lane = threadIdx.x & 31u;
     const int l = lane % G;
@@ -282,8 +291,8 @@ gotoh_packed_kernel(const PackedParams P)
                         int k = 0;
 #pragma unroll
                         for (int r = 0; r < C; ++r) if (r == rs) k = D[r];
-                        P.out_score[out] = k >> 20;
-                        P.out_pay[out] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & 511u) << 10);   // wide-kernel layout
+                        P.out_score[out] = k >> PK<LONG>::SHIFT;
+                        P.out_pay[out] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & PK<LONG>::IXMASK) << 10);   // wide-kernel layout
                     }
                     ++out; ++q;
                     if (--nq > 0) {
@@ -302,7 +311,7 @@ gotoh_packed_kernel(const PackedParams P)
     }
 }
 
-template <int G, int C>
+template <int G, int C, bool LONG>
 int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
 {
     const unsigned warps_needed = (unsigned)((P.n_runs + (32 / G) - 1) / (32 / G));
@@ -310,8 +319,8 @@ int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
     const unsigned cap = (unsigned)h->sm_count * 4u;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (mixed) gotoh_packed_kernel<G, C, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
-    else       gotoh_packed_kernel<G, C, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    if (mixed) gotoh_packed_kernel<G, C, true, LONG><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    else       gotoh_packed_kernel<G, C, false, LONG><<<blocks, GT_THREADS, 0, h->stream>>>(P);
     h->timing.total_launches++;
     h->timing.align_launches++;
     IGD_CUDA(cudaGetLastError());
@@ -351,25 +360,40 @@ int igd_align_bucket_of(int target_len)
     return -1;
 }
 
+template <bool LONG>
+static void fill_packed(PackedParams &P, const igd_align_job &job)
+{
+    constexpr int S = PK<LONG>::S, PR = PK<LONG>::PR;
+    P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
+    P.runs = job.d_runs; P.n_runs = job.n_work;
+    P.inc_match = job.sc.match * S + 2 * PR + 1;
+    P.inc_mismatch = job.sc.mismatch * S + 2 * PR;
+    P.to = job.sc.target_internal_open * S; P.te = job.sc.target_internal_extend * S;
+    P.qio = job.sc.query_internal_open * S; P.qie = job.sc.query_internal_extend * S;
+    P.qeo = job.sc.query_end_open * S; P.qee = job.sc.query_end_extend * S;
+    P.m_clear = ~PK<LONG>::PRMASK; P.m_pr = PR; P.one = 1;
+    P.out_score = job.d_score; P.out_pay = job.d_pay; P.counter = job.d_counter;
+}
+
 static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
 {
     PackedParams P;
-    P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
-    P.runs = job.d_runs; P.n_runs = job.n_work;
-    P.inc_match = job.sc.match * PK_S + 2 * PK_PR + 1;
-    P.inc_mismatch = job.sc.mismatch * PK_S + 2 * PK_PR;
-    P.to = job.sc.target_internal_open * PK_S; P.te = job.sc.target_internal_extend * PK_S;
-    P.qio = job.sc.query_internal_open * PK_S; P.qie = job.sc.query_internal_extend * PK_S;
-    P.qeo = job.sc.query_end_open * PK_S; P.qee = job.sc.query_end_extend * PK_S;
-    P.m_clear = ~PK_PRMASK; P.m_pr = PK_PR; P.one = 1;
-    P.out_score = job.d_score; P.out_pay = job.d_pay; P.counter = job.d_counter;
-    switch (job.bucket) {
-    case 0: return launch_packed<8, 9>(h, P, job.mixed_case);
-    case 1: return launch_packed<32, 6>(h, P, job.mixed_case);
-    case 2: return launch_packed<32, 11>(h, P, job.mixed_case);
-    case 3: return launch_packed<32, 16>(h, P, job.mixed_case);
+    if (job.packed == 1) {
+        fill_packed<false>(P, job);
+        switch (job.bucket) {
+        case 0: return launch_packed<8, 9, false>(h, P, job.mixed_case);
+        case 1: return launch_packed<32, 6, false>(h, P, job.mixed_case);
+        case 2: return launch_packed<32, 11, false>(h, P, job.mixed_case);
+        case 3: return launch_packed<32, 16, false>(h, P, job.mixed_case);
+        }
+    } else {
+        fill_packed<true>(P, job);
+        switch (job.bucket) {
+        case 4: return launch_packed<32, 25, true>(h, P, job.mixed_case);
+        case 5: return launch_packed<32, 32, true>(h, P, job.mixed_case);
+        }
     }
-    igd_set_error("bad packed align bucket %d", job.bucket);
+    igd_set_error("bad packed align bucket %d (layout %d)", job.bucket, job.packed);
     return IGD_ERR_ARG;
 }
 

@@ -23,6 +23,23 @@ if what == "scan":
     for _ in range(iters):
         n = eng.scan_rss_count(SPACER_LENGTH)
         print("hits", n, eng.timing()["scan_ms"], "ms")
+elif what == "windows":
+    import synth
+    rng = np.random.default_rng(1)
+    genes = list(canon["V"].values())
+    wins = []
+    for i in range(int(mbases)):          # here: number of 800-nt raw-case windows
+        g = genes[rng.integers(len(genes))]
+        w = (synth.background(rng, 300).tobytes().decode() + synth.mutate(rng, g, 0.1, 0.01) + synth.background(rng, 500).tobytes().decode())[:800]
+        if i % 2:
+            w = w[:200] + w[200:500].lower() + w[500:]
+        wins.append(w)
+    pt, pq = [x.ravel() for x in np.meshgrid(np.arange(len(wins)), np.arange(len(genes)), indexing="ij")]
+    for detail in (False, True):
+        for _ in range(iters):
+            eng.align(wins, genes, pt, pq, detail=detail)
+            t = eng.timing()
+            print("windows detail=%s" % detail, t["align_ms"], "ms", t["align_cells"] / t["align_ms"] / 1e6, "GCUPS", t["align_launches"], "launches")
 else:
     import synth
     rng = np.random.default_rng(0)
