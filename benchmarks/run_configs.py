@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Measurements on BASELINE.json configs 3-5 (the bench.py line covers config 2; config 1 is the parity
+suite).  Prints one JSON line per config; run on a B200 box:
+
+    python benchmarks/run_configs.py [--configs 3,4,5] [--scale 1.0] [--device 0]
+
+config 3: ~3 Gb mammalian-shaped assembly (40 SUPER_* scaffolds + 460 unplaced), scanned whole, V/J/D
+          candidates scored vs combined IGHV/IGHJ -- "scan + score a 3 Gb assembly"
+config 4: iterative-mode scoring: candidates (350-nt V flanks / 70-nt J flanks / 800-nt raw-case windows)
+          against ALL V (1172) / J (235) genes of combined_reference_genes, both orientations
+config 5: fragmented assembly: 200 k contigs, Pareto lengths 1 kb-5 Mb
+--scale shrinks the sizes proportionally (1.0 = the sizes of SURVEY.md 8(d)).
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import synth  # noqa: E402
+from igdetective_b200 import datafiles, igdetective  # noqa: E402
+from igdetective_b200.engine import Engine  # noqa: E402
+from igdetective_b200.fasta import reverse_complement  # noqa: E402
+from igdetective_b200.rss import SPACER_LENGTH  # noqa: E402
+from igdetective_b200.scoring import align_fragment_to_genes, window_alignments  # noqa: E402
+
+DATA = os.path.join(ROOT, "tests", "golden", "datafiles")
+
+
+class LazySeq:
+    """str-like view of a uint8 contig: slicing (Python semantics) returns a str, nothing else is copied."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def __len__(self):
+        return len(self.a)
+
+    def __getitem__(self, s):
+        return self.a[s].tobytes().decode("latin-1")
+
+
+def genes(kind):
+    out = {}
+    d = os.path.join(DATA, "combined_reference_genes")
+    for fn in sorted(os.listdir(d)):
+        if fn[3] == kind:
+            from igdetective_b200.fasta import read_fasta
+            for rid, s in read_fasta(os.path.join(d, fn)):
+                if 0 < len(s) <= 511:
+                    out[fn[:4] + "|" + rid] = s.upper()
+    return out
+
+
+def big_assembly(seed, lengths, motifs, canon, clusters, n_runs):
+    rng = np.random.default_rng(seed)
+    contigs = []
+    for L in lengths:
+        buf = np.empty(L, np.uint8)
+        for p in range(0, L, 50_000_000):                     # blockwise: rng.choice makes int64 temporaries
+            n = min(50_000_000, L - p)
+            buf[p:p + n] = synth.background(rng, n)
+        contigs.append(buf)
+    truth = []
+    for (ci, nv, nd, nj) in clusters:
+        L = len(contigs[ci])
+        lo = int(rng.integers(0, max(1, L - 2_000_000)))
+        truth += synth.plant_locus(rng, contigs[ci], motifs, canon["V"], canon["J"], nv, nd, nj, lo, min(L, lo + 2_000_000))
+    for buf in contigs[:40]:
+        for _ in range(n_runs):
+            n = int(rng.integers(100, 50_000))
+            p = int(rng.integers(0, max(1, len(buf) - n)))
+            buf[p:p + n] = ord("N")
+    return contigs, truth
+
+
+def scan_and_score(eng, contigs, ids, canon, label, extra):
+    n_bases = int(sum(len(c) for c in contigs))
+    buf = np.concatenate(contigs) if len(contigs) > 1 else contigs[0]
+    off = np.zeros(len(contigs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in contigs], dtype=np.uint64)
+    seqs = {i: LazySeq(c) for i, c in zip(ids, contigs)}
+    t0 = time.perf_counter()
+    eng.load_contigs((buf, off), ids)
+    t_load = time.perf_counter() - t0
+    pack_ms = eng.timing()["pack_ms"]
+    times = []
+    for _ in range(3):
+        eng.scan_rss_count(SPACER_LENGTH)
+        times.append(eng.timing()["scan_ms"])
+    scan_ms = float(np.median(times))
+    t0 = time.perf_counter()
+    info, rows = igdetective.detect(eng, seqs, canon, order="canonical", load=False)
+    t_detect = time.perf_counter() - t0
+    out = {"config": label, "bases": n_bases, "contigs": len(contigs),
+           "load_h2d_pack_s": t_load, "pack_kernel_ms": pack_ms, "scan_kernel_ms": scan_ms,
+           "scan_gb_per_s_kernel": n_bases / scan_ms / 1e6, "scan_hbm_gbs": n_bases / 4 / scan_ms / 1e6,
+           "scan_plus_scoring_s": t_detect, "whole_job_s": t_load + t_detect,
+           "rss": {st: sum(len(v) for sd in info[st] for v in info[st][sd].values()) for st in info},
+           "rows": {g: len(r) for g, r in rows.items()}}
+    out.update(extra)
+    print(json.dumps(out), flush=True)
+
+
+def config3(eng, motifs, canon, scale):
+    rng = np.random.default_rng(3)
+    sup = np.exp(rng.uniform(np.log(20e6), np.log(250e6), 40))
+    sup = (sup / sup.sum() * 2.9e9 * scale).astype(np.int64)
+    unp = np.exp(rng.uniform(np.log(10e3), np.log(2e6), 460)).astype(np.int64)
+    lengths = sup.tolist() + (unp * min(1.0, scale * 4)).astype(np.int64).tolist()
+    ids = ["SUPER_%d" % (i + 1) for i in range(40)] + ["scaffold_%d" % i for i in range(460)]
+    t0 = time.perf_counter()
+    contigs, truth = big_assembly(3, lengths, motifs, canon, [(i, 60, 6, 3) for i in (2, 7, 11, 23, 31)], 3)
+    scan_and_score(eng, contigs, ids, canon, "3: synthetic mammalian-shaped assembly, whole-genome scan + scoring",
+                   {"generate_s": time.perf_counter() - t0, "planted": len(truth)})
+
+
+def config5(eng, motifs, canon, scale):
+    rng = np.random.default_rng(5)
+    n = int(200_000 * scale)
+    lengths = np.minimum((1000 * (1 - rng.random(n)) ** (-1 / 1.1)).astype(np.int64), 5_000_000)
+    t0 = time.perf_counter()
+    contigs = [synth.background(rng, int(L)) for L in lengths]
+    sets = {x: (sorted(motifs[x]["7"]), sorted(motifs[x]["9"])) for x in synth.SIG}
+    for c in contigs[::20]:                                     # RSS at contig edges in 5 % of contigs
+        u = np.frombuffer(synth.rss_unit(rng, motifs, synth.SIG[rng.integers(4)], sets).encode(), np.uint8)
+        if len(c) >= len(u):
+            p = 0 if rng.integers(2) else len(c) - len(u)
+            c[p:p + len(u)] = u
+    ids = ["ctg%06d" % i for i in range(n)]
+    scan_and_score(eng, contigs, ids, canon, "5: fragmented assembly, skewed contig lengths",
+                   {"generate_s": time.perf_counter() - t0})
+
+
+def config4(eng, canon, scale):
+    rng = np.random.default_rng(4)
+    gv, gj = genes("V"), genes("J")
+    vlist, jlist = list(gv.values()), list(gj.values())
+    n = int(100_000 * scale)
+    nv, nj, nw = n // 4, n // 4, n // 2
+
+    def bg(k):
+        return synth.background(rng, k).tobytes().decode()
+    res = {"config": "4: iterative-mode scoring vs all V (%d) / J (%d) genes of combined_reference_genes" % (len(vlist), len(jlist)),
+           "candidates": {"V_flank_350": nv, "J_flank_70": nj, "window_800": nw}}
+    vf = [(bg(350) + synth.mutate(rng, vlist[rng.integers(len(vlist))], 0.1, 0.01))[-350:] if rng.random() < 0.3 else bg(350)
+          for _ in range(nv)]
+    jf = [(synth.mutate(rng, jlist[rng.integers(len(jlist))], 0.1, 0.01) + bg(70))[:70] if rng.random() < 0.3 else bg(70)
+          for _ in range(nj)]
+    wf = []
+    for i in range(nw):
+        w = (bg(300) + synth.mutate(rng, vlist[rng.integers(len(vlist))], 0.1, 0.01) + bg(500))[:800] if rng.random() < 0.3 else bg(800)
+        if i % 3 == 0:
+            w = w[:250] + w[250:600].lower() + w[600:]          # soft-masked stretch
+        wf.append(w)
+    for name, frs, gl, fn in (("V_flank_350", vf, vlist, "A"), ("J_flank_70", jf, jlist, "A"), ("window_800", wf, list(gv.items()), "B")):
+        c0, m0, wall = eng.align_cells_total, eng.align_ms_total, time.perf_counter()
+        for b0 in range(0, len(frs), 512):                      # batches bound the pair tables (~1.2 M pairs)
+            chunk = frs[b0:b0 + 512]
+            if fn == "A":
+                align_fragment_to_genes(chunk, gl, engine=eng)
+            else:
+                window_alignments(eng, chunk, gl)
+        wall = time.perf_counter() - wall
+        cells, ms = eng.align_cells_total - c0, eng.align_ms_total - m0
+        res[name] = {"cells": int(cells), "kernel_s": ms / 1e3, "gcups_kernel": cells / ms / 1e6 if ms else 0.0,
+                     "wall_s": wall, "gcups_wall": cells / wall / 1e9}
+    print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args()
+    motifs = datafiles.load_motifs(DATA)
+    canon = {g: datafiles.load_canonical_genes("IGH", g, "combined_reference_genes", DATA) for g in ("V", "J")}
+    eng = Engine(a.device, motifs)
+    for c in a.configs.split(","):
+        if c == "3":
+            config3(eng, motifs, canon, a.scale)
+        elif c == "4":
+            config4(eng, canon, a.scale)
+        elif c == "5":
+            config5(eng, motifs, canon, a.scale)

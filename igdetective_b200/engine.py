@@ -57,6 +57,8 @@ class Engine:
         self.contig_lens = np.zeros(0, np.int64)
         self.h2d_bytes = 0          # bytes handed to the C ABI as inputs / read back as results
         self.d2h_bytes = 0
+        self.align_ms_total = 0.0   # running sums over align() calls (device time of the DP kernels, cell updates)
+        self.align_cells_total = 0
         if motifs is not None:
             self.set_motifs(motifs)
 
@@ -158,6 +160,9 @@ class Engine:
             res["start"].ctypes.data if detail else None, res["ient"].ctypes.data if detail else None))
         if detail:
             res["end"] = res["start"] + res["alen"]
+        t = self.timing()
+        self.align_ms_total += t["align_ms"]
+        self.align_cells_total += t["align_cells"]
         self.h2d_bytes += tb.nbytes + to.nbytes + qb.nbytes + qo.nbytes + 3 * pt.nbytes
         self.d2h_bytes += (4 if detail else 2) * 4 * n
         return res
