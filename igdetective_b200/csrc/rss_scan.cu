@@ -26,8 +26,9 @@
 // verifies that property for the tables it is given; tables that break it use the exhaustive
 // instance of the same kernel).  Survivors are looked up in the exact 7-mer flag table in shared
 // memory; real heptamer hits (~1 % of positions) are compacted into a per-warp queue.
-// Phase B runs whenever a warp has 32 queued hits, so all lanes are busy: it re-reads the few
-// words it needs through L2 (the stage may already be recycled) and pairs heptamer and nonamers.
+// Phase B runs on the staged tile too (halo = 64 bases >= the 40-base RSS span): hits are expanded
+// into (heptamer, window) items, 32 items are probed at a time against a shared-memory bitmap of all
+// 9-mers, and only the ~3 % of items that find a 9-mer touch the exact tables and the validity plane.
 #include "common.cuh"
 
 namespace {
@@ -35,6 +36,12 @@ namespace {
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int ROWS_PER_WARP = IGD_TILE_CHUNKS / 32 / SCAN_WARPS;      // 2
+#ifndef SCAN_ANY9_SMEM
+#define SCAN_ANY9_SMEM 0
+#endif
+#ifndef SCAN_MIN_CTAS
+#define SCAN_MIN_CTAS 3
+#endif
 constexpr int NSTAGE = 3;
 constexpr int STAGE_BYTES = IGD_STAGE_CHUNKS * 16;          // 8224
 constexpr int STAGE_STRIDE = 8320;                          // 128-byte aligned
@@ -85,22 +92,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
     return ok != 0;
 }
 
-// ---- phase B helpers: everything addressed by global base index g, read through L1/L2 ---------
+// ---- phase B helpers ----------------------------------------------------------------------------
+struct Stage {
+    const uint32_t *sw;            // stage words: record r = {lo0, lo1, hi0, hi1} at sw[4r..4r+3]
+    const uint8_t *lut7;           // shared-memory copies of the motif tables
+    const uint32_t *any9;
+    unsigned long long g0;         // global base index of stage position 0
+};
 
-// 32 consecutive positions of both bit-planes starting at global position g: two 16-byte record
-// loads (through L1/L2), then a funnel shift per plane
-__device__ __forceinline__ void gwin32x2(const ScanParams &P, unsigned long long g, unsigned &lo, unsigned &hi)
+// 32 consecutive positions of both bit-planes starting at stage position p
+__device__ __forceinline__ void swin32x2(const uint32_t *sw, int p, unsigned &lo, unsigned &hi)
 {
-    const unsigned rec = (unsigned)(g >> 6);                 // < 2^32 chunks
-    const uint4 r0 = __ldg(&P.planes[rec]);
-    const uint4 r1 = __ldg(&P.planes[rec + 1]);
-    const bool up = (g >> 5) & 1ull;
-    const unsigned sh = (unsigned)g & 31u;
-    lo = __funnelshift_r(up ? r0.y : r0.x, up ? r1.x : r0.y, sh);
-    hi = __funnelshift_r(up ? r0.w : r0.z, up ? r1.z : r0.w, sh);
+    const int b0 = p >> 5, b1 = b0 + 1;
+    const int w0 = 4 * (b0 >> 1) + (b0 & 1), w1 = 4 * (b1 >> 1) + (b1 & 1);
+    lo = __funnelshift_r(sw[w0], sw[w1], p & 31);
+    hi = __funnelshift_r(sw[w0 + 2], sw[w1 + 2], p & 31);
 }
 
-// true iff no base of [g, g+k) is marked invalid
+// true iff no base of [g, g+k) is marked invalid (global coordinates; rare path)
 __device__ __forceinline__ bool window_valid(const ScanParams &P, unsigned long long g, int k)
 {
     const unsigned long long c0 = g >> 6, c1 = (g + k - 1) >> 6;
@@ -117,14 +126,14 @@ __device__ __forceinline__ bool window_valid(const ScanParams &P, unsigned long 
     return true;
 }
 
-// heptamer flags at g (0 if the window holds an invalid base)
-__device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const uint8_t *s_lut7, unsigned long long g)
+// heptamer flags at stage position p (0 if the window holds an invalid base)
+__device__ __forceinline__ unsigned hept_flags(const ScanParams &P, const Stage &T, int p)
 {
     unsigned lo, hi;
-    gwin32x2(P, g, lo, hi);
-    const unsigned f = s_lut7[((hi & 127u) << 7) | (lo & 127u)];
+    swin32x2(T.sw, p, lo, hi);
+    const unsigned f = T.lut7[((hi & 127u) << 7) | (lo & 127u)];
     if (!f) return 0;
-    return window_valid(P, g, 7) ? f : 0;
+    return window_valid(P, T.g0 + p, 7) ? f : 0;
 }
 
 __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq, int t, int strand, int d)
@@ -133,11 +142,12 @@ __device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq,
     if (i < P.cap) P.hits[i] = (gq << 8) | ((unsigned long long)t << 4) | ((unsigned long long)strand << 3) | (unsigned long long)d;
 }
 
-// Rare path: window w of heptamer gq (flags f) has at least one nonamer carrying a wanted flag.
-// nf[i] = 9-mer flags at window position i (i = 0,1,2 ascending).  Applies the reference's ranking.
-__device__ __noinline__ void resolve_window(const ScanParams &P, const uint8_t *s_lut7, unsigned long long gq,
+// Rare path: window w of the heptamer at stage position q has at least one nonamer carrying a wanted
+// flag.  nf[i] = 9-mer flags at window position i (ascending).  Applies the reference's ranking.
+__device__ __noinline__ void resolve_window(const ScanParams &P, const Stage &T, int q,
                                             unsigned fm, int w, unsigned nf0, unsigned nf1, unsigned nf2)
 {
+    const unsigned long long gq = T.g0 + q;
     if (!window_valid(P, gq, 7)) return;
     const unsigned long long x = gq + (long long)P.woff[w];
     if (nf0 && !window_valid(P, x, 9)) nf0 = 0;
@@ -159,8 +169,8 @@ __device__ __noinline__ void resolve_window(const ScanParams &P, const uint8_t *
             emit(P, gq, t, strand, (n & 2u) ? 0 : ((n & bm) ? 1 : 2));
         } else {                                               // each nonamer picks its best-ranked heptamer
             if (!have_nb && (n & 5u)) {
-                hm2 = hept_flags(P, s_lut7, gq - 2); hm1 = hept_flags(P, s_lut7, gq - 1);
-                hp1 = hept_flags(P, s_lut7, gq + 1); hp2 = hept_flags(P, s_lut7, gq + 2);
+                hm2 = hept_flags(P, T, q - 2); hm1 = hept_flags(P, T, q - 1);
+                hp1 = hept_flags(P, T, q + 1); hp2 = hept_flags(P, T, q + 2);
                 have_nb = true;
             }
             if (n & 2u) emit(P, gq, t, strand, 0);
@@ -175,37 +185,38 @@ __device__ __noinline__ void resolve_window(const ScanParams &P, const uint8_t *
     }
 }
 
-// One (heptamer, window) work item: probe the three adjacent 9-mers of window w next to heptamer
-// gq; fm = the heptamer's flag bits served by that window.  Validity is checked on the rare path.
-__device__ __forceinline__ void probe_window(const ScanParams &P, const uint8_t *s_lut7, unsigned long long item)
+// One (heptamer, window) work item = stage position | window << 16 | served flag bits << 24: probe the
+// three adjacent 9-mers of that window in the shared-memory bitmap; the exact flags (L2) and the
+// validity plane are touched only when the bitmap says a 9-mer of some set is there (~3 % of items).
+__device__ __forceinline__ void probe_window(const ScanParams &P, const Stage &T, unsigned item)
 {
-    const unsigned long long gq = item & 0xffffffffffffull;
-    const int w = (int)(item >> 48) & 7;
-    const unsigned fm = (unsigned)(item >> 56);
+    const int q = (int)(item & 0xffffu);
+    const int w = (int)(item >> 16) & 7;
+    const unsigned fm = item >> 24;
     unsigned lo, hi;
-    gwin32x2(P, gq + (long long)P.woff[w], lo, hi);
+    swin32x2(T.sw, q + P.woff[w], lo, hi);
     unsigned nf[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const unsigned idx = (((hi >> i) & 511u) << 9) | ((lo >> i) & 511u);
         nf[i] = 0;
-        if ((__ldg(&P.any9[idx >> 5]) >> (idx & 31)) & 1u) nf[i] = __ldg(&P.lut9[idx]);
+        if ((SCAN_ANY9_SMEM ? T.any9[idx >> 5] : __ldg(&T.any9[idx >> 5])) >> (idx & 31) & 1u) nf[i] = __ldg(&P.lut9[idx]);
     }
-    if ((nf[0] | nf[1] | nf[2]) & fm) resolve_window(P, s_lut7, gq, fm, w, nf[0], nf[1], nf[2]);
+    if ((nf[0] | nf[1] | nf[2]) & fm) resolve_window(P, T, q, fm, w, nf[0], nf[1], nf[2]);
 }
 
-// Phase B for one round of up to 32 queued heptamer hits (lane < take holds one): look up the
-// heptamer's flags, expand into one item per window that serves any of them, and probe items 32 at
-// a time so that every lane does useful work.  ni = items waiting in iq (warp-uniform).
-__device__ __noinline__ int phase_b(const ScanParams &P, const uint8_t *s_lut7, unsigned long long *iq, int ni,
-                                   unsigned long long gq, bool active, bool drain)
+// Phase B for one round of up to 32 queued heptamer hits (lane `active` holds stage position q): look
+// up the heptamer's flags, expand into one item per window that serves any of them, and probe items
+// 32 at a time so that every lane does useful work.  ni = items waiting in iq (warp-uniform).
+__device__ __noinline__ int phase_b(const ScanParams &P, const Stage &T, unsigned *iq, int ni,
+                                   int q, bool active, bool drain)
 {
     const unsigned lane = threadIdx.x & 31u;
     unsigned f = 0, need = 0;
     if (active) {
         unsigned lo, hi;
-        gwin32x2(P, gq, lo, hi);
-        f = s_lut7[((hi & 127u) << 7) | (lo & 127u)];
+        swin32x2(T.sw, q, lo, hi);
+        f = T.lut7[((hi & 127u) << 7) | (lo & 127u)];
         for (int w = 0; w < P.nwin; ++w) need |= (f & P.wmask[w]) ? (1u << w) : 0u;
     }
     const int cnt = __popc(need);
@@ -220,14 +231,14 @@ __device__ __noinline__ int phase_b(const ScanParams &P, const uint8_t *s_lut7, 
     while (need) {
         const int w = __ffs(need) - 1;
         need &= need - 1;
-        iq[off++] = gq | ((unsigned long long)w << 48) | ((unsigned long long)(f & P.wmask[w]) << 56);
+        iq[off++] = (unsigned)q | ((unsigned)w << 16) | ((f & P.wmask[w]) << 24);
     }
     ni += tot;
     __syncwarp();
     while (ni >= 32 || (drain && ni > 0)) {
         const int take = min(ni, 32);
         ni -= take;
-        if ((int)lane < take) probe_window(P, s_lut7, iq[ni + lane]);
+        if ((int)lane < take) probe_window(P, T, iq[ni + lane]);
         __syncwarp();
     }
     return ni;
@@ -270,14 +281,20 @@ __device__ __forceinline__ uint32_t lut_filter(uint32_t m, uint32_t l0, uint32_t
 }
 
 template <bool PREFILTER>
-__global__ void __launch_bounds__(SCAN_THREADS, 2)
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
 rss_scan_kernel(const __grid_constant__ ScanParams P)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *s_stage = smem;                                           // NSTAGE * STAGE_STRIDE
     uint8_t *s_lut7 = smem + NSTAGE * STAGE_STRIDE;                          // 16384
-    unsigned long long *s_wq = (unsigned long long *)(s_lut7 + 16384);       // SCAN_WARPS * WQCAP
-    unsigned long long *s_iq = s_wq + SCAN_WARPS * WQCAP;                    // SCAN_WARPS * IQCAP
+#if SCAN_ANY9_SMEM
+    uint32_t *s_any9 = (uint32_t *)(s_lut7 + 16384);                         // 32768
+    unsigned *s_wq = s_any9 + 8192;                                          // SCAN_WARPS * WQCAP
+#else
+    const uint32_t *s_any9 = P.any9;                                         // served by L1
+    unsigned *s_wq = (unsigned *)(s_lut7 + 16384);
+#endif
+    unsigned *s_iq = s_wq + SCAN_WARPS * WQCAP;                              // SCAN_WARPS * IQCAP
     uint64_t *s_full = (uint64_t *)(s_iq + SCAN_WARPS * IQCAP);              // NSTAGE
     uint64_t *s_empty = s_full + NSTAGE;                                     // NSTAGE
 
@@ -287,9 +304,13 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    {   // exact 7-mer flag table -> shared memory (L2-resident after the first CTA)
+    {   // motif tables -> shared memory (L2-resident after the first CTA)
         const uint4 *src7 = (const uint4 *)P.lut7; uint4 *dst7 = (uint4 *)s_lut7;
         for (int i = tid; i < 16384 / 16; i += SCAN_THREADS) dst7[i] = __ldg(&src7[i]);
+#if SCAN_ANY9_SMEM
+        const uint4 *src9 = (const uint4 *)P.any9; uint4 *dst9 = (uint4 *)s_any9;
+        for (int i = tid; i < 32768 / 16; i += SCAN_THREADS) dst9[i] = __ldg(&src9[i]);
+#endif
     }
     __syncthreads();
 
@@ -304,91 +325,86 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         }
     }
 
-    unsigned long long *wq = s_wq + warp * WQCAP;
-    unsigned long long *iq = s_iq + warp * IQCAP;
-    int nq = 0, ni = 0;                                   // queued hits / items of this warp (warp-uniform)
+    unsigned *wq = s_wq + warp * WQCAP;
+    unsigned *iq = s_iq + warp * IQCAP;
     unsigned it = 0;
-    unsigned long long tile = tile0;
-    bool more = tile < P.n_tiles;
-    while (more || nq > 0 || ni > 0) {
-        if (more) {
-            const int stage = it % NSTAGE;
-            const unsigned parity = (it / NSTAGE) & 1u;
-            if (tid == 0) {
-                // producer: refill the stage that was read during iteration it-1, once all warps left it
-                const unsigned long long nxt = tile + (unsigned long long)(NSTAGE - 1) * stride;
-                if (nxt < P.n_tiles) {
-                    const int ns = (it + NSTAGE - 1) % NSTAGE;
-                    if (it >= 1) {
-                        const unsigned ep = ((it - 1) / NSTAGE) & 1u;
-                        while (!mbar_try_wait(&s_empty[ns], ep)) { }
-                    }
-                    mbar_expect_tx(&s_full[ns], STAGE_BYTES);
-                    bulk_g2s(s_stage + ns * STAGE_STRIDE, P.planes + nxt * IGD_TILE_CHUNKS, STAGE_BYTES, &s_full[ns]);
+    for (unsigned long long tile = tile0; tile < P.n_tiles; tile += stride, ++it) {
+        const int stage = it % NSTAGE;
+        const unsigned parity = (it / NSTAGE) & 1u;
+        if (tid == 0) {
+            // producer: refill the stage that was read during iteration it-1, once all warps left it
+            const unsigned long long nxt = tile + (unsigned long long)(NSTAGE - 1) * stride;
+            if (nxt < P.n_tiles) {
+                const int ns = (it + NSTAGE - 1) % NSTAGE;
+                if (it >= 1) {
+                    const unsigned ep = ((it - 1) / NSTAGE) & 1u;
+                    while (!mbar_try_wait(&s_empty[ns], ep)) { }
                 }
+                mbar_expect_tx(&s_full[ns], STAGE_BYTES);
+                bulk_g2s(s_stage + ns * STAGE_STRIDE, P.planes + nxt * IGD_TILE_CHUNKS, STAGE_BYTES, &s_full[ns]);
             }
-            __syncwarp();
-            while (!mbar_try_wait(&s_full[stage], parity)) { }
-
-            const uint4 *rec = (const uint4 *)(s_stage + stage * STAGE_STRIDE);
-            const unsigned long long g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);   // stage record 0
-#pragma unroll 1
-            for (int row = 0; row < ROWS_PER_WARP; ++row) {
-                // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk
-                const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;        // stage record of the chunk
-                uint32_t hit0, hit1;
-                {
-                    const uint4 r = rec[c];
-                    const uint4 n = rec[c + 1];
-                    uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
-                    if (PREFILTER) {
-                        const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
-                        cand0 = consensus_ge4(i0, i1);
-                        cand1 = consensus_ge4(i1, i2);
-                    }
-                    hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
-                    hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
-                }
-                // ---- compaction of the hit positions into the warp queue (nq < 64 on entry; a pass
-                //      queues at most what fits, so pathological densities just take more passes)
-                const unsigned long long gc = g0 + (unsigned long long)c * 64ull;
-                unsigned long long m = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
-                while (__any_sync(0xffffffffu, m != 0ull)) {
-                    const int cnt = __popcll(m);
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += v;
-                    }
-                    const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                    const int space = WQCAP - nq;
-                    int off = incl - cnt;
-                    while (m && off < space) {
-                        const int b = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        wq[nq + off] = gc + b;
-                        ++off;
-                    }
-                    nq += min(tot, space);
-                    __syncwarp();
-                    if (nq >= 64) {                       // keep room for the next chunk; full rounds only
-                        nq -= 32;
-                        ni = phase_b(P, s_lut7, iq, ni, wq[nq + lane], true, false);
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[stage]);      // this warp no longer needs the stage
-            tile += stride; ++it;
-            more = tile < P.n_tiles;
         }
-        // ---- phase B: 32 queued heptamers at a time so that every lane is busy (the tail is partial)
-        if (nq >= 32 || !more) {
+        __syncwarp();
+        while (!mbar_try_wait(&s_full[stage], parity)) { }
+
+        const uint4 *rec = (const uint4 *)(s_stage + stage * STAGE_STRIDE);
+        Stage T;
+        T.sw = (const uint32_t *)rec; T.lut7 = s_lut7; T.any9 = s_any9;
+        T.g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);     // stage record 0 = chunk tile*512
+        int nq = 0, ni = 0;                               // queued hits / items of this warp (warp-uniform)
+#pragma unroll 1
+        for (int row = 0; row < ROWS_PER_WARP; ++row) {
+            // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk
+            const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;        // stage record of the chunk
+            uint32_t hit0, hit1;
+            {
+                const uint4 r = rec[c];
+                const uint4 n = rec[c + 1];
+                uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
+                if (PREFILTER) {
+                    const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
+                    cand0 = consensus_ge4(i0, i1);
+                    cand1 = consensus_ge4(i1, i2);
+                }
+                hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
+                hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
+            }
+            // ---- compaction of the hit positions into the warp queue (a pass queues at most what fits,
+            //      so pathological densities just take more passes)
+            unsigned long long m = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
+            while (__any_sync(0xffffffffu, m != 0ull)) {
+                const int cnt = __popcll(m);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int space = WQCAP - nq;
+                int off = incl - cnt;
+                while (m && off < space) {
+                    const int b = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    wq[nq + off] = (unsigned)(c * 64 + b);
+                    ++off;
+                }
+                nq += min(tot, space);
+                __syncwarp();
+                if (nq >= 64) {                           // keep room for the next chunk; full rounds only
+                    nq -= 32;
+                    ni = phase_b(P, T, iq, ni, (int)wq[nq + lane], true, false);
+                }
+            }
+        }
+        // ---- phase B for what is left of this tile, then release the stage
+        do {
             const int take = min(nq, 32);
             nq -= take;
-            ni = phase_b(P, s_lut7, iq, ni, lane < take ? wq[nq + lane] : 0ull, lane < take, !more && nq == 0);
-        }
+            ni = phase_b(P, T, iq, ni, lane < take ? (int)wq[nq + lane] : 0, lane < take, nq == 0);
+        } while (nq > 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
     }
 }
 
@@ -440,7 +456,7 @@ kmer_scan_kernel(const KmerParams P)
 
 } // namespace
 
-static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + SCAN_WARPS * (WQCAP + IQCAP) * 8 + 2 * NSTAGE * 8 + 16;
+static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + (SCAN_ANY9_SMEM ? 32768 : 0) + SCAN_WARPS * (WQCAP + IQCAP) * 4 + 2 * NSTAGE * 8 + 16;
 
 int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
 {
