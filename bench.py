@@ -205,11 +205,15 @@ def gpu_arm(a):
         # ALU pipe (neither HBM nor tensor); achieved = cell updates/s x ALU-pipe instructions per cell
         "roofline": {"kernel": "gotoh_packed_kernel<32,11>", "bound": "alu", "achieved": kstat["gcups"] * kstat["ops_per_cell"] / 1e3,
                      "peak": int_peak, "unit": "T lane-ops/s", "frac": kstat["gcups"] * kstat["ops_per_cell"] / 1e3 / int_peak,
-                     "traffic": None, "gcups": kstat["gcups"], "alu_ops_per_cell": kstat["ops_per_cell"],
+                     # dram bytes of one launch of this shape from the ncu --set full capture in profiles/ (inputs are KB per pair)
+                     "traffic": 1068288 if a.mbases == 100.0 else None,
+                     "gcups": kstat["gcups"], "alu_ops_per_cell": kstat["ops_per_cell"],
                      "peak_source": "148 SMs x 64 ALU lanes/clk x SM clock sampled during the run"},
         # the HBM-bound kernel of the path (north star: scan vs HBM roofline), 0.25 algorithmic bytes per base
         "roofline_scan": {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+                          "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes": alg_bytes,
+                          # dram__bytes_read+write of one launch, ncu --set full capture in profiles/: equals the algorithmic bytes
+                          "traffic": 25355264 if a.mbases == 100.0 else None,
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
     }
     if not a.no_cpu:
