@@ -173,6 +173,37 @@ def config4(eng, canon, scale):
     print(json.dumps(res), flush=True)
 
 
+def ingest(eng, motifs, canon, scale):
+    """FASTA ingest ("next" row 1): C++ reader + igd_load_fasta vs the Python reader the reference path implies"""
+    import tempfile
+    from igdetective_b200.fasta import NativeFasta, read_fasta
+    rng = np.random.default_rng(9)
+    n = int(1e9 * scale)
+    lengths = [n // 2, n // 4, n // 8, n // 8]
+    path = os.path.join(tempfile.gettempdir(), "igd_ingest_%d.fa" % os.getpid())
+    with open(path, "wb") as f:
+        for i, L in enumerate(lengths):
+            f.write(b">contig_%d synthetic\n" % i)
+            for p in range(0, L, 60_000_000):
+                blk = synth.background(rng, min(60_000_000, L - p))
+                pad = (-len(blk)) % 60
+                rows = np.concatenate([blk, np.full(pad, 32, np.uint8)]).reshape(-1, 60)
+                out = np.concatenate([rows, np.full((len(rows), 1), 10, np.uint8)], axis=1).ravel()
+                f.write(out.tobytes())
+    size = os.path.getsize(path)
+    t0 = time.perf_counter(); nf = NativeFasta(path); t_parse = time.perf_counter() - t0
+    t0 = time.perf_counter(); eng.load_fasta(nf); t_load = time.perf_counter() - t0
+    hits = eng.scan_rss_count(SPACER_LENGTH)
+    t0 = time.perf_counter(); recs = read_fasta(path); t_py = time.perf_counter() - t0
+    ok = [r[0] for r in recs] == nf.ids and all(len(r[1]) == L for r, L in zip(recs, nf.lengths)) \
+        and recs[3][1][-1000:] == nf[nf.ids[3]][-1000:]
+    os.remove(path)
+    print(json.dumps({"config": "ingest: %d-byte FASTA, 60-column lines" % size, "bases": int(sum(nf.lengths)),
+                      "native_parse_s": t_parse, "native_parse_gb_per_s": size / t_parse / 1e9,
+                      "h2d_pack_s": t_load, "python_reader_s": t_py, "python_reader_gb_per_s": size / t_py / 1e9,
+                      "same_records": bool(ok), "rss_hits": int(hits)}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="3,4,5")
@@ -189,3 +220,5 @@ if __name__ == "__main__":
             config4(eng, canon, a.scale)
         elif c == "5":
             config5(eng, motifs, canon, a.scale)
+        elif c == "ingest":
+            ingest(eng, motifs, canon, a.scale)

@@ -6,6 +6,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <unordered_map>
 
 static thread_local std::string g_err;
 
@@ -222,6 +227,111 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     h->contigs_loaded = true;
     h->last_scan_kind = 0;
     return IGD_OK;
+}
+
+// ---- FASTA ingest -----------------------------------------------------------------------------------
+igd_fasta *igd_fasta_open(const char *path)
+{
+    if (!path) { igd_set_error("null path"); return nullptr; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) { igd_set_error("cannot open %s", path); return nullptr; }
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); igd_set_error("cannot stat %s", path); return nullptr; }
+    const size_t fsize = (size_t)st.st_size;
+    const char *data = fsize ? (const char *)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (fsize && data == MAP_FAILED) { igd_set_error("cannot map %s", path); return nullptr; }
+    if (fsize >= 2 && (unsigned char)data[0] == 0x1f && (unsigned char)data[1] == 0x8b) {
+        munmap((void *)data, fsize);
+        igd_set_error("%s is gzip-compressed; igd_fasta_open reads plain FASTA", path); return nullptr;
+    }
+    if (fsize && madvise((void *)data, fsize, MADV_SEQUENTIAL) != 0) { /* advisory only */ }
+    igd_fasta *f = new igd_fasta();
+    std::vector<uint8_t> buf(fsize + 1);                // the letters can never outnumber the file bytes
+    struct Rec { std::string id; uint64_t off, len; };
+    std::vector<Rec> recs;
+    const char *p = data, *end = data + fsize;
+    uint8_t *w = buf.data();
+    bool in_record = false;
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    while (p < end) {
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = nl ? nl : end;                 // line = [p, le)
+        if (p < le && *p == '>') {
+            const char *q = p + 1;
+            while (q < le && blank(*q)) ++q;             // the id is the first token of the header
+            const char *b = q;
+            while (q < le && !blank(*q)) ++q;
+            if (in_record) recs.back().len = (uint64_t)(w - buf.data()) - recs.back().off;
+            recs.push_back({std::string(b, q), (uint64_t)(w - buf.data()), 0});
+            in_record = true;
+        } else if (in_record) {
+            const char *q = p;
+            while (q < le) {                            // copy the runs between blanks
+                const char *s = q;
+                while (q < le && !blank(*q)) ++q;
+                memcpy(w, s, (size_t)(q - s)); w += q - s;
+                while (q < le && blank(*q)) ++q;
+            }
+        }
+        p = nl ? nl + 1 : end;
+    }
+    if (in_record) recs.back().len = (uint64_t)(w - buf.data()) - recs.back().off;
+    if (fsize) munmap((void *)data, fsize);
+    // dict semantics: a repeated id keeps its first position and takes the last sequence
+    std::unordered_map<std::string, size_t> first;
+    std::vector<size_t> order;
+    for (size_t i = 0; i < recs.size(); ++i) {
+        auto it = first.find(recs[i].id);
+        if (it == first.end()) { first.emplace(recs[i].id, order.size()); order.push_back(i); }
+        else order[it->second] = i;
+    }
+    f->off.assign(1, 0);
+    bool in_place = order.size() == recs.size();
+    for (size_t k = 0; k < order.size(); ++k) {
+        const Rec &r = recs[order[k]];
+        f->ids.push_back(r.id);
+        f->off.push_back(f->off.back() + r.len);
+    }
+    if (in_place) {
+        buf.resize((size_t)(w - buf.data()));
+        f->seq.swap(buf);
+    } else {                                            // rare: duplicates -> rebuild in dict order
+        f->seq.resize(f->off.back());
+        for (size_t k = 0; k < order.size(); ++k)
+            memcpy(f->seq.data() + f->off[k], buf.data() + recs[order[k]].off, (size_t)recs[order[k]].len);
+    }
+    return f;
+}
+
+void igd_fasta_close(igd_fasta *f) { delete f; }
+
+int32_t igd_fasta_count(const igd_fasta *f) { return f ? (int32_t)f->ids.size() : 0; }
+
+int igd_fasta_info(const igd_fasta *f, int32_t i, const char **id, uint64_t *length)
+{
+    if (!f || i < 0 || (size_t)i >= f->ids.size()) { igd_set_error("contig index out of range"); return IGD_ERR_ARG; }
+    if (id) *id = f->ids[i].c_str();
+    if (length) *length = f->off[i + 1] - f->off[i];
+    return IGD_OK;
+}
+
+int igd_fasta_read(const igd_fasta *f, int32_t i, uint64_t start, uint64_t len, uint8_t *out)
+{
+    if (!f || i < 0 || (size_t)i >= f->ids.size() || (!out && len)) { igd_set_error("bad arguments to igd_fasta_read"); return IGD_ERR_ARG; }
+    const uint64_t L = f->off[i + 1] - f->off[i];
+    if (start > L || len > L - start) {
+        igd_set_error("slice [%llu, +%llu) outside contig of %llu", (unsigned long long)start, (unsigned long long)len, (unsigned long long)L);
+        return IGD_ERR_ARG;
+    }
+    memcpy(out, f->seq.data() + f->off[i] + start, (size_t)len);
+    return IGD_OK;
+}
+
+int igd_load_fasta(igd_handle *h, const igd_fasta *f)
+{
+    if (!h || !f) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    return igd_load_contigs(h, f->seq.data(), f->off.data(), (int32_t)f->ids.size());
 }
 
 static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint64_t *n_hits)

@@ -21,6 +21,12 @@ constexpr int IGD_CHUNK_BASES = 64;
 constexpr int IGD_TILE_CHUNKS = 512;                  // chunks per scan tile = threads per CTA
 constexpr int IGD_STAGE_CHUNKS = IGD_TILE_CHUNKS + 2; // one halo chunk each side (RSS span <= 40 bases)
 
+struct igd_fasta {
+    std::vector<uint8_t> seq;          // letters of all contigs, concatenated in dict order
+    std::vector<uint64_t> off;         // n + 1 offsets
+    std::vector<std::string> ids;
+};
+
 struct igd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;

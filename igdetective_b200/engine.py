@@ -106,6 +106,14 @@ class Engine:
         self.h2d_bytes += int(off[-1] - off[0]) + off.nbytes
         return n
 
+    def load_fasta(self, fasta):
+        """fasta: a fasta.NativeFasta.  Sends its contigs to the GPU straight from the library's buffer."""
+        _lib.check(self._lib.igd_load_fasta(self._h, fasta._f))
+        self.contig_ids = list(fasta.ids)
+        self.contig_lens = np.asarray(fasta.lengths, np.int64)
+        self.h2d_bytes += int(self.contig_lens.sum()) + 8 * (len(fasta.ids) + 1)
+        return len(fasta.ids)
+
     def scan_rss(self, spacers):
         """spacers: {signal name: length} or 4 ints in (V, D_left, D_right, J) order.
         Returns a HIT_DTYPE array sorted by (contig, sig_type, strand, scan-order index)."""

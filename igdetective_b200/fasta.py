@@ -37,3 +37,84 @@ def fasta_dict(path, upper=False):
     for rid, s in read_fasta(path):
         d[rid] = s.upper() if upper else s
     return d
+
+
+class ContigView:
+    """One contig of a NativeFasta: len() and slicing with Python semantics (negative indices wrap,
+    out-of-range bounds clamp), returning str -- what the reference does with parent_seq[contig]."""
+
+    def __init__(self, owner, index, length):
+        self._o, self._i, self._n = owner, index, length
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, key):
+        if isinstance(key, slice):
+            a, b, step = key.indices(self._n)
+            if step != 1:
+                return str(self)[key]
+            return self._o.read(self._i, a, max(0, b - a))
+        if key < 0:
+            key += self._n
+        return self._o.read(self._i, key, 1)
+
+    def __str__(self):
+        return self._o.read(self._i, 0, self._n)
+
+
+class NativeFasta:
+    """FASTA file parsed by the C++ reader of libigd_b200.so (igd_fasta_*): a read-only mapping
+    {record id: ContigView} in the reference's dict order.  The letters live in host memory owned by
+    the library; Engine.load_fasta(self) sends them to the GPU without a Python copy."""
+
+    def __init__(self, path):
+        import ctypes
+
+        from . import _lib
+        self._lib = _lib.load()
+        self._ct = ctypes
+        self._f = self._lib.igd_fasta_open(str(path).encode())
+        if not self._f:
+            raise _lib.IgdError(_lib.IGD_ERR_ARG, self._lib.igd_last_error().decode("utf-8", "replace"))
+        self.ids, self.lengths = [], []
+        cid, n = ctypes.c_char_p(), ctypes.c_uint64()
+        for i in range(self._lib.igd_fasta_count(self._f)):
+            _lib.check(self._lib.igd_fasta_info(self._f, i, ctypes.byref(cid), ctypes.byref(n)))
+            self.ids.append(cid.value.decode("latin-1"))
+            self.lengths.append(n.value)
+        self._views = {rid: ContigView(self, i, L) for i, (rid, L) in enumerate(zip(self.ids, self.lengths))}
+
+    def read(self, i, start, n):
+        from . import _lib
+        buf = self._ct.create_string_buffer(n) if n else None
+        _lib.check(self._lib.igd_fasta_read(self._f, i, start, n, buf))
+        return buf.raw.decode("latin-1") if n else ""
+
+    def close(self):
+        if getattr(self, "_f", None):
+            self._lib.igd_fasta_close(self._f)
+            self._f = None
+
+    __del__ = close
+
+    def __getitem__(self, rid):
+        return self._views[rid]
+
+    def __iter__(self):
+        return iter(self.ids)
+
+    def __len__(self):
+        return len(self.ids)
+
+    def __contains__(self, rid):
+        return rid in self._views
+
+    def keys(self):
+        return list(self.ids)
+
+    def items(self):
+        return [(r, self._views[r]) for r in self.ids]
+
+    def values(self):
+        return [self._views[r] for r in self.ids]

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import datafiles as dfiles
 from .engine import Engine
-from .fasta import fasta_dict, reverse_complement
+from .fasta import NativeFasta, fasta_dict, reverse_complement
 from .rss import (D, DL, DR, FWD, GENE_LENGTH, J, REV, SIGNAL_TYPES, V, RssScan, combine_D_RSS,
                   get_s_fragment_from_RSS)
 from .scoring import align_fragment_to_genes, compute_alignments
@@ -142,7 +142,8 @@ def run(input_path, output_path, locus="IGH", rss_only=False, engine=None, dataf
     try:
         engine.set_motifs(dfiles.load_motifs(datafiles))
         print("Finding immunoglobulin genes for locus " + locus + "...")
-        input_seq_dict = fasta_dict(input_path)
+        # plain FASTA goes through the native reader (igd_fasta_open); .gz through the Python one
+        input_seq_dict = fasta_dict(input_path) if str(input_path).endswith(".gz") else NativeFasta(input_path)
         canonical = {g: dfiles.load_canonical_genes(locus, g, gene_dir, datafiles) for g in (V, J)}
         os.makedirs(output_path, exist_ok=True)
         print("Finding candidate RSS...", end=" ")

@@ -34,7 +34,10 @@ class RssScan:
         self.spacers = dict(spacers or SPACER_LENGTH)
         self.order = order
         if load:                       # load=False: the caller already put these contigs on the engine
-            engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
+            if hasattr(parent_seq, "_f"):                  # fasta.NativeFasta: no Python copy of the letters
+                engine.load_fasta(parent_seq)
+            else:
+                engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
         self.hits = engine.scan_rss(self.spacers)
         self._kmers = {}
         self._cache = {}

@@ -111,6 +111,21 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9);
  * device and packs to 2-bit planes + validity plane there. */
 int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs);
 
+/* Ingest ("next" row of the scope table): input_seq_dict = {rec.id: rec.seq for rec in
+ * SeqIO.parse(INPUT_PATH, "fasta")} (py/IGDetective.py:129) done natively.  igd_fasta_open parses
+ * an uncompressed FASTA file on the host: id = first whitespace-delimited token of the header,
+ * sequence lines concatenated with blanks / CR / LF removed, case preserved; a repeated id keeps
+ * its first position and takes the last sequence, like the dict comprehension.  The letters stay
+ * in host memory for slicing (igd_fasta_read == parent_seq[contig][a:a+n]); igd_load_fasta copies
+ * them to the device and packs them, like igd_load_contigs.  No GPU is needed to open a file. */
+typedef struct igd_fasta igd_fasta;
+igd_fasta *igd_fasta_open(const char *path);    /* NULL on failure (see igd_last_error) */
+void       igd_fasta_close(igd_fasta *f);
+int32_t    igd_fasta_count(const igd_fasta *f);
+int        igd_fasta_info(const igd_fasta *f, int32_t i, const char **id, uint64_t *length);
+int        igd_fasta_read(const igd_fasta *f, int32_t i, uint64_t start, uint64_t len, uint8_t *out);
+int        igd_load_fasta(igd_handle *h, const igd_fasta *f);
+
 /* find_valid_motif_idx + find_valid_rss over both strands and the four signal
  * types (py/IGDetective.py:138-177, call site :443) in one pass over the packed
  * contigs.  spacer[t] = SPACER_LENGTH of signal type t.  Hits stay on the

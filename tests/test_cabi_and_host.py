@@ -104,3 +104,43 @@ def test_fasta_reader_and_translate():
     for s in ("ATGGCCTAA", "atggcNtga", "ATGNNNAC", "GCNTAR", ""):
         assert translate(s) == O.translate(s)
     assert translate("ATGGCCTAA") == "MA*" and translate("GCN") == "A" and translate("TAR") == "*"
+
+
+def test_native_fasta_reader_equals_oracle(tmp_path):
+    """igd_fasta_open (C++) vs the oracle's restatement of SeqIO.parse on awkward files"""
+    import gzip
+
+    from igdetective_b200._lib import IgdError
+    from igdetective_b200.fasta import NativeFasta
+    cases = {
+        "plain": ">a desc here\nACGT\nacgtn\n>b\nTTTT\n",
+        "crlf": ">a x\r\nACGT\r\nAC GT\r\n\r\n>b\r\nNNNN\r\n",
+        "no_final_newline": ">only\nACGTACGT",
+        "blank_lines_and_tabs": "\n\n>a\tb c\n\nAC\tGT\n  \nGG  \n>empty\n>c\nA\n",
+        "text_before_first_header": "junk line\nACGT\n>a\nCC\n",
+        "duplicate_ids": ">a\nAAAA\n>b\nCC\n>a\nGGGGGG\n>c\nT\n>b\nTTT\n",
+        "empty_id": ">\nACGT\n> spaced id\nGG\n",
+        "empty_file": "",
+    }
+    for name, text in cases.items():
+        p = tmp_path / (name + ".fa")
+        p.write_text(text, newline="")
+        want = O.fasta_dict(str(p))
+        nf = NativeFasta(str(p))
+        assert list(nf) == list(want), name
+        for k in want:
+            assert str(nf[k]) == want[k], (name, k)
+            s = want[k]
+            for a, b in ((0, 3), (-3, None), (2, 100), (-350, 1), (1, -1), (5, 2)):
+                assert nf[k][a:b] == s[a:b], (name, k, a, b)
+        nf.close()
+    # a real locus, byte for byte
+    raw = tmp_path / "cow.fa"
+    raw.write_bytes(gzip.open(golden_input("cow")).read())
+    nf = NativeFasta(str(raw))
+    want = O.fasta_dict(golden_input("cow"))
+    assert list(nf) == list(want) and str(nf[list(want)[0]]) == want[list(want)[0]]
+    with pytest.raises(IgdError):
+        NativeFasta(golden_input("cow"))          # gzip is refused loudly, not misparsed
+    with pytest.raises(IgdError):
+        NativeFasta(str(tmp_path / "missing.fa"))
