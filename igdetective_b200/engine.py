@@ -63,11 +63,15 @@ class Engine:
             self.set_motifs(motifs)
 
     def close(self):
-        if getattr(self, "_h", None):
-            self._lib.igd_destroy(self._h)
-            self._h = None
+        h, self._h = getattr(self, "_h", None), None
+        if h and getattr(self, "_lib", None) is not None:
+            self._lib.igd_destroy(h)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown: the library may already be gone
+            pass
 
     def __enter__(self):
         return self

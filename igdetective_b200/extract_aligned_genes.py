@@ -10,7 +10,7 @@ import pandas as pd
 
 from .datafiles import load_gene_records
 from .engine import Engine
-from .fasta import read_fasta
+from .fasta import NativeFasta, read_fasta
 from .scoring import window_alignments
 
 _BASES = "TCAG"
@@ -106,7 +106,10 @@ def main(genome_fasta, gene_fasta, output_dir, engine=None, sam_file=None, devic
     if len(position_dict) == 0:
         print('no matches were found')
         return
-    contig_dict = {rid: s for rid, s in read_fasta(genome_fasta) if rid in position_dict}
+    if str(genome_fasta).endswith(".gz"):
+        contig_dict = {rid: s for rid, s in read_fasta(genome_fasta) if rid in position_dict}
+    else:                                    # native reader: only the 800-nt windows are ever copied out
+        contig_dict = NativeFasta(genome_fasta)
     genes = load_gene_records(gene_fasta)
     own = engine is None
     if own:

@@ -92,11 +92,15 @@ class NativeFasta:
         return buf.raw.decode("latin-1") if n else ""
 
     def close(self):
-        if getattr(self, "_f", None):
-            self._lib.igd_fasta_close(self._f)
-            self._f = None
+        f, self._f = getattr(self, "_f", None), None
+        if f and getattr(self, "_lib", None) is not None:
+            self._lib.igd_fasta_close(f)
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # interpreter shutdown: the library may already be gone
+            pass
 
     def __getitem__(self, rid):
         return self._views[rid]

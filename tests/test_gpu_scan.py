@@ -205,3 +205,52 @@ def test_scan_large_properties(engine, motifs):
         parts |= set(zip(np.asarray(idx)[p["contig"]].tolist(), p["sig_type"].tolist(), p["strand"].tolist(),
                          p["hept"].tolist(), p["nona"].tolist()))
     assert parts == full
+
+
+def test_scan_arbitrary_motif_tables_and_spacers(motifs):
+    """tables that break the consensus property (-> exhaustive kernel instance) and four different
+    spacers (-> eight distinct nonamer windows): still exact"""
+    from igdetective_b200.engine import Engine
+    rng = np.random.default_rng(123)
+
+    def rand_set(k, n):
+        return {"".join("ACGT"[i] for i in rng.integers(0, 4, k)) for _ in range(n)}
+    custom = {t: {"7": rand_set(7, 60), "9": rand_set(9, 2500)} for t in SIG}
+    custom["V"]["7"] |= {"AAAAAAA", "TTTTTTT"}          # also hit by packed N runs / padding ('A' code)
+    custom["J"]["9"] |= {"AAAAAAAAA"}
+    spacers = {"V": 20, "D_left": 5, "D_right": 9, "J": 14}
+    contigs, _ = synth.assembly(8, [150_000, 777, 20_001], motifs, n_runs=2, soft_mask=0.2)
+    # plant units of the custom sets
+    for c in contigs:
+        for _ in range(len(c) // 400):
+            t = SIG[rng.integers(4)]
+            h = sorted(custom[t]["7"])[rng.integers(len(custom[t]["7"]))]
+            n = sorted(custom[t]["9"])[rng.integers(len(custom[t]["9"]))]
+            sp = "".join("ACGT"[i] for i in rng.integers(0, 4, spacers[t] + int(rng.integers(-1, 2))))
+            u = np.frombuffer((h + sp + n if synth.HEPT_FIRST[t] else n + sp + h).encode(), np.uint8)
+            if rng.integers(2):
+                u = synth.revcomp_bytes(u)
+            if len(c) > len(u):
+                p = int(rng.integers(0, len(c) - len(u)))
+                c[p:p + len(u)] = u
+    seqs = {"c%d" % i: c.tobytes().decode() for i, c in enumerate(contigs)}
+    with Engine(0, custom) as eng:
+        eng.load_contigs(seqs)
+        h = eng.scan_rss(spacers)
+        got = {}
+        for r in h:
+            got.setdefault((int(r["contig"]), SIG[r["sig_type"]], "+-"[r["strand"]]), []).append((int(r["hept"]), int(r["nona"])))
+        total = 0
+        for t in SIG:
+            for sd in "+-":
+                want = O.get_contigwise_rss(t, sd, seqs, custom, order="canonical", spacers=spacers)
+                for ci, c in enumerate(seqs):
+                    assert sorted(got.get((ci, t, sd), [])) == sorted(want[c]), (ci, t, sd)
+                    total += len(want[c])
+        assert total > 200
+        for k in (7, 9):
+            kh = eng.scan_kmers(k)
+            s = seqs["c0"]
+            sel = kh[kh["contig"] == 0]
+            for ti, t in enumerate(SIG):
+                assert sel["pos"][(sel["flags"] >> ti) & 1 == 1].tolist() == O.find_valid_motif_idx(s, custom[t][str(k)], k)
