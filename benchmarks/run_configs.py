@@ -57,25 +57,27 @@ def genes(kind):
     return out
 
 
-def big_assembly(seed, lengths, motifs, canon, clusters, n_runs):
-    rng = np.random.default_rng(seed)
-    contigs = []
-    for L in lengths:
+def big_assembly(seed, lengths, motifs, canon, clusters, n_runs, only=None):
+    """Contig i depends only on (seed, i), so a rank can build just the contigs it owns (`only`)."""
+    contigs, truth = {}, []
+    cl = {ci: (nv, nd, nj) for ci, nv, nd, nj in clusters}
+    for i, L in enumerate(lengths):
+        if only is not None and i not in only:
+            continue
+        rng = np.random.default_rng([seed, i])
         buf = np.empty(L, np.uint8)
         for p in range(0, L, 50_000_000):                     # blockwise: rng.choice makes int64 temporaries
             n = min(50_000_000, L - p)
             buf[p:p + n] = synth.background(rng, n)
-        contigs.append(buf)
-    truth = []
-    for (ci, nv, nd, nj) in clusters:
-        L = len(contigs[ci])
-        lo = int(rng.integers(0, max(1, L - 2_000_000)))
-        truth += synth.plant_locus(rng, contigs[ci], motifs, canon["V"], canon["J"], nv, nd, nj, lo, min(L, lo + 2_000_000))
-    for buf in contigs[:40]:
-        for _ in range(n_runs):
-            n = int(rng.integers(100, 50_000))
-            p = int(rng.integers(0, max(1, len(buf) - n)))
-            buf[p:p + n] = ord("N")
+        if i in cl:
+            lo = int(rng.integers(0, max(1, L - 2_000_000)))
+            truth += synth.plant_locus(rng, buf, motifs, canon["V"], canon["J"], *cl[i], lo, min(L, lo + 2_000_000))
+        if i < 40:
+            for _ in range(n_runs):
+                n = int(rng.integers(100, 50_000))
+                p = int(rng.integers(0, max(1, L - n)))
+                buf[p:p + n] = ord("N")
+        contigs[i] = buf
     return contigs, truth
 
 
@@ -114,10 +116,52 @@ def config3(eng, motifs, canon, scale):
     unp = np.exp(rng.uniform(np.log(10e3), np.log(2e6), 460)).astype(np.int64)
     lengths = sup.tolist() + (unp * min(1.0, scale * 4)).astype(np.int64).tolist()
     ids = ["SUPER_%d" % (i + 1) for i in range(40)] + ["scaffold_%d" % i for i in range(460)]
+    clusters = [(i, 60, 6, 3) for i in (2, 7, 11, 23, 31)]
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        return config3_sharded(eng, motifs, canon, lengths, ids, clusters)
     t0 = time.perf_counter()
-    contigs, truth = big_assembly(3, lengths, motifs, canon, [(i, 60, 6, 3) for i in (2, 7, 11, 23, 31)], 3)
-    scan_and_score(eng, contigs, ids, canon, "3: synthetic mammalian-shaped assembly, whole-genome scan + scoring",
+    contigs, truth = big_assembly(3, lengths, motifs, canon, clusters, 3)
+    scan_and_score(eng, [contigs[i] for i in range(len(lengths))], ids, canon,
+                   "3: synthetic mammalian-shaped assembly, whole-genome scan + scoring",
                    {"generate_s": time.perf_counter() - t0, "planted": len(truth)})
+
+
+def config3_sharded(eng, motifs, canon, lengths, ids, clusters):
+    """The same assembly sharded by contig over the ranks of a torchrun launch (LPT on length): every
+    rank loads, scans and scores its own contigs; rank 0 gathers the row lists.  No data-path collective."""
+    import torch
+    import torch.distributed as dist
+    from igdetective_b200 import shard
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = shard.partition_contigs(lengths, world)[rank]
+    t0 = time.perf_counter()
+    contigs, truth = big_assembly(3, lengths, motifs, canon, clusters, 3, only=set(mine))
+    t_gen = time.perf_counter() - t0
+    local = [contigs[i] for i in mine]
+    buf = np.concatenate(local) if len(local) > 1 else local[0]
+    off = np.zeros(len(local) + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in local], dtype=np.uint64)
+    seqs = {ids[i]: LazySeq(contigs[i]) for i in mine}
+    dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.load_contigs((buf, off), [ids[i] for i in mine])
+    t_load = time.perf_counter() - t0
+    info, rows = igdetective.detect(eng, seqs, canon, order="canonical", load=False)
+    t_job = time.perf_counter() - t0
+    scan_ms = eng.timing()["scan_ms"]
+    merged = shard.gather_rows(rows, ids)
+    t_all = time.perf_counter() - t0
+    stats = torch.tensor([t_job, t_load, scan_ms, float(len(buf)), t_all], dtype=torch.float64, device="cuda")
+    mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({"config": "3 sharded by contig over %d GPUs (LPT), whole-genome scan + scoring" % world,
+                          "bases": int(sm[3].item()), "contigs": len(lengths), "n_gpus": world,
+                          "whole_job_s_max_over_ranks": mx[0].item(), "incl_gather_s": mx[4].item(),
+                          "load_h2d_pack_s_max": mx[1].item(), "scan_kernel_ms_max": mx[2].item(),
+                          "max_shard_bases": int(mx[3].item()), "generate_s": t_gen,
+                          "rows": {g: len(r) for g, r in merged.items()}}), flush=True)
 
 
 def config5(eng, motifs, canon, scale):
@@ -212,6 +256,12 @@ if __name__ == "__main__":
     a = ap.parse_args()
     motifs = datafiles.load_motifs(DATA)
     canon = {g: datafiles.load_canonical_genes("IGH", g, "combined_reference_genes", DATA) for g in ("V", "J")}
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:       # torchrun: one process per GPU
+        import torch
+        import torch.distributed as dist
+        a.device = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(a.device)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", a.device))
     eng = Engine(a.device, motifs)
     for c in a.configs.split(","):
         if c == "3":
@@ -222,3 +272,6 @@ if __name__ == "__main__":
             config5(eng, motifs, canon, a.scale)
         elif c == "ingest":
             ingest(eng, motifs, canon, a.scale)
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
