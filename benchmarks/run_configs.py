@@ -143,6 +143,7 @@ def config3_sharded(eng, motifs, canon, lengths, ids, clusters):
     off = np.zeros(len(local) + 1, np.uint64)
     off[1:] = np.cumsum([len(c) for c in local], dtype=np.uint64)
     seqs = {ids[i]: LazySeq(contigs[i]) for i in mine}
+    shard.gather_rows({"warmup": []}, ids)                 # first object collective pays communicator set-up
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
     eng.load_contigs((buf, off), [ids[i] for i in mine])
