@@ -45,7 +45,7 @@ class IgdError(RuntimeError):
 EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "igd_sync", "igd_get_timing",
            "igd_set_motifs", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
-           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta")
+           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense")
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load():
     lib.igd_fetch_kmer_hits.argtypes = [vp, vp, ctypes.c_uint64]
     lib.igd_align_batch.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, i64,
                                     ctypes.POINTER(Scoring), vp, vp, vp, vp, vp]
+    lib.igd_align_dense.argtypes = [vp, vp, vp, i32, vp, vp, i32, ctypes.POINTER(Scoring), vp, vp, vp]
+    lib.igd_align_dense.restype = ctypes.c_int
     lib.igd_fasta_open.restype = vp
     lib.igd_fasta_open.argtypes = [ctypes.c_char_p]
     lib.igd_fasta_close.restype = None
@@ -85,7 +87,7 @@ def load():
     lib.igd_fasta_info.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_char_p), u64p]
     lib.igd_fasta_read.argtypes = [vp, i32, ctypes.c_uint64, ctypes.c_uint64, vp]
     lib.igd_load_fasta.argtypes = [vp, vp]
-    for name in ("igd_fasta_info", "igd_fasta_read", "igd_load_fasta"):
+    for name in ("igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense"):
         getattr(lib, name).restype = ctypes.c_int
     for name in ("igd_sync", "igd_get_timing", "igd_set_motifs", "igd_load_contigs", "igd_scan",
                  "igd_fetch_hits", "igd_scan_kmers", "igd_fetch_kmer_hits", "igd_align_batch"):

@@ -660,4 +660,121 @@ int igd_align_batch(igd_handle *h,
     return IGD_OK;
 }
 
+// Dense form of igd_align_batch: every target against every query, outputs [n_tgt][n_qry].  This is
+// the shape of align_fragment_to_genes (py/IGDetective.py:335-341) and of the iterative stage's
+// ComputeAlignment (py/extract_aligned_genes.py:89-92); without pair tables the host does no per-pair
+// work and every target becomes runs for the packed kernel.  Falls back to igd_align_batch when some
+// pair does not fit the packed word.
+int igd_align_dense(igd_handle *h,
+                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                    const igd_scoring *sc, int32_t *score, int32_t *matches, int32_t *alen)
+{
+    if (!h || !tgt_off || !qry_off || !sc || n_tgt < 0 || n_qry < 0 || !score) {
+        igd_set_error("bad arguments to igd_align_dense"); return IGD_ERR_ARG;
+    }
+    const int64_t n_pairs = (int64_t)n_tgt * (int64_t)n_qry;
+    if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
+    int max_q = 0, min_q = 1 << 30;
+    for (int q = 0; q < n_qry; ++q) { const int n = qry_off[q + 1] - qry_off[q]; max_q = std::max(max_q, n); min_q = std::min(min_q, n); }
+    bool fast = n_pairs > 0 && min_q >= 1 && max_q <= IGD_MAX_QUERY_LEN && packed_scheme_ok(sc)
+             && sc->target_end_open == sc->target_internal_open && sc->target_end_extend == sc->target_internal_extend
+             && sc->target_internal_extend >= sc->target_internal_open && sc->query_internal_extend >= sc->query_internal_open
+             && sc->query_end_extend >= sc->query_end_open;
+    constexpr int NB = 6;
+    std::vector<int32_t> tl[NB];                       // targets per kernel shape
+    uint64_t cells = 0, qsum = n_qry ? (uint64_t)qry_off[n_qry] - (uint64_t)qry_off[0] : 0;
+    for (int t = 0; t < n_tgt && fast; ++t) {
+        const int nA = tgt_off[t + 1] - tgt_off[t];
+        if (nA < 0 || nA > IGD_MAX_TARGET_LEN) { fast = false; break; }
+        if (nA == 0) continue;
+        const int b = igd_align_bucket_of(nA);
+        // the packed word must hold the longest and the shortest query alike
+        const int k = std::min(packed_layout_for(sc, nA, max_q), packed_layout_for(sc, nA, min_q)) == 0 ? 0
+                    : std::max(packed_layout_for(sc, nA, max_q), packed_layout_for(sc, nA, min_q));
+        if ((b <= 3 && k != 1) || (b >= 4 && k != 2)) { fast = false; break; }
+        tl[b].push_back(t);
+        cells += (uint64_t)nA * qsum;
+    }
+    if (!fast) {                                       // generic path: explicit pair tables
+        std::vector<int32_t> pt((size_t)n_pairs), pq((size_t)n_pairs);
+        for (int t = 0; t < n_tgt; ++t)
+            for (int q = 0; q < n_qry; ++q) { pt[(size_t)t * n_qry + q] = t; pq[(size_t)t * n_qry + q] = q; }
+        return igd_align_batch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, pt.data(), pq.data(), n_pairs, sc,
+                               score, matches, alen, nullptr, nullptr);
+    }
+    IGD_CUDA(cudaSetDevice(h->device));
+    h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
+    bool mixed = false;
+    const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
+    for (size_t i = 0; i < tbytes && !mixed; ++i) mixed = (unsigned)(tgt[i] - 'a') < 26u;
+    for (size_t i = 0; i < qbytes && !mixed; ++i) mixed = (unsigned)(qry[i] - 'a') < 26u;
+    int rc;
+    if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
+    if ((rc = igd_reserve(h, S_TGTOFF, (size_t)(n_tgt + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_QRYOFF, (size_t)(n_qry + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_SCORE, (size_t)n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_PAY, (size_t)n_pairs * 4))) return rc;
+    if (tbytes) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGT], tgt, tbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], tgt_off, (size_t)(n_tgt + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRY], qry, qbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, (size_t)(n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    // runs: each target's query list cut into chunks small enough to balance the persistent warps
+    std::vector<int4> allruns;
+    size_t roff[NB + 1];
+    for (int b = 0; b < NB; ++b) {
+        roff[b] = allruns.size();
+        if (tl[b].empty()) continue;
+        const size_t slots = (size_t)h->sm_count * 16 * (b == 0 ? 4 : 1);
+        const size_t pairs_b = tl[b].size() * (size_t)n_qry;
+        const int chunk = (int)std::min<size_t>(64, std::max<size_t>(1, pairs_b / (slots * 16)));
+        for (int32_t t : tl[b])
+            for (int q0 = 0; q0 < n_qry; q0 += chunk)
+                allruns.push_back(make_int4(t, q0, std::min(chunk, n_qry - q0), (int)((size_t)t * n_qry + q0)));
+    }
+    roff[NB] = allruns.size();
+    if ((rc = igd_reserve(h, S_RUNS, allruns.size() * sizeof(int4)))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], allruns.data(), allruns.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
+    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int b = 0; b < NB; ++b) {
+        if (tl[b].empty()) continue;
+        igd_align_job job;
+        job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
+        job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
+        job.d_pair_t = nullptr; job.d_pair_q = nullptr; job.d_work = nullptr;
+        job.d_runs = (const int4 *)h->d_scratch[S_RUNS] + roff[b];
+        job.n_work = (int32_t)(roff[b + 1] - roff[b]);
+        job.bucket = b; job.mixed_case = mixed; job.packed = b <= 3 ? 1 : 2; job.pay_mode = 0; job.sc = *sc;
+        job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
+        job.d_counter = (unsigned int *)(h->d_count + 8 + job.packed * NB + b);
+        if ((rc = igd_launch_gotoh(h, job))) return rc;
+    }
+    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(score, h->d_scratch[S_SCORE], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int32_t> h_pay((size_t)n_pairs);
+    IGD_CUDA(cudaMemcpyAsync(h_pay.data(), h->d_scratch[S_PAY], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    IGD_CUDA(cudaEventElapsedTime(&h->timing.align_ms, h->ev0, h->ev1));
+    h->timing.align_cells = cells;
+    for (int t = 0; t < n_tgt; ++t) {
+        const int nA = tgt_off[t + 1] - tgt_off[t];
+        const size_t base = (size_t)t * n_qry;
+        for (int q = 0; q < n_qry; ++q) {
+            const int nB = qry_off[q + 1] - qry_off[q];
+            if (nA == 0) {                              // gene row against gaps only (row 0 of the DP)
+                score[base + q] = sc->target_end_open + sc->target_end_extend * (nB - 1);
+                if (matches) matches[base + q] = 0;
+                if (alen) alen[base + q] = nB;
+                continue;
+            }
+            const uint32_t pay = (uint32_t)h_pay[base + q];
+            if (matches) matches[base + q] = (int)(pay & 1023);
+            if (alen) alen[base + q] = nB + ((int)(pay >> 10) & 1023);
+        }
+    }
+    return IGD_OK;
+}
+
 } // extern "C"

@@ -179,6 +179,29 @@ class Engine:
         self.d2h_bytes += (4 if detail else 2) * 4 * n
         return res
 
+    def align_dense(self, targets, queries, scoring=None):
+        """Every target against every query: dict of int32 arrays [T, Q] (score, matches, alen)."""
+        tb, to = targets if isinstance(targets, tuple) else concat(targets)
+        qb, qo = queries if isinstance(queries, tuple) else concat(queries)
+        tb = np.ascontiguousarray(tb, np.uint8)
+        qb = np.ascontiguousarray(qb, np.uint8)
+        to = np.ascontiguousarray(to, np.int32)
+        qo = np.ascontiguousarray(qo, np.int32)
+        T, Q = len(to) - 1, len(qo) - 1
+        sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
+        res = {k: np.zeros((T, Q), np.int32) for k in ("score", "matches", "alen")}
+        if T and Q:
+            _lib.check(self._lib.igd_align_dense(
+                self._h, tb.ctypes.data if tb.size else None, to.ctypes.data, T,
+                qb.ctypes.data if qb.size else None, qo.ctypes.data, Q, ctypes.byref(sc),
+                res["score"].ctypes.data, res["matches"].ctypes.data, res["alen"].ctypes.data))
+            t = self.timing()
+            self.align_ms_total += t["align_ms"]
+            self.align_cells_total += t["align_cells"]
+        self.h2d_bytes += tb.nbytes + to.nbytes + qb.nbytes + qo.nbytes
+        self.d2h_bytes += 2 * 4 * T * Q
+        return res
+
     def sync(self):
         _lib.check(self._lib.igd_sync(self._h))
 

@@ -88,24 +88,37 @@ def align_fragment_to_genes(fragments, canon_genes, scoring_scheme=None, gene=No
             targets.append(s)
             targets.append(reverse_complement(s))
         return tindex[s]
-    # pairs are laid out [fragment][orientation][gene]: every target meets the genes in table order,
-    # which the C ABI turns into runs for the packed kernel
-    pt = np.zeros((F, 2, G), np.int32)
+    # every (fragment, orientation) meets every gene: a dense batch.  Empty fragments stand for
+    # 'A' * len(gene) (:339-340), a different target per gene, and go through the pair-list call.
+    idx = np.zeros((F, 2), np.int32)
+    empty = []
     for i, f in enumerate(fragments):
         q = str(f).upper()
         if len(q):
             t = tid(q)
-            pt[i, 0, :] = t
-            pt[i, 1, :] = t + 1
-        else:                                    # empty fragment -> 'A' * len(gene) (:339-340)
-            for j, g in enumerate(genes):
-                t = tid("A" * len(g))
-                pt[i, 0, j] = t
-                pt[i, 1, j] = t + 1
-    pq = np.broadcast_to(np.arange(G, dtype=np.int32)[None, None, :], (F, 2, G))
-    r = engine.align(targets, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
-    m = r["matches"].reshape(F, 2, G)
-    ln = r["alen"].reshape(F, 2, G)
+            idx[i] = (t, t + 1)
+        else:
+            empty.append(i)
+            idx[i] = (0, 0)
+    m = np.zeros((F, 2, G), np.int32)
+    ln = np.ones((F, 2, G), np.int32)
+    if targets:
+        r = engine.align_dense(targets, genes)
+        m[:] = r["matches"][idx]
+        ln[:] = r["alen"][idx]
+    if empty:
+        et, eidx = [], {}
+        for g in genes:
+            if len(g) not in eidx:
+                eidx[len(g)] = len(et)
+                et.append("A" * len(g))
+                et.append(reverse_complement("A" * len(g)))
+        pt = np.array([[eidx[len(g)], eidx[len(g)] + 1] for g in genes], np.int32).T      # [2, G]
+        pq = np.broadcast_to(np.arange(G, dtype=np.int32), (2, G))
+        r = engine.align(et, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
+        for i in empty:
+            m[i] = r["matches"].reshape(2, G)
+            ln[i] = r["alen"].reshape(2, G)
     fwd = (m[:, 0, :] - 1) > (m[:, 1, :] - 1)
     mm = np.where(fwd, m[:, 0, :], m[:, 1, :])
     ll = np.where(fwd, ln[:, 0, :], ln[:, 1, :])
@@ -139,9 +152,7 @@ def window_alignments(engine, windows, genes):
     out = []
     if W == 0 or G == 0:
         return [(Alignment(), "") for _ in windows]
-    pt = np.repeat(np.arange(2 * W, dtype=np.int32), G)
-    pq = np.tile(np.arange(G, dtype=np.int32), 2 * W)
-    r = engine.align(targets, [g[1] for g in genes], pt, pq)
+    r = engine.align_dense(targets, [g[1] for g in genes])
     pi = pi_from(r["matches"], r["alen"]).reshape(W, 2 * G)
     # last index attaining the maximum, provided the maximum is >= 0 (best_pi starts at 0)
     best = 2 * G - 1 - np.argmax(pi[:, ::-1], axis=1)

@@ -167,6 +167,14 @@ int igd_align_batch(igd_handle *h,
                     const igd_scoring *sc,
                     int32_t *score, int32_t *matches, int32_t *alen, int32_t *start, int32_t *ient);
 
+/* The same for EVERY target against EVERY query (the shape of align_fragment_to_genes,
+ * py/IGDetective.py:335-341, and of the iterative stage's loop, py/extract_aligned_genes.py:89-92):
+ * outputs are [n_tgt][n_qry], target-major; no pair tables, no start / ient. */
+int igd_align_dense(igd_handle *h,
+                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                    const igd_scoring *sc, int32_t *score, int32_t *matches, int32_t *alen);
+
 #ifdef __cplusplus
 }
 #endif

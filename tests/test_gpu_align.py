@@ -152,3 +152,20 @@ def test_align_other_schemes(engine):
         assert np.array_equal(fast["score"], want["score"].astype(np.int64)), sc
         assert np.array_equal(fast["matches"], want["matches"]), sc
         assert np.array_equal(fast["alen"], want["end"] - want["start"]), sc
+
+
+def test_align_dense_equals_oracle(engine):
+    """igd_align_dense: fast path (all pairs fit the packed word), with an empty target, and the fallback
+    to pair tables (a query longer than 511)"""
+    rng = np.random.default_rng(8)
+    genes = list(canonical("combined_reference_genes")["V"].values())[:70]
+    targets = [rand_seq(rng, n) for n in (350, 350, 70, 1, 200, 352, 353, 511)] + [""]
+    targets += [(rand_seq(rng, 300) + synth.mutate(rng, genes[3], 0.1, 0.02) + rand_seq(rng, 300))[:800].lower()[:400] + rand_seq(rng, 400)]
+    for queries in (genes, genes[:5] + [rand_seq(rng, 600)]):
+        T, Q = len(targets), len(queries)
+        pt, pq = [a.ravel() for a in np.meshgrid(np.arange(T), np.arange(Q), indexing="ij")]
+        want = O.align_stats(targets, queries, pt, pq, threads=8)
+        got = engine.align_dense(targets, queries)
+        assert np.array_equal(got["score"].ravel(), want["score"].astype(np.int64))
+        assert np.array_equal(got["matches"].ravel(), want["matches"])
+        assert np.array_equal(got["alen"].ravel(), want["end"] - want["start"])
