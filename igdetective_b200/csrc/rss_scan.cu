@@ -27,8 +27,9 @@
 // instance of the same kernel).  Survivors are looked up in the exact 7-mer flag table in shared
 // memory; real heptamer hits (~1 % of positions) are compacted into a per-warp queue.
 // Phase B runs on the staged tile too (halo = 64 bases >= the 40-base RSS span): hits are expanded
-// into (heptamer, window) items, 32 items are probed at a time against a shared-memory bitmap of all
-// 9-mers, and only the ~3 % of items that find a 9-mer touch the exact tables and the validity plane.
+// into (heptamer, window) items, 32 items are probed at a time against the 32 KB bitmap of all 9-mers
+// (L1-resident; SCAN_ANY9_SMEM=1 keeps it in shared memory at the price of one CTA per SM less), and
+// only the ~3 % of items that find a 9-mer touch the exact tables and the validity plane.
 #include "common.cuh"
 
 namespace {
