@@ -254,3 +254,34 @@ def test_scan_arbitrary_motif_tables_and_spacers(motifs):
             sel = kh[kh["contig"] == 0]
             for ti, t in enumerate(SIG):
                 assert sel["pos"][(sel["flags"] >> ti) & 1 == 1].tolist() == O.find_valid_motif_idx(s, custom[t][str(k)], k)
+
+
+def test_scan_pathological_density_and_buffer_regrow(engine, motifs):
+    """a contig made of back-to-back RSS units: ~1.5 M hits overflow the initial hit buffer (regrow +
+    rerun) and every warp queue / item list runs at its densest; prefix checked against the oracle,
+    the rest through periodicity"""
+    h7 = sorted(motifs["D_right"]["7"])[3]
+    n9 = sorted(motifs["D_right"]["9"])[5]
+    unit = h7 + "ACGTTGCAAGCT" + n9                     # 7 + 12 + 9 = 28
+    assert len(unit) == 28
+    n_units = 1_500_000
+    s = unit * n_units
+    engine.load_contigs([s])
+    h = engine.scan_rss(O.SPACER_LENGTH)
+    assert len(h) > 1_400_000                            # > max(2^20, bases / 32): the buffer had to grow
+    want = O.scan_all({"c": s[:28 * 2000]}, motifs, order="canonical")
+    lim = 28 * 2000 - 100
+    for ti, t in enumerate(SIG):
+        for si, sd in enumerate("+-"):
+            sel = h[(h["sig_type"] == ti) & (h["strand"] == si)]
+            got = [(int(a), int(b)) for a, b in zip(sel["hept"], sel["nona"]) if 100 <= a < lim and 100 <= b < lim]
+            exp = [(a, b) for a, b in want[t][sd]["c"] if 100 <= a < lim and 100 <= b < lim]
+            assert sorted(got) == sorted(exp), (t, sd)
+    # periodicity: away from the ends every unit contributes the same hits
+    mid = h[(h["hept"] >= 28 * 1000) & (h["hept"] < 28 * (n_units - 1000))]
+    per_unit = len(mid) / (n_units - 2000)
+    assert per_unit == int(per_unit) and per_unit >= 1
+    ph = np.unique((mid["hept"] % 28).astype(np.int64) * 64 + mid["sig_type"] * 2 + mid["strand"], return_counts=True)[1]
+    assert np.all(ph == n_units - 2000)
+    kh = engine.scan_kmers(7)
+    assert len(kh) >= n_units
