@@ -97,6 +97,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
 struct Stage {
     const uint32_t *sw;            // stage words: record r = {lo0, lo1, hi0, hi1} at sw[4r..4r+3]
     const uint8_t *lut7;           // shared-memory copies of the motif tables
+    const uint8_t *need;           // 7-mer flags -> bitmask of the windows that serve any of them
     const uint32_t *any9;
     unsigned long long g0;         // global base index of stage position 0
 };
@@ -193,7 +194,7 @@ __device__ __forceinline__ void probe_window(const ScanParams &P, const Stage &T
 {
     const int q = (int)(item & 0xffffu);
     const int w = (int)(item >> 16) & 7;
-    const unsigned fm = item >> 24;
+    const unsigned fm = (item >> 24) & P.wmask[w];
     unsigned lo, hi;
     swin32x2(T.sw, q + P.woff[w], lo, hi);
     unsigned nf[3];
@@ -218,7 +219,7 @@ __device__ __noinline__ int phase_b(const ScanParams &P, const Stage &T, unsigne
         unsigned lo, hi;
         swin32x2(T.sw, q, lo, hi);
         f = T.lut7[((hi & 127u) << 7) | (lo & 127u)];
-        for (int w = 0; w < P.nwin; ++w) need |= (f & P.wmask[w]) ? (1u << w) : 0u;
+        need = T.need[f];
     }
     const int cnt = __popc(need);
     int incl = cnt;
@@ -232,7 +233,7 @@ __device__ __noinline__ int phase_b(const ScanParams &P, const Stage &T, unsigne
     while (need) {
         const int w = __ffs(need) - 1;
         need &= need - 1;
-        iq[off++] = (unsigned)q | ((unsigned)w << 16) | ((f & P.wmask[w]) << 24);
+        iq[off++] = (unsigned)q | ((unsigned)w << 16) | (f << 24);
     }
     ni += tot;
     __syncwarp();
@@ -296,7 +297,8 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     unsigned *s_wq = (unsigned *)(s_lut7 + 16384);
 #endif
     unsigned *s_iq = s_wq + SCAN_WARPS * WQCAP;                              // SCAN_WARPS * IQCAP
-    uint64_t *s_full = (uint64_t *)(s_iq + SCAN_WARPS * IQCAP);              // NSTAGE
+    uint8_t *s_need = (uint8_t *)(s_iq + SCAN_WARPS * IQCAP);                // 256
+    uint64_t *s_full = (uint64_t *)(s_need + 256);                           // NSTAGE
     uint64_t *s_empty = s_full + NSTAGE;                                     // NSTAGE
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -312,6 +314,11 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         const uint4 *src9 = (const uint4 *)P.any9; uint4 *dst9 = (uint4 *)s_any9;
         for (int i = tid; i < 32768 / 16; i += SCAN_THREADS) dst9[i] = __ldg(&src9[i]);
 #endif
+    }
+    for (int f = tid; f < 256; f += SCAN_THREADS) {
+        unsigned need = 0;
+        for (int w = 0; w < P.nwin; ++w) need |= ((unsigned)f & P.wmask[w]) ? (1u << w) : 0u;
+        s_need[f] = (uint8_t)need;
     }
     __syncthreads();
 
@@ -350,52 +357,57 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
 
         const uint4 *rec = (const uint4 *)(s_stage + stage * STAGE_STRIDE);
         Stage T;
-        T.sw = (const uint32_t *)rec; T.lut7 = s_lut7; T.any9 = s_any9;
+        T.sw = (const uint32_t *)rec; T.lut7 = s_lut7; T.need = s_need; T.any9 = s_any9;
         T.g0 = tile * (unsigned long long)(IGD_TILE_CHUNKS * IGD_CHUNK_BASES);     // stage record 0 = chunk tile*512
         int nq = 0, ni = 0;                               // queued hits / items of this warp (warp-uniform)
-#pragma unroll 1
-        for (int row = 0; row < ROWS_PER_WARP; ++row) {
-            // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk
-            const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;        // stage record of the chunk
-            uint32_t hit0, hit1;
-            {
-                const uint4 r = rec[c];
-                const uint4 n = rec[c + 1];
-                uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
-                if (PREFILTER) {
-                    const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
-                    cand0 = consensus_ge4(i0, i1);
-                    cand1 = consensus_ge4(i1, i2);
-                }
-                hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
-                hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
-            }
-            // ---- compaction of the hit positions into the warp queue (a pass queues at most what fits,
-            //      so pathological densities just take more passes)
-            unsigned long long m = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
-            while (__any_sync(0xffffffffu, m != 0ull)) {
-                const int cnt = __popcll(m);
-                int incl = cnt;
+        // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk of each row
+        unsigned long long hm[ROWS_PER_WARP];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const int tot = __shfl_sync(0xffffffffu, incl, 31);
-                const int space = WQCAP - nq;
-                int off = incl - cnt;
-                while (m && off < space) {
-                    const int b = __ffsll((long long)m) - 1;
-                    m &= m - 1;
+        for (int row = 0; row < ROWS_PER_WARP; ++row) {
+            const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;        // stage record of the chunk
+            const uint4 r = rec[c];
+            const uint4 n = rec[c + 1];
+            uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
+            if (PREFILTER) {
+                const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
+                cand0 = consensus_ge4(i0, i1);
+                cand1 = consensus_ge4(i1, i2);
+            }
+            const uint32_t hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
+            const uint32_t hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
+            hm[row] = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
+        }
+        // ---- compaction of the tile's hit positions into the warp queue: one prefix sum per pass; a pass
+        //      queues at most what fits, so pathological densities just take more passes
+        for (;;) {
+            int cnt = 0;
+#pragma unroll
+            for (int row = 0; row < ROWS_PER_WARP; ++row) cnt += __popcll(hm[row]);
+            if (!__any_sync(0xffffffffu, cnt != 0)) break;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int tot = __shfl_sync(0xffffffffu, incl, 31);
+            const int space = WQCAP - nq;
+            int off = incl - cnt;
+#pragma unroll
+            for (int row = 0; row < ROWS_PER_WARP; ++row) {
+                const int c = (row * SCAN_WARPS + warp) * 32 + lane + 1;
+                while (hm[row] && off < space) {
+                    const int b = __ffsll((long long)hm[row]) - 1;
+                    hm[row] &= hm[row] - 1;
                     wq[nq + off] = (unsigned)(c * 64 + b);
                     ++off;
                 }
-                nq += min(tot, space);
-                __syncwarp();
-                if (nq >= 64) {                           // keep room for the next chunk; full rounds only
-                    nq -= 32;
-                    ni = phase_b(P, T, iq, ni, (int)wq[nq + lane], true, false);
-                }
+            }
+            nq += min(tot, space);
+            __syncwarp();
+            while (nq >= 64) {                            // keep room for the next pass; full rounds only
+                nq -= 32;
+                ni = phase_b(P, T, iq, ni, (int)wq[nq + lane], true, false);
             }
         }
         // ---- phase B for what is left of this tile, then release the stage
@@ -457,7 +469,7 @@ kmer_scan_kernel(const KmerParams P)
 
 } // namespace
 
-static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + (SCAN_ANY9_SMEM ? 32768 : 0) + SCAN_WARPS * (WQCAP + IQCAP) * 4 + 2 * NSTAGE * 8 + 16;
+static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + (SCAN_ANY9_SMEM ? 32768 : 0) + SCAN_WARPS * (WQCAP + IQCAP) * 4 + 256 + 2 * NSTAGE * 8 + 16;
 
 int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
 {
