@@ -60,9 +60,11 @@ def d_gene_rows(parent_seq, rss_idx):
     """extract_genes for D, py/IGDetective.py:366-378."""
     rows = []
     for strand in rss_idx:
-        for contig in rss_idx[strand]:
+        for contig, entries in rss_idx[strand].items():
+            if not entries:
+                continue
             s = parent_seq[contig]
-            for e in rss_idx[strand][contig]:
+            for e in entries:
                 lh, ln = _kmer(s, e[0], 7, strand), _kmer(s, e[1], 9, strand)
                 rh, rn = _kmer(s, e[2], 7, strand), _kmer(s, e[3], 9, strand)
                 if strand == FWD:

@@ -63,26 +63,24 @@ class RssScan:
             return self._cache[key]
         t, s = SIGNAL_INDEX[sig_type], (0 if strand == FWD else 1)
         h = self.hits[(self.hits["sig_type"] == t) & (self.hits["strand"] == s)]
-        # hits arrive sorted by (contig, type, strand, scan-order index): one split per contig
-        cuts = np.searchsorted(h["contig"], np.arange(len(self.ids) + 1))
-        hept, nona = h["hept"].tolist(), h["nona"].tolist()
-        res = {}
-        for ci, cid in enumerate(self.ids):
-            lo, hi = cuts[ci], cuts[ci + 1]
-            if lo == hi:
-                res[cid] = []
-                continue
-            tuples = list(zip(hept[lo:hi], nona[lo:hi]))
-            if self.order == "reference" and len(tuples) > 1:
-                k = 7 if HEPT_FIRST[sig_type] else 9
-                L = self.lens[ci]
-                rank = rank_map(self._first_set(sig_type, strand, ci))
-                first = 0 if HEPT_FIRST[sig_type] else 1
-                if strand == FWD:
-                    tuples.sort(key=lambda tp: rank[tp[first]])
-                else:
-                    tuples.sort(key=lambda tp: rank[L - tp[first] - k])
-            res[cid] = tuples
+        # hits arrive sorted by (contig, type, strand, scan-order index): one split per contig that has any
+        res = {cid: [] for cid in self.ids}
+        if len(h):
+            cs, first = np.unique(h["contig"], return_index=True)
+            bounds = np.append(first, len(h)).tolist()
+            hept, nona = h["hept"].tolist(), h["nona"].tolist()
+            for ci, lo, hi in zip(cs.tolist(), bounds[:-1], bounds[1:]):
+                tuples = list(zip(hept[lo:hi], nona[lo:hi]))
+                if self.order == "reference" and len(tuples) > 1:
+                    k = 7 if HEPT_FIRST[sig_type] else 9
+                    L = self.lens[ci]
+                    rank = rank_map(self._first_set(sig_type, strand, ci))
+                    first_el = 0 if HEPT_FIRST[sig_type] else 1
+                    if strand == FWD:
+                        tuples.sort(key=lambda tp: rank[tp[first_el]])
+                    else:
+                        tuples.sort(key=lambda tp: rank[L - tp[first_el] - k])
+                res[self.ids[ci]] = tuples
         self._cache[key] = res
         return res
 
@@ -102,8 +100,8 @@ def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GEN
     dr-outer / dl-inner in the given list orders.  The reference's double loop is replaced by one
     sorted search per contig; the output (content and order) is the same."""
     res = {c: [] for c in input_seq_dict.keys()}
-    for c in input_seq_dict:
-        dls, drs = D_left_idx[c], D_right_idx[c]
+    for c, drs in D_right_idx.items():
+        dls = D_left_idx[c] if drs else None
         if not dls or not drs:
             continue
         dl0 = np.fromiter((x[0] for x in dls), np.int64, len(dls))
@@ -135,10 +133,12 @@ def extract_s_fragment(index, extract_dir, length, parent_seq):
 def get_s_fragment_from_RSS(gene, strand, input_rss_info, input_seq_dict):
     """py/IGDetective.py:268-300 (the globals it reads are parameters here)."""
     out = {c: [] for c in input_rss_info[gene][strand]}
-    for c in input_rss_info[gene][strand]:
+    for c, rss in input_rss_info[gene][strand].items():
+        if not rss:
+            continue
         s = input_seq_dict[c]
         frs = []
-        for r in input_rss_info[gene][strand][c]:
+        for r in rss:
             if (gene == V and strand == FWD) or (gene == J and strand == REV):
                 frs.append(extract_s_fragment(r[0], REV, GENE_LENGTH[gene], s))
             elif gene in (V, J):
