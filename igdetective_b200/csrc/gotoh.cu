@@ -18,6 +18,7 @@
 // bottom row of each lane travels to the next lane by shuffle.  No shared memory, no tensor
 // cores: the work is integer add / max / select.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -316,7 +317,8 @@ int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
 {
     const unsigned warps_needed = (unsigned)((P.n_runs + (32 / G) - 1) / (32 / G));
     unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);
-    const unsigned cap = (unsigned)h->sm_count * 4u;
+    static const unsigned per_sm = getenv("IGD_GOTOH_BLOCKS_PER_SM") ? (unsigned)atoi(getenv("IGD_GOTOH_BLOCKS_PER_SM")) : 6u;
+    const unsigned cap = (unsigned)h->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (mixed) gotoh_packed_kernel<G, C, true, LONG><<<blocks, GT_THREADS, 0, h->stream>>>(P);
