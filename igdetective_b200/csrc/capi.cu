@@ -10,6 +10,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
+#include <thread>
 #include <unordered_map>
 
 static thread_local std::string g_err;
@@ -246,38 +247,78 @@ igd_fasta *igd_fasta_open(const char *path)
         igd_set_error("%s is gzip-compressed; igd_fasta_open reads plain FASTA", path); return nullptr;
     }
     if (fsize && madvise((void *)data, fsize, MADV_SEQUENTIAL) != 0) { /* advisory only */ }
-    igd_fasta *f = new igd_fasta();
-    std::vector<uint8_t> buf(fsize + 1);                // the letters can never outnumber the file bytes
+    // Parallel parse: the file is cut at line starts into one piece per thread; every piece is parsed
+    // into its own buffer (letters with blanks removed + the headers it contains), then the pieces are
+    // concatenated by a parallel copy.  Letters in front of the file's first header are dropped.
+    struct Hdr { std::string id; uint64_t at; };         // at = letters of the piece in front of the header
+    struct Piece { uint8_t *buf = nullptr; uint64_t n = 0; std::vector<Hdr> hdrs; };
+    unsigned nthreads = std::max(1u, std::min(std::min(std::thread::hardware_concurrency(), 32u), (unsigned)(fsize / (32u << 20)) + 1u));
+    std::vector<size_t> cut(nthreads + 1, fsize);
+    cut[0] = 0;
+    for (unsigned k = 1; k < nthreads; ++k) {
+        size_t p = std::max(cut[k - 1], fsize / nthreads * k);
+        const char *nl = p < fsize ? (const char *)memchr(data + p, '\n', fsize - p) : nullptr;
+        cut[k] = nl ? (size_t)(nl - data) + 1 : fsize;
+    }
+    std::vector<Piece> pieces(nthreads);
+    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
+    auto parse = [&](unsigned k) {
+        Piece &pc = pieces[k];
+        const char *p = data + cut[k], *end = data + cut[k + 1];
+        pc.buf = (uint8_t *)malloc((size_t)(end - p) + 1);
+        uint8_t *w = pc.buf;
+        while (p < end) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+            const char *le = nl ? nl : end;             // line = [p, le)
+            if (p < le && *p == '>') {
+                const char *q = p + 1;
+                while (q < le && blank(*q)) ++q;         // the id is the first token of the header
+                const char *b = q;
+                while (q < le && !blank(*q)) ++q;
+                pc.hdrs.push_back({std::string(b, q), (uint64_t)(w - pc.buf)});
+            } else {
+                const char *q = p;
+                while (q < le) {                        // copy the runs between blanks
+                    const char *s = q;
+                    while (q < le && !blank(*q)) ++q;
+                    memcpy(w, s, (size_t)(q - s)); w += q - s;
+                    while (q < le && blank(*q)) ++q;
+                }
+            }
+            p = nl ? nl + 1 : end;
+        }
+        pc.n = (uint64_t)(w - pc.buf);
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nthreads; ++k) th.emplace_back(parse, k);
+        parse(0);
+        for (auto &t : th) t.join();
+    }
+    if (fsize) munmap((void *)data, fsize);
+    // global letter offset of every piece; everything in front of the first header is dropped
+    unsigned first_piece = nthreads;
+    for (unsigned k = 0; k < nthreads && first_piece == nthreads; ++k) if (!pieces[k].hdrs.empty()) first_piece = k;
+    std::vector<uint64_t> base(nthreads + 1, 0), skip(nthreads, 0);
+    for (unsigned k = 0; k < nthreads; ++k) {
+        skip[k] = k < first_piece ? pieces[k].n : (k == first_piece ? pieces[k].hdrs[0].at : 0);
+        base[k + 1] = base[k] + pieces[k].n - skip[k];
+    }
+    const uint64_t total = base[nthreads];
     struct Rec { std::string id; uint64_t off, len; };
     std::vector<Rec> recs;
-    const char *p = data, *end = data + fsize;
-    uint8_t *w = buf.data();
-    bool in_record = false;
-    auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
-    while (p < end) {
-        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
-        const char *le = nl ? nl : end;                 // line = [p, le)
-        if (p < le && *p == '>') {
-            const char *q = p + 1;
-            while (q < le && blank(*q)) ++q;             // the id is the first token of the header
-            const char *b = q;
-            while (q < le && !blank(*q)) ++q;
-            if (in_record) recs.back().len = (uint64_t)(w - buf.data()) - recs.back().off;
-            recs.push_back({std::string(b, q), (uint64_t)(w - buf.data()), 0});
-            in_record = true;
-        } else if (in_record) {
-            const char *q = p;
-            while (q < le) {                            // copy the runs between blanks
-                const char *s = q;
-                while (q < le && !blank(*q)) ++q;
-                memcpy(w, s, (size_t)(q - s)); w += q - s;
-                while (q < le && blank(*q)) ++q;
-            }
-        }
-        p = nl ? nl + 1 : end;
+    for (unsigned k = first_piece; k < nthreads; ++k)
+        for (const Hdr &hd : pieces[k].hdrs) recs.push_back({hd.id, base[k] + hd.at - skip[k], 0});
+    for (size_t i = 0; i < recs.size(); ++i) recs[i].len = (i + 1 < recs.size() ? recs[i + 1].off : total) - recs[i].off;
+    uint8_t *all = (uint8_t *)malloc((size_t)total + 1);
+    {
+        auto copy = [&](unsigned k) { memcpy(all + base[k], pieces[k].buf + skip[k], (size_t)(pieces[k].n - skip[k])); free(pieces[k].buf); };
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < nthreads; ++k) th.emplace_back(copy, k);
+        copy(0);
+        for (auto &t : th) t.join();
     }
-    if (in_record) recs.back().len = (uint64_t)(w - buf.data()) - recs.back().off;
-    if (fsize) munmap((void *)data, fsize);
+    igd_fasta *f = new igd_fasta();
     // dict semantics: a repeated id keeps its first position and takes the last sequence
     std::unordered_map<std::string, size_t> first;
     std::vector<size_t> order;
@@ -287,19 +328,19 @@ igd_fasta *igd_fasta_open(const char *path)
         else order[it->second] = i;
     }
     f->off.assign(1, 0);
-    bool in_place = order.size() == recs.size();
+    const bool in_place = order.size() == recs.size();
     for (size_t k = 0; k < order.size(); ++k) {
         const Rec &r = recs[order[k]];
         f->ids.push_back(r.id);
         f->off.push_back(f->off.back() + r.len);
     }
     if (in_place) {
-        buf.resize((size_t)(w - buf.data()));
-        f->seq.swap(buf);
+        f->seq = all;
     } else {                                            // rare: duplicates -> rebuild in dict order
-        f->seq.resize(f->off.back());
+        f->seq = (uint8_t *)malloc((size_t)f->off.back() + 1);
         for (size_t k = 0; k < order.size(); ++k)
-            memcpy(f->seq.data() + f->off[k], buf.data() + recs[order[k]].off, (size_t)recs[order[k]].len);
+            memcpy(f->seq + f->off[k], all + recs[order[k]].off, (size_t)recs[order[k]].len);
+        free(all);
     }
     return f;
 }
@@ -324,14 +365,14 @@ int igd_fasta_read(const igd_fasta *f, int32_t i, uint64_t start, uint64_t len, 
         igd_set_error("slice [%llu, +%llu) outside contig of %llu", (unsigned long long)start, (unsigned long long)len, (unsigned long long)L);
         return IGD_ERR_ARG;
     }
-    memcpy(out, f->seq.data() + f->off[i] + start, (size_t)len);
+    memcpy(out, f->seq + f->off[i] + start, (size_t)len);
     return IGD_OK;
 }
 
 int igd_load_fasta(igd_handle *h, const igd_fasta *f)
 {
     if (!h || !f) { igd_set_error("null argument"); return IGD_ERR_ARG; }
-    return igd_load_contigs(h, f->seq.data(), f->off.data(), (int32_t)f->ids.size());
+    return igd_load_contigs(h, f->seq, f->off.data(), (int32_t)f->ids.size());
 }
 
 static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint64_t *n_hits)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "../../include/igd_b200.h"
@@ -22,9 +23,10 @@ constexpr int IGD_TILE_CHUNKS = 512;                  // chunks per scan tile = 
 constexpr int IGD_STAGE_CHUNKS = IGD_TILE_CHUNKS + 2; // one halo chunk each side (RSS span <= 40 bases)
 
 struct igd_fasta {
-    std::vector<uint8_t> seq;          // letters of all contigs, concatenated in dict order
+    uint8_t *seq = nullptr;            // letters of all contigs, concatenated in dict order (malloc)
     std::vector<uint64_t> off;         // n + 1 offsets
     std::vector<std::string> ids;
+    ~igd_fasta() { free(seq); }
 };
 
 struct igd_handle {

@@ -144,3 +144,29 @@ def test_native_fasta_reader_equals_oracle(tmp_path):
         NativeFasta(golden_input("cow"))          # gzip is refused loudly, not misparsed
     with pytest.raises(IgdError):
         NativeFasta(str(tmp_path / "missing.fa"))
+
+
+def test_native_fasta_reader_multithreaded(tmp_path):
+    """a file large enough to be cut into several pieces (one per parser thread): records of skewed
+    lengths, CRLF, a duplicate id, text in front of the first header; same result as the oracle reader"""
+    from igdetective_b200.fasta import NativeFasta
+    rng = np.random.default_rng(3)
+    p = tmp_path / "big.fa"
+    with open(p, "wb") as f:
+        f.write(b"preamble that is not part of any record\nACGTACGT\n")
+        for i in range(60):
+            L = int(rng.integers(1, 4_000_000))
+            name = b"dup" if i in (7, 41) else b"rec%d" % i
+            f.write(b">" + name + b" some description\r\n")
+            seq = np.frombuffer(b"ACGTNacgt", np.uint8)[rng.integers(0, 9, L)]
+            w = int(rng.integers(50, 90))
+            pad = (-L) % w
+            rows = np.concatenate([seq, np.full(pad, 32, np.uint8)]).reshape(-1, w)
+            f.write(np.concatenate([rows, np.full((len(rows), 1), 13, np.uint8), np.full((len(rows), 1), 10, np.uint8)], axis=1).tobytes())
+    assert os.path.getsize(p) > 3 * (32 << 20)
+    want = O.fasta_dict(str(p))
+    nf = NativeFasta(str(p))
+    assert list(nf) == list(want)
+    for k in want:
+        assert len(nf[k]) == len(want[k]), k
+        assert str(nf[k]) == want[k], k
