@@ -8,7 +8,9 @@ Layout:
   scoring.py            ComputeAlignment / align_fragment_to_genes / BioAlign view (:307-360, BioAlign)
   igdetective.py        the de-novo stage: same CLI flags and TSV outputs as py/IGDetective.py
   extract_aligned_genes.py  the iterative stage: same main() and outputs as py/extract_aligned_genes.py
-  shard.py              contig / pair sharding across ranks and the deterministic merge
+  shard.py, multi.py    contig sharding across torchrun ranks, deterministic merge, sharded CLI
+  fasta.py              FASTA readers (Python, and NativeFasta over the library's parallel C++ parser)
+  datafiles.py, order.py  motif / gene-set loading; replay of the reference's set iteration order
 There is no CPU implementation of the scan or the aligner in this package.
 """
 __version__ = "0.1.0"
