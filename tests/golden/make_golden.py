@@ -69,10 +69,10 @@ def make_data():
                        read_fasta(os.path.join(REF, "examples", "igh_locus_examples", fn)))
 
 
-def run_reference_igdetective(example, gene_dir, jobs, rss_only):
+def run_reference_igdetective(example, gene_dir, jobs, rss_only, locus="IGH"):
     """cwd gets a datafiles/ view whose combined_reference_genes points at `gene_dir`
     (the script hard-codes that name, IGDetective.py:133)."""
-    out = os.path.join(HERE, "igdetective", "%s__%s" % (example, gene_dir))
+    out = os.path.join(HERE, "igdetective", "%s__%s" % (example, gene_dir) + ("" if locus == "IGH" else "__" + locus))
     os.makedirs(out, exist_ok=True)
     with tempfile.TemporaryDirectory() as tmp:
         os.makedirs(os.path.join(tmp, "datafiles"))
@@ -82,7 +82,7 @@ def run_reference_igdetective(example, gene_dir, jobs, rss_only):
         env = dict(os.environ, PYTHONPATH=SHIM, PYTHONHASHSEED="0")
         cmd = [sys.executable, os.path.join(REF, "py", "IGDetective.py"),
                "-i", os.path.join(REF, "examples", "igh_locus_examples", EXAMPLES[example]),
-               "-o", os.path.join(tmp, "out"), "-m", str(jobs), "-l", "IGH"] + (["-r"] if rss_only else [])
+               "-o", os.path.join(tmp, "out"), "-m", str(jobs), "-l", locus] + (["-r"] if rss_only else [])
         subprocess.run(cmd, cwd=tmp, env=env, check=True, stdout=subprocess.DEVNULL)
         for fn in sorted(os.listdir(os.path.join(tmp, "out"))):
             shutil.copyfile(os.path.join(tmp, "out", fn), os.path.join(out, fn))
@@ -94,6 +94,10 @@ def make_igdetective(jobs):
         run_reference_igdetective(ex, "combined_reference_genes", jobs, rss_only=True)
         run_reference_igdetective(ex, "combined_reference_genes", jobs, rss_only=False)
     run_reference_igdetective("human", "human_reference_genes", jobs, rss_only=False)
+    # other loci select other gene sets (IGKV 358 / IGKJ 14 mixed case, IGLV 200 / IGLJ 20, TRBV 66 / TRBJ 36);
+    # the spacers stay the IGH ones because InitializeVariables (:36-51) only assigns locals
+    for locus in ("IGK", "IGL", "TRB"):
+        run_reference_igdetective("cow", "combined_reference_genes", jobs, rss_only=False, locus=locus)
 
 
 # scoring-B scenarios: (name, example, gene fasta, 1-based SAM positions)

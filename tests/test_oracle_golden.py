@@ -34,6 +34,16 @@ def test_oracle_genes_tsv_cow(cow):
         assert _tsv_bytes([O.D_HEADER if g == "D" else O.VJ_HEADER] + rows[g]) == want, g
 
 
+@pytest.mark.parametrize("locus", ["IGK", "TRB"])
+def test_oracle_genes_tsv_other_loci(motifs, locus):
+    seqs = O.fasta_dict(golden_input("cow"))
+    rows, _ = O.igdetective(seqs, motifs, canonical("combined_reference_genes", locus), threads=THREADS)
+    gdir = os.path.join(GOLDEN, "igdetective", "cow__combined_reference_genes__" + locus)
+    for g in ("V", "D", "J"):
+        want = open(os.path.join(gdir, "genes_%s.tsv" % g), "rb").read()
+        assert _tsv_bytes([O.D_HEADER if g == "D" else O.VJ_HEADER] + rows[g]) == want, (locus, g)
+
+
 def test_oracle_rss_csv_cow(cow):
     seqs, (rows, rss) = cow
     gdir = os.path.join(GOLDEN, "igdetective", "cow__combined_reference_genes")
