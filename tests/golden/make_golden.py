@@ -69,6 +69,55 @@ def make_data():
                        read_fasta(os.path.join(REF, "examples", "igh_locus_examples", fn)))
 
 
+def make_multi_contig_input():
+    """A multi-contig FASTA that walks the reference's corner cases: slices of the three loci (one all
+    lower-case), a repeated record id, contigs shorter than the 350-nt V flank with an RSS inside
+    (negative slice start, IGDetective.py:265), an RSS within 350 nt of the start of a longer contig
+    (empty fragment -> 'A' * len(gene), :339-340), an empty record."""
+    motifs = pickle.load(open(os.path.join(REF, "datafiles", "motifs"), "rb"))
+    ex = {n: read_fasta(os.path.join(REF, "examples", "igh_locus_examples", fn))[0][1] for n, fn in EXAMPLES.items()}
+    v9, j9, j7 = sorted(motifs["V"]["9"]), sorted(motifs["J"]["9"]), sorted(motifs["J"]["7"])
+    comp = str.maketrans("ACGT", "TGCA")
+    v_unit = "CACAGTG" + "ACGTACGTTGCAACGTTGCAATC" + v9[10]                 # heptamer, 23 nt, nonamer
+    j_unit = j9[3] + "TTGACCATGCAAGTCCGATAGCA" + j7[5]                      # nonamer, 23 nt, heptamer
+    filler = ex["human"][500000:500600]
+    recs = [
+        ("ctgA human slice", ex["human"][1000000:1323718]),
+        ("ctgB first copy, replaced below", ex["mouse"][:1000]),
+        ("ctgC", ex["cow"][:250000]),
+        ("short_v 300 nt, V RSS at 250", filler[:250] + v_unit + filler[:11]),
+        ("early_v V RSS 100 nt into a 900-nt contig", filler[:100] + v_unit + filler[:600] + filler[:161]),
+        ("rev_units", (filler[:80] + j_unit + filler[:400] + v_unit + filler[:90]).translate(comp)[::-1]),
+        ("ctgB", ex["mouse"][2400000:2751186]),
+        ("empty_record", ""),
+        ("short_j 60 nt", j_unit + filler[:21]),
+    ]
+    path = os.path.join(HERE, "inputs", "multi.fa.gz")
+    write_fasta_gz(path, recs)
+    return path
+
+
+def run_reference_on_file(fasta_gz, tag, jobs):
+    out = os.path.join(HERE, "igdetective", tag)
+    os.makedirs(out, exist_ok=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "datafiles"))
+        os.symlink(os.path.join(REF, "datafiles", "motifs"), os.path.join(tmp, "datafiles", "motifs"))
+        os.symlink(os.path.join(REF, "datafiles", "combined_reference_genes"),
+                   os.path.join(tmp, "datafiles", "combined_reference_genes"))
+        plain = os.path.join(tmp, "input.fa")
+        with open(plain, "wb") as f:
+            f.write(gzip.open(fasta_gz).read())
+        env = dict(os.environ, PYTHONPATH=SHIM, PYTHONHASHSEED="0")
+        for extra in ([], ["-r"]):
+            cmd = [sys.executable, os.path.join(REF, "py", "IGDetective.py"), "-i", plain,
+                   "-o", os.path.join(tmp, "out"), "-m", str(jobs), "-l", "IGH"] + extra
+            subprocess.run(cmd, cwd=tmp, env=env, check=True, stdout=subprocess.DEVNULL)
+        for fn in sorted(os.listdir(os.path.join(tmp, "out"))):
+            shutil.copyfile(os.path.join(tmp, "out", fn), os.path.join(out, fn))
+            print("  wrote", os.path.relpath(os.path.join(out, fn), ROOT))
+
+
 def run_reference_igdetective(example, gene_dir, jobs, rss_only, locus="IGH"):
     """cwd gets a datafiles/ view whose combined_reference_genes points at `gene_dir`
     (the script hard-codes that name, IGDetective.py:133)."""
@@ -98,6 +147,7 @@ def make_igdetective(jobs):
     # the spacers stay the IGH ones because InitializeVariables (:36-51) only assigns locals
     for locus in ("IGK", "IGL", "TRB"):
         run_reference_igdetective("cow", "combined_reference_genes", jobs, rss_only=False, locus=locus)
+    run_reference_on_file(make_multi_contig_input(), "multi__combined_reference_genes", jobs)
 
 
 # scoring-B scenarios: (name, example, gene fasta, 1-based SAM positions)

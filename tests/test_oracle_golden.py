@@ -44,6 +44,19 @@ def test_oracle_genes_tsv_other_loci(motifs, locus):
         assert _tsv_bytes([O.D_HEADER if g == "D" else O.VJ_HEADER] + rows[g]) == want, (locus, g)
 
 
+def test_oracle_multi_contig_corner_cases(motifs):
+    seqs = O.fasta_dict(golden_input("multi"))
+    assert list(seqs) == ["ctgA", "ctgB", "ctgC", "short_v", "early_v", "rev_units", "empty_record", "short_j"]
+    rows, rss = O.igdetective(seqs, motifs, canonical("combined_reference_genes"), threads=THREADS)
+    gdir = os.path.join(GOLDEN, "igdetective", "multi__combined_reference_genes")
+    for g in ("V", "D", "J"):
+        want = open(os.path.join(gdir, "genes_%s.tsv" % g), "rb").read()
+        assert _tsv_bytes([O.D_HEADER if g == "D" else O.VJ_HEADER] + rows[g]) == want, g
+    for st in O.SIGNAL_TYPES:
+        want = open(os.path.join(gdir, "rss_%s.csv" % st), "rb").read()
+        assert _tsv_bytes(O.rss_rows(rss[st], seqs)) == want, st
+
+
 def test_oracle_rss_csv_cow(cow):
     seqs, (rows, rss) = cow
     gdir = os.path.join(GOLDEN, "igdetective", "cow__combined_reference_genes")
