@@ -167,6 +167,36 @@ def scoring_b_scenarios():
     return sc
 
 
+def make_scoring_b_multi():
+    """scoring B on the multi-contig input against the short, lower-case IGHJ gene file: positions on
+    several contigs (one all lower-case), near contig ends, on contigs shorter than the window"""
+    import csv
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, os.path.join(REF, "py"))
+    os.environ["PATH"] = STUBS + os.pathsep + os.environ["PATH"]
+    import extract_aligned_genes as ref_mod
+    rows = list(csv.reader(open(os.path.join(HERE, "igdetective", "multi__combined_reference_genes", "genes_J.tsv"),
+                                newline=""), delimiter="\t"))[1:]
+    hits = [(r[0], int(r[6]) + 1) for r in rows] + [("ctgC", 120000), ("ctgC", 120350), ("ctgC", 249990), ("ctgA", 5),
+            ("short_j", 10), ("short_v", 200), ("rev_units", 300), ("ctgB", 1000), ("ctgB", 350000)]
+    out = os.path.join(HERE, "scoring_b", "multi_IGHJ")
+    os.makedirs(out, exist_ok=True)
+    sam = os.path.join(out, "alignment.sam")
+    with open(sam, "w") as f:
+        f.write("@HD\tVN:1.6\n")
+        for i, (c, p) in enumerate(hits):
+            f.write("g%d\t0\t%s\t%d\t60\t*\t*\t0\t0\t*\t*\n" % (i, c, p))
+    os.environ["IGD_STUB_SAM"] = sam
+    with tempfile.TemporaryDirectory() as tmp:
+        plain = os.path.join(tmp, "multi.fa")
+        with open(plain, "wb") as f:
+            f.write(gzip.open(os.path.join(HERE, "inputs", "multi.fa.gz")).read())
+        ref_mod.main(plain, os.path.join(REF, "datafiles", "combined_reference_genes", "IGHJ.fa"), os.path.join(tmp, "o"))
+        for fn in ("genes.tsv", "genes.fasta"):
+            shutil.copyfile(os.path.join(tmp, "o", fn), os.path.join(out, fn))
+            print("  wrote", os.path.relpath(os.path.join(out, fn), ROOT))
+
+
 def make_scoring_b():
     sys.path.insert(0, SHIM)
     sys.path.insert(0, os.path.join(REF, "py"))
@@ -203,3 +233,4 @@ if __name__ == "__main__":
         make_igdetective(a.jobs)
     if a.only in ("", "scoring_b"):
         make_scoring_b()
+        make_scoring_b_multi()

@@ -106,7 +106,7 @@ def test_oracle_invariants(motifs, cow):
         assert len(r[12]) <= 150 and r[4] in motifs["D_left"]["7"] and r[8] in motifs["D_right"]["7"]
 
 
-@pytest.mark.parametrize("scenario,example", [("human_IGHV", "human"), ("cow_IGHV", "cow")])
+@pytest.mark.parametrize("scenario,example", [("human_IGHV", "human"), ("cow_IGHV", "cow"), ("multi_IGHJ", "multi")])
 def test_oracle_scoring_b(scenario, example):
     gdir = os.path.join(GOLDEN, "scoring_b", scenario)
     contigs = O.fasta_dict(golden_input(example))
@@ -117,7 +117,8 @@ def test_oracle_scoring_b(scenario, example):
         f = line.split()
         if f[2] != "*" and int(f[3]) not in pos.setdefault(f[2], []):
             pos[f[2]].append(int(f[3]))
-    genes = [(i, s.upper()) for i, s in O.read_fasta(os.path.join(DATAFILES, "combined_reference_genes", "IGHV.fa.gz"))]
+    genes = [(i, s.upper()) for i, s in O.read_fasta(os.path.join(DATAFILES, "combined_reference_genes",
+                                                                   scenario.split("_")[1] + ".fa.gz"))]
     df = pd.DataFrame(O.extract_aligned_genes(contigs, pos, genes, threads=THREADS))
     want = open(os.path.join(gdir, "genes.tsv")).read()
     assert df.to_csv(index=False, sep="\t") == want
