@@ -217,6 +217,7 @@ def gpu_arm(a):
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
     }
     if not a.no_cpu:
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
         line["cpu_baseline"] = cpu_sample(contig, seqs, motifs, canon, kstat["fragments"], a)
     print(json.dumps(line))
     if world > 1:
