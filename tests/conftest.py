@@ -30,6 +30,10 @@ def motifs():
 @pytest.fixture(scope="session")
 def engine(motifs):
     """One Engine per session; creating it fails loudly when the CUDA library or a B200 is missing."""
+    from igdetective_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):        # a fresh checkout: the test harness builds, the product never does
+        from igdetective_b200 import build
+        build.build()
     from igdetective_b200.engine import Engine
     e = Engine(0, motifs)
     yield e
