@@ -19,6 +19,10 @@ def _oracle_built():
     """The oracle's C part is compiled on demand (gcc only)."""
     import subprocess
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
+    # the CUDA library too (nvcc cross-compiles without a GPU): the C-ABI symbol test loads it on CPU
+    from igdetective_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()
 
 
 @pytest.fixture(scope="session")
