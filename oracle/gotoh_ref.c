@@ -27,6 +27,9 @@
  * PARITY UNPINNED: the reference ships no tests or golden vectors, and real
  * BioPython could not be run in this environment, so the tie-break order above
  * is restated from the published source, not checked against its output.
+ * Supporting evidence only: tests/test_oracle_biopython_recalled.py lists seven
+ * known-answer cases of BioPython's own Tests/test_pairwise_aligner.py, recalled
+ * from memory (scores and first alignments); this file reproduces all of them.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
  * arm may load this library.  The product path (igdetective_b200/) never does.
