@@ -103,6 +103,7 @@ gotoh_kernel(const GotohParams P)
                 }
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
+                const float bf = (float)b;
                 const bool lastcol = (j == nB);
                 const int qo4 = lastcol ? P.qeo4 : P.qio4;
                 const int qe4 = lastcol ? P.qee4 + 1 : P.qie4 + 1;   // +1: priority of the Ix state on the extend candidate
@@ -200,8 +201,18 @@ struct PackedParams {
 // the concatenated columns of the whole run, so the systolic pipeline fills and drains once per
 // run instead of once per pair; at a gene boundary a lane stores the result (if it owns row nA)
 // and re-initialises its column state while the lanes below are still finishing the previous gene.
-template <int G, int C, bool MIXED, bool LONG>
-__global__ void __launch_bounds__(GT_THREADS)
+//
+// FPINC: the substitution increment is computed on the FMA pipe instead of the saturated ALU pipe.
+// Letters are held as floats (MIXED: raw + 256 * upper-cased, so equal raw bytes give a difference of
+// 0 and equal letters of different case a difference of +-32, nothing else does); eq = sat(1 - d*d)
+// is exactly 1.0 or 0.0, and the increment words are used as float BIT PATTERNS: a non-negative
+// integer below 2^24 is the bit pattern of the float n * 2^-149, whose sums are exact, so
+// fma(eq, match - mismatch, mismatch) yields the integer increment bit for bit (FADD + FFMA.SAT + FFMA
+// replace ISETP + SEL).  The host selects FPINC only when both increments lie in [0, 2^24).
+// resident CTAs per SM the register allocation aims for: 6 for the shapes that fit 80 registers
+constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : 1; }
+template <int G, int C, bool MIXED, bool LONG, bool FPINC>
+__global__ void __launch_bounds__(GT_THREADS, packed_min_blocks(C))
 gotoh_packed_kernel(const PackedParams P)
 {
     constexpr int PK_PR = PK<LONG>::PR, PK_PRMASK = PK<LONG>::PRMASK, PK_UI = PK<LONG>::UI, PK_NEG = PK<LONG>::NEG;
@@ -235,18 +246,21 @@ gotoh_packed_kernel(const PackedParams P)
         for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
 
         unsigned a[C];
-        int D[C], Y[C];                                       // D(i, j-1) with priority, Iy(i, j-1) clean
+        float af[C];
+        const float wx = __int_as_float(P.inc_mismatch), wd = __int_as_float(P.inc_match) - __int_as_float(P.inc_mismatch);
+        const float w1 = __int_as_float(1);
+        int D[C], Y[C], E[C];                                 // D(i, j-1) with priority, Iy(i, j-1) clean, D(i-1, j-1) clean
         const int i0 = l * C;
 #pragma unroll
         for (int r = 0; r < C; ++r) {
             const int i = i0 + r + 1;
             const unsigned ch = (have && i <= nA) ? A[i - 1] : 0u;
             a[r] = MIXED ? (ch | (up8(ch) << 8)) : ch;
+            af[r] = (float)a[r];
             D[r] = P.qeo + P.qee * (i - 1) + PK_PR;           // D(i,0) = Ix(i,0), priority 1
             Y[r] = PK_NEG;
+            E[r] = (i == 1) ? 0 : P.qeo + P.qee * (i - 2);    // clean D(i-1, 0)
         }
-        const int diag0 = (l == 0) ? 0 : (P.qeo + P.qee * (i0 - 1));   // clean D(i0, 0)
-        int diag = diag0;
         int botD = PK_NEG, botX = PK_NEG;
         const int ls = (nA - 1) / C, rs = (nA - 1) % C;       // lane / row that owns target row nA
         int j = 0;                                            // columns of the current gene already done
@@ -260,33 +274,44 @@ gotoh_packed_kernel(const PackedParams P)
                 if (l == 0) { upD = P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j), priority 0
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
+                const float bf = (float)b;
                 const bool lastcol = (j == nB);
                 // an Ix move in an internal column counts one internal-Ix unit: the unit rides on the
                 // gap score constants, so both candidates carry it into the max
                 const int qo = lastcol ? P.qeo : P.qio + PK_UI;
                 const int qe = lastcol ? P.qee : P.qie + PK_UI;
-                const int nextdiag = upD & ~PK_PRMASK;
-                int dc = diag, uD = upD, uX = upX;
+                int uD = upD, uX = upX;
 #pragma unroll
                 for (int r = 0; r < C; ++r) {
                     int inc;
-                    if (MIXED) {
+                    if (FPINC) {
+                        const float dd = af[r] - bf;
+                        const float eq = __saturatef(fmaf(-dd, dd, 1.0f));
+                        if (MIXED) {
+                            const float du = fabsf(dd) - 32.0f;
+                            const float eu = __saturatef(fmaf(-du, du, 1.0f));
+                            inc = __float_as_int(fmaf(eq, wd, fmaf(eu, w1, wx)));
+                        } else {
+                            inc = __float_as_int(fmaf(eq, wd, wx));
+                        }
+                    } else if (MIXED) {
                         const unsigned x = a[r] ^ b;
                         inc = (x & 0xffu) == 0u ? P.inc_match : ((x & 0xff00u) == 0u ? P.inc_mismatch + 1 : P.inc_mismatch);
                     } else {
                         inc = (a[r] == b) ? P.inc_match : P.inc_mismatch;
                     }
-                    const int m = dc + inc;                                            // M(i,j), priority 2
+                    const int m = E[r] + inc;                                          // M(i,j), priority 2
                     const int x = __viaddmax_s32(uD, qo, uX * one + qe);               // Ix(i,j) raw
                     const int xs = (x & m_clear) | m_pr;                               // priority 1 (one LOP3)
                     const int y = __viaddmax_s32(D[r], P.to, Y[r] * one + P.te) & ~PK_PRMASK; // Iy(i,j), priority 0
                     const int d = __vimax3_s32(m, xs, y);
-                    dc = D[r] & ~PK_PRMASK;
+                    // the diagonal of the next column is updated in place once it has been read, so no
+                    // state needs two live copies (saves the register moves of "dc = old D[r]")
+                    E[r] = (r == 0 && l == 0) ? (P.to + P.te * (j - 1)) : (uD & ~PK_PRMASK);
                     D[r] = d; Y[r] = y;
                     uD = d; uX = xs;
                 }
                 botD = uD; botX = uX;
-                diag = (l == 0) ? (P.to + P.te * (j - 1)) : nextdiag;
                 if (lastcol) {                                // this lane is through with the current gene
                     if (l == ls) {
                         int k = 0;
@@ -301,8 +326,10 @@ gotoh_packed_kernel(const PackedParams P)
                         nB = P.qry_off[q + 1] - P.qry_off[q];
                         j = 0;
 #pragma unroll
-                        for (int r = 0; r < C; ++r) { D[r] = P.qeo + P.qee * (i0 + r) + PK_PR; Y[r] = PK_NEG; }
-                        diag = diag0;
+                        for (int r = 0; r < C; ++r) {
+                            D[r] = P.qeo + P.qee * (i0 + r) + PK_PR; Y[r] = PK_NEG;
+                            E[r] = (i0 + r == 0) ? 0 : P.qeo + P.qee * (i0 + r - 1);
+                        }
                     } else {
                         active = false;
                     }
@@ -321,8 +348,16 @@ int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
     const unsigned cap = (unsigned)h->sm_count * per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (mixed) gotoh_packed_kernel<G, C, true, LONG><<<blocks, GT_THREADS, 0, h->stream>>>(P);
-    else       gotoh_packed_kernel<G, C, false, LONG><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    // increments usable as float bit patterns (see FPINC above); IGD_GOTOH_FPINC=0 forces the integer form
+    static const bool fp_allowed = !(getenv("IGD_GOTOH_FPINC") && atoi(getenv("IGD_GOTOH_FPINC")) == 0);
+    const bool fp = fp_allowed && P.inc_match >= 0 && P.inc_match < (1 << 24) && P.inc_mismatch >= 0 && P.inc_mismatch + 1 < (1 << 24);
+    if (fp) {
+        if (mixed) gotoh_packed_kernel<G, C, true, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        else       gotoh_packed_kernel<G, C, false, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    } else {
+        if (mixed) gotoh_packed_kernel<G, C, true, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        else       gotoh_packed_kernel<G, C, false, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    }
     h->timing.total_launches++;
     h->timing.align_launches++;
     IGD_CUDA(cudaGetLastError());
