@@ -38,7 +38,7 @@ int igd_reserve(igd_handle *h, int slot, size_t bytes)
     return IGD_OK;
 }
 
-enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS };
+enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK, S_COUNT };
 
 extern "C" {
 
@@ -88,7 +88,8 @@ void igd_destroy(igd_handle *h)
     cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any7);
     cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
     cudaFree(h->d_hits); cudaFree(h->d_count);
-    for (int i = 0; i < 13; ++i) cudaFree(h->d_scratch[i]);
+    for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -706,14 +707,17 @@ int igd_align_batch(igd_handle *h,
 // ComputeAlignment (py/extract_aligned_genes.py:89-92); without pair tables the host does no per-pair
 // work and every target becomes runs for the packed kernel.  Falls back to igd_align_batch when some
 // pair does not fit the packed word.
-int igd_align_dense(igd_handle *h,
-                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
-                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
-                    const igd_scoring *sc, int32_t *score, int32_t *matches, int32_t *alen)
+} // extern "C"
+
+// Every target against every query through the packed run-mode kernels, results left on the device
+// (S_SCORE, S_PAY: [n_tgt][n_qry]); *launched = false (and nothing done) when some pair does not fit
+// the packed kernels, the caller then takes the pair-table path.
+static int dense_launch(igd_handle *h,
+                        const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                        const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                        const igd_scoring *sc, bool *launched)
 {
-    if (!h || !tgt_off || !qry_off || !sc || n_tgt < 0 || n_qry < 0 || !score) {
-        igd_set_error("bad arguments to igd_align_dense"); return IGD_ERR_ARG;
-    }
+    *launched = false;
     const int64_t n_pairs = (int64_t)n_tgt * (int64_t)n_qry;
     if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
     int max_q = 0, min_q = 1 << 30;
@@ -737,13 +741,7 @@ int igd_align_dense(igd_handle *h,
         tl[b].push_back(t);
         cells += (uint64_t)nA * qsum;
     }
-    if (!fast) {                                       // generic path: explicit pair tables
-        std::vector<int32_t> pt((size_t)n_pairs), pq((size_t)n_pairs);
-        for (int t = 0; t < n_tgt; ++t)
-            for (int q = 0; q < n_qry; ++q) { pt[(size_t)t * n_qry + q] = t; pq[(size_t)t * n_qry + q] = q; }
-        return igd_align_batch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, pt.data(), pq.data(), n_pairs, sc,
-                               score, matches, alen, nullptr, nullptr);
-    }
+    if (!fast) return IGD_OK;
     IGD_CUDA(cudaSetDevice(h->device));
     h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
     bool mixed = false;
@@ -793,12 +791,38 @@ int igd_align_dense(igd_handle *h,
         if ((rc = igd_launch_gotoh(h, job))) return rc;
     }
     IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    h->timing.align_cells = cells;
+    *launched = true;
+    return IGD_OK;
+}
+
+extern "C" {
+
+int igd_align_dense(igd_handle *h,
+                    const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                    const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                    const igd_scoring *sc, int32_t *score, int32_t *matches, int32_t *alen)
+{
+    if (!h || !tgt_off || !qry_off || !sc || n_tgt < 0 || n_qry < 0 || !score) {
+        igd_set_error("bad arguments to igd_align_dense"); return IGD_ERR_ARG;
+    }
+    const int64_t n_pairs = (int64_t)n_tgt * (int64_t)n_qry;
+    if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
+    bool launched = false;
+    int rc;
+    if ((rc = dense_launch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, sc, &launched))) return rc;
+    if (!launched) {                                   // generic path: explicit pair tables
+        std::vector<int32_t> pt((size_t)n_pairs), pq((size_t)n_pairs);
+        for (int t = 0; t < n_tgt; ++t)
+            for (int q = 0; q < n_qry; ++q) { pt[(size_t)t * n_qry + q] = t; pq[(size_t)t * n_qry + q] = q; }
+        return igd_align_batch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, pt.data(), pq.data(), n_pairs, sc,
+                               score, matches, alen, nullptr, nullptr);
+    }
     IGD_CUDA(cudaMemcpyAsync(score, h->d_scratch[S_SCORE], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     std::vector<int32_t> h_pay((size_t)n_pairs);
     IGD_CUDA(cudaMemcpyAsync(h_pay.data(), h->d_scratch[S_PAY], (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
     IGD_CUDA(cudaEventElapsedTime(&h->timing.align_ms, h->ev0, h->ev1));
-    h->timing.align_cells = cells;
     for (int t = 0; t < n_tgt; ++t) {
         const int nA = tgt_off[t + 1] - tgt_off[t];
         const size_t base = (size_t)t * n_qry;
@@ -813,6 +837,145 @@ int igd_align_dense(igd_handle *h,
             const uint32_t pay = (uint32_t)h_pay[base + q];
             if (matches) matches[base + q] = (int)(pay & 1023);
             if (alen) alen[base + q] = nB + ((int)(pay >> 10) & 1023);
+        }
+    }
+    return IGD_OK;
+}
+
+} // extern "C"
+
+// str(Seq(s).reverse_complement()) for upper-cased input (Bio.Seq's IUPAC table, as fasta.py:_COMP);
+// bytes outside the table stay as they are.
+static uint8_t g_comp[256];
+static bool g_comp_ready = false;
+static void init_comp()
+{
+    if (g_comp_ready) return;
+    for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
+    const char *from = "ACGTMRWSYKVHDBXNU", *to = "TGCAKYWSRMBDHVXNA";
+    for (int i = 0; from[i]; ++i) g_comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    g_comp_ready = true;
+}
+
+static int stage_reserve(igd_handle *h, size_t bytes)
+{
+    if (h->h_stage_cap >= bytes) return IGD_OK;
+    if (h->h_stage) { IGD_CUDA(cudaFreeHost(h->h_stage)); h->h_stage = nullptr; h->h_stage_cap = 0; }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    IGD_CUDA(cudaMallocHost(&h->h_stage, cap));
+    h->h_stage_cap = cap;
+    return IGD_OK;
+}
+
+extern "C" {
+
+int igd_score_fragments(igd_handle *h,
+                        const uint8_t *frag, const int32_t *frag_off, int32_t n_frag,
+                        const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                        const igd_scoring *sc, double *pi, double *alen, uint8_t *direction)
+{
+    if (!h || !frag_off || !gene_off || !sc || n_frag < 0 || n_gene < 0 || !pi || !alen) {
+        igd_set_error("bad arguments to igd_score_fragments"); return IGD_ERR_ARG;
+    }
+    if ((int64_t)n_frag * n_gene == 0) return IGD_OK;
+    init_comp();
+    // upper-cased fragments, identical ones scored once; targets 2u / 2u+1 = fragment u / its reverse complement
+    std::unordered_map<std::string, int32_t> seen;
+    std::vector<int32_t> uidx((size_t)n_frag, -1), toff(1, 0);
+    std::vector<uint8_t> tgt;
+    bool any_empty = false;
+    for (int i = 0; i < n_frag; ++i) {
+        const int n = frag_off[i + 1] - frag_off[i];
+        if (n < 0) { igd_set_error("fragment offsets must ascend"); return IGD_ERR_ARG; }
+        if (n == 0) { any_empty = true; continue; }
+        std::string u((const char *)frag + frag_off[i], (size_t)n);
+        for (char &c : u) if ((unsigned)(c - 'a') < 26u) c = (char)(c - 32);
+        auto it = seen.find(u);
+        if (it == seen.end()) {
+            const int32_t id = (int32_t)seen.size();
+            it = seen.emplace(std::move(u), id).first;
+            const std::string &f = it->first;
+            tgt.insert(tgt.end(), f.begin(), f.end());
+            toff.push_back((int32_t)tgt.size());
+            for (int k = n - 1; k >= 0; --k) tgt.push_back(g_comp[(uint8_t)f[(size_t)k]]);
+            toff.push_back((int32_t)tgt.size());
+        }
+        uidx[(size_t)i] = it->second;
+    }
+    const int32_t U = (int32_t)seen.size();
+    const size_t UG = (size_t)U * (size_t)n_gene;
+    std::vector<uint32_t> host_pick;
+    const uint32_t *pick = nullptr;
+    float ms_total = 0.f; int launches = 0; uint64_t cells = 0;
+    int rc;
+    if (U > 0) {
+        bool launched = false;
+        if ((rc = dense_launch(h, tgt.data(), toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched))) return rc;
+        if (launched) {
+            if ((rc = igd_reserve(h, S_PICK, UG * 4))) return rc;
+            if ((rc = stage_reserve(h, UG * 4))) return rc;
+            if ((rc = igd_launch_pick(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_QRYOFF],
+                                      U, n_gene, (uint32_t *)h->d_scratch[S_PICK]))) return rc;
+            IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_PICK], UG * 4, cudaMemcpyDeviceToHost, h->stream));
+            IGD_CUDA(cudaStreamSynchronize(h->stream));
+            IGD_CUDA(cudaEventElapsedTime(&h->timing.align_ms, h->ev0, h->ev1));
+            pick = (const uint32_t *)h->h_stage;
+        } else {                                       // some pair does not fit the packed kernels: pair-table path
+            const size_t np = 2 * UG;
+            std::vector<int32_t> s_(np), m_(np), l_(np);
+            if ((rc = igd_align_dense(h, tgt.data(), toff.data(), 2 * U, gene, gene_off, n_gene, sc, s_.data(), m_.data(), l_.data()))) return rc;
+            host_pick.resize(UG);
+            for (int32_t u = 0; u < U; ++u)
+                for (int32_t g = 0; g < n_gene; ++g) {
+                    const size_t f = (size_t)(2 * u) * n_gene + g, r = (size_t)(2 * u + 1) * n_gene + g;
+                    const bool fwd = m_[f] > m_[r];
+                    const size_t w = fwd ? f : r;
+                    host_pick[(size_t)u * n_gene + g] = (uint32_t)m_[w] | ((uint32_t)l_[w] << 10) | (fwd ? 0x80000000u : 0u);
+                }
+            pick = host_pick.data();
+        }
+        ms_total += h->timing.align_ms; launches += h->timing.align_launches; cells += h->timing.align_cells;
+    }
+    // an empty fragment stands for 'A' * len(gene) (py/IGDetective.py:339-340): one target pair per gene length
+    std::vector<uint32_t> empty_pick;
+    if (any_empty) {
+        std::unordered_map<int, int32_t> by_len;
+        std::vector<uint8_t> et; std::vector<int32_t> eoff(1, 0), pt, pq;
+        for (int32_t g = 0; g < n_gene; ++g) {
+            const int n = gene_off[g + 1] - gene_off[g];
+            auto it = by_len.find(n);
+            if (it == by_len.end()) {
+                it = by_len.emplace(n, (int32_t)by_len.size()).first;
+                et.insert(et.end(), (size_t)n, (uint8_t)'A'); eoff.push_back((int32_t)et.size());
+                et.insert(et.end(), (size_t)n, (uint8_t)'T'); eoff.push_back((int32_t)et.size());
+            }
+            pt.push_back(2 * it->second); pq.push_back(g);
+            pt.push_back(2 * it->second + 1); pq.push_back(g);
+        }
+        std::vector<int32_t> s_(pt.size()), m_(pt.size()), l_(pt.size());
+        if ((rc = igd_align_batch(h, et.data(), eoff.data(), (int32_t)eoff.size() - 1, gene, gene_off, n_gene,
+                                  pt.data(), pq.data(), (int64_t)pt.size(), sc, s_.data(), m_.data(), l_.data(), nullptr, nullptr))) return rc;
+        empty_pick.resize((size_t)n_gene);
+        for (int32_t g = 0; g < n_gene; ++g) {
+            const bool fwd = m_[2 * (size_t)g] > m_[2 * (size_t)g + 1];
+            const size_t w = 2 * (size_t)g + (fwd ? 0 : 1);
+            empty_pick[(size_t)g] = (uint32_t)m_[w] | ((uint32_t)l_[w] << 10) | (fwd ? 0x80000000u : 0u);
+        }
+        ms_total += h->timing.align_ms; launches += h->timing.align_launches; cells += h->timing.align_cells;
+    }
+    h->timing.align_ms = ms_total; h->timing.align_launches = launches; h->timing.align_cells = cells;
+    // BioAlign.PI(): (matches - 1) / len * 100 in float64, left to right (py/extract_aligned_genes.py:44-45)
+    for (int i = 0; i < n_frag; ++i) {
+        const uint32_t *row = uidx[(size_t)i] >= 0 ? pick + (size_t)uidx[(size_t)i] * n_gene : empty_pick.data();
+        double *po = pi + (size_t)i * n_gene, *lo = alen + (size_t)i * n_gene;
+        uint8_t *dd = direction ? direction + (size_t)i * n_gene : nullptr;
+        for (int32_t g = 0; g < n_gene; ++g) {
+            const uint32_t w = row[g];
+            const double m = (double)((int)(w & 1023u) - 1), l = (double)((w >> 10) & 0x1fffffu);
+            po[g] = m / l * 100.0;
+            lo[g] = l;
+            if (dd) dd[g] = (w & 0x80000000u) ? '+' : '-';
         }
     }
     return IGD_OK;

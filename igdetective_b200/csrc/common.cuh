@@ -65,8 +65,10 @@ struct igd_handle {
     int32_t last_spacer[4] = {0, 0, 0, 0};
 
     // generic growable device scratch for the aligner
-    void *d_scratch[13] = {nullptr};
-    size_t scratch_cap[13] = {0};
+    void *d_scratch[14] = {nullptr};
+    size_t scratch_cap[14] = {0};
+    void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
+    size_t h_stage_cap = 0;
 
     igd_timing timing = {};
 };
@@ -104,4 +106,7 @@ struct igd_align_job {
     unsigned int *d_counter;
 };
 int igd_align_bucket_of(int target_len);
+// out[u][q] = matches | alen << 10 | forward << 31 of the better orientation of fragment u (rows 2u, 2u+1 of pay)
+int igd_launch_pick(igd_handle *h, const uint32_t *d_pay, const int32_t *d_qry_off, int32_t n_unique, int32_t n_qry,
+                    uint32_t *d_out);
 int igd_launch_gotoh(igd_handle *h, const igd_align_job &job);

@@ -18,6 +18,7 @@
 // bottom row of each lane travels to the next lane by shuffle.  No shared memory, no tensor
 // cores: the work is integer add / max / select.
 #include "common.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace {
@@ -103,7 +104,6 @@ gotoh_kernel(const GotohParams P)
                 }
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
-                const float bf = (float)b;
                 const bool lastcol = (j == nB);
                 const int qo4 = lastcol ? P.qeo4 : P.qio4;
                 const int qe4 = lastcol ? P.qee4 + 1 : P.qie4 + 1;   // +1: priority of the Ix state on the extend candidate
@@ -432,6 +432,35 @@ static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
     }
     igd_set_error("bad packed align bucket %d (layout %d)", job.bucket, job.packed);
     return IGD_ERR_ARG;
+}
+
+// ComputeAlignment's choice between the two orientations of a fragment (py/IGDetective.py:314-317):
+// forward iff its match count is strictly larger.  pay rows 2u / 2u+1 = fragment u / its reverse complement.
+__global__ void __launch_bounds__(256)
+pick_orientation_kernel(const uint32_t *pay, const int32_t *qry_off, int n_unique, int n_qry, uint32_t *out)
+{
+    const size_t n = (size_t)n_unique * n_qry;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t u = i / n_qry, q = i - u * n_qry;
+        const uint32_t f = pay[(2 * u) * n_qry + q], r = pay[(2 * u + 1) * n_qry + q];
+        const bool fwd = (f & 1023u) > (r & 1023u);
+        const uint32_t w = fwd ? f : r;
+        const uint32_t alen = (uint32_t)(qry_off[q + 1] - qry_off[q]) + ((w >> 10) & 1023u);
+        out[i] = (w & 1023u) | (alen << 10) | (fwd ? 0x80000000u : 0u);
+    }
+}
+
+int igd_launch_pick(igd_handle *h, const uint32_t *d_pay, const int32_t *d_qry_off, int32_t n_unique, int32_t n_qry,
+                    uint32_t *d_out)
+{
+    const size_t n = (size_t)n_unique * n_qry;
+    unsigned blocks = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8);
+    if (blocks < 1) blocks = 1;
+    pick_orientation_kernel<<<blocks, 256, 0, h->stream>>>(d_pay, d_qry_off, n_unique, n_qry, d_out);
+    h->timing.total_launches++;
+    h->timing.align_launches++;
+    IGD_CUDA(cudaGetLastError());
+    return IGD_OK;
 }
 
 int igd_launch_gotoh(igd_handle *h, const igd_align_job &job)

@@ -202,6 +202,33 @@ class Engine:
         self.d2h_bytes += 2 * 4 * T * Q
         return res
 
+    def score_fragments(self, fragments, genes, scoring=None, direction=False):
+        """align_fragment_to_genes on the device (igd_score_fragments): float64 [F, G] matrices
+        (pi, alen) of the better orientation of every fragment against every gene; with
+        direction=True also a [F, G] uint8 matrix of '+' / '-'."""
+        fb, fo = fragments if isinstance(fragments, tuple) else concat(fragments)
+        gb, go = genes if isinstance(genes, tuple) else concat(genes)
+        fb = np.ascontiguousarray(fb, np.uint8)
+        gb = np.ascontiguousarray(gb, np.uint8)
+        fo = np.ascontiguousarray(fo, np.int32)
+        go = np.ascontiguousarray(go, np.int32)
+        F, G = len(fo) - 1, len(go) - 1
+        sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
+        pi = np.zeros((F, G), np.float64)
+        alen = np.zeros((F, G), np.float64)
+        dirs = np.zeros((F, G), np.uint8) if direction else None
+        if F and G:
+            _lib.check(self._lib.igd_score_fragments(
+                self._h, fb.ctypes.data if fb.size else None, fo.ctypes.data, F,
+                gb.ctypes.data if gb.size else None, go.ctypes.data, G, ctypes.byref(sc),
+                pi.ctypes.data, alen.ctypes.data, dirs.ctypes.data if direction else None))
+            t = self.timing()
+            self.align_ms_total += t["align_ms"]
+            self.align_cells_total += t["align_cells"]
+        self.h2d_bytes += 2 * fb.nbytes + 2 * fo.nbytes + gb.nbytes + go.nbytes
+        self.d2h_bytes += 4 * F * G
+        return (pi, alen, dirs) if direction else (pi, alen)
+
     def sync(self):
         _lib.check(self._lib.igd_sync(self._h))
 

@@ -80,49 +80,9 @@ def align_fragment_to_genes(fragments, canon_genes, scoring_scheme=None, gene=No
     F, G = len(fragments), len(genes)
     if F == 0 or G == 0:
         return np.zeros((F, G)), np.zeros((F, G))
-    targets, tindex = [], {}
-
-    def tid(s):
-        if s not in tindex:
-            tindex[s] = len(targets)
-            targets.append(s)
-            targets.append(reverse_complement(s))
-        return tindex[s]
-    # every (fragment, orientation) meets every gene: a dense batch.  Empty fragments stand for
-    # 'A' * len(gene) (:339-340), a different target per gene, and go through the pair-list call.
-    idx = np.zeros((F, 2), np.int32)
-    empty = []
-    for i, f in enumerate(fragments):
-        q = str(f).upper()
-        if len(q):
-            t = tid(q)
-            idx[i] = (t, t + 1)
-        else:
-            empty.append(i)
-            idx[i] = (0, 0)
-    m = np.zeros((F, 2, G), np.int32)
-    ln = np.ones((F, 2, G), np.int32)
-    if targets:
-        r = engine.align_dense(targets, genes)
-        m[:] = r["matches"][idx]
-        ln[:] = r["alen"][idx]
-    if empty:
-        et, eidx = [], {}
-        for g in genes:
-            if len(g) not in eidx:
-                eidx[len(g)] = len(et)
-                et.append("A" * len(g))
-                et.append(reverse_complement("A" * len(g)))
-        pt = np.array([[eidx[len(g)], eidx[len(g)] + 1] for g in genes], np.int32).T      # [2, G]
-        pq = np.broadcast_to(np.arange(G, dtype=np.int32), (2, G))
-        r = engine.align(et, genes, pt.reshape(-1), np.ascontiguousarray(pq).reshape(-1))
-        for i in empty:
-            m[i] = r["matches"].reshape(2, G)
-            ln[i] = r["alen"].reshape(2, G)
-    fwd = (m[:, 0, :] - 1) > (m[:, 1, :] - 1)
-    mm = np.where(fwd, m[:, 0, :], m[:, 1, :])
-    ll = np.where(fwd, ln[:, 0, :], ln[:, 1, :])
-    return pi_from(mm, ll), ll.astype(np.float64)
+    # upper-casing, the reverse-complement orientation, the choice between the two (:314-317), the
+    # 'A' * len(gene) stand-in of an empty fragment (:339-340) and PI happen behind the C ABI
+    return engine.score_fragments([str(f) for f in fragments], genes)
 
 
 class Alignment:

@@ -175,6 +175,22 @@ int igd_align_dense(igd_handle *h,
                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
                     const igd_scoring *sc, int32_t *score, int32_t *matches, int32_t *alen);
 
+/* Replaces align_fragment_to_genes(fragments, canon_genes, scheme, gene), py/IGDetective.py:319-360,
+ * i.e. ComputeAlignment (:307-317) for every (fragment, gene) pair followed by BioAlign.PI() / len()
+ * (py/extract_aligned_genes.py:38-45): each fragment is upper-cased (ASCII), aligned as it is and
+ * reverse-complemented (Bio.Seq's IUPAC table) against every gene; the forward orientation is kept
+ * iff it has strictly more matches; an empty fragment stands for 'A' * len(gene) (:339-340).
+ * Outputs are [n_frag][n_gene], fragment-major, float64 like the reference's matrices:
+ *   pi        (matches - 1) / len * 100, evaluated left to right in float64
+ *   alen      len(alignment) (the gene range)
+ *   direction '+' or '-' per pair (may be NULL)
+ * Both orientations run on the device, the choice is made there, and only one word per
+ * (fragment, gene) travels back. */
+int igd_score_fragments(igd_handle *h,
+                        const uint8_t *frag, const int32_t *frag_off, int32_t n_frag,
+                        const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                        const igd_scoring *sc, double *pi, double *alen, uint8_t *direction);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,4 +1,5 @@
-"""Wall-clock timeline of one resident step of the bench workload (where the non-kernel time goes)."""
+"""Wall-clock timeline of one resident step of the bench workload (where the non-kernel time goes):
+detect() with perf_counter wrappers around its stages and around the two C-ABI alignment calls."""
 import os
 import sys
 import time
@@ -19,21 +20,43 @@ contig, _ = bench.make_workload(2, int(100e6), motifs, canon)
 seqs = {"c": contig.tobytes().decode("latin-1")}
 eng = Engine(0, motifs)
 eng.load_contigs((contig, np.array([0, len(contig)], np.uint64)), ["c"])
-for rep in range(3):
-    T = [("start", time.perf_counter())]
-    mark = lambda n: T.append((n, time.perf_counter()))
-    scan = R.RssScan(eng, seqs, order="canonical", load=False); mark("scan+fetch")
-    info = {st: {sd: scan.contigwise(st, sd) for sd in "+-"} for st in R.SIGNAL_TYPES}; mark("contigwise x8")
-    info["D"] = {sd: R.combine_D_RSS(info["D_left"][sd], info["D_right"][sd], seqs, sd) for sd in "+-"}; mark("combine_D")
-    frags = {g: {sd: R.get_s_fragment_from_RSS(g, sd, info, seqs) for sd in "+-"} for g in "VJ"}; mark("fragments")
-    drows = I.d_gene_rows(seqs, info["D"]); mark("D rows")
-    for g in "VJ":
-        ids, glist = list(canon[g].keys()), list(canon[g].values())
-        flat = [f for sd in "+-" for c in frags[g][sd] for f in frags[g][sd][c]]
-        k0 = eng.align_ms_total
-        pi, ln = S.align_fragment_to_genes(flat, glist, engine=eng); mark("%s align_fragment_to_genes (kernel %.2f ms)" % (g, eng.align_ms_total - k0))
-        rows = I.vj_gene_rows(eng, seqs, g, info[g], frags[g], canon[g]); mark("%s vj_gene_rows incl. a second align" % g)
-    if rep == 2:
-        for (a, ta), (b, tb) in zip(T, T[1:]):
-            print("%-62s %7.2f ms" % (b, 1e3 * (tb - ta)))
-        print("total %.2f ms" % (1e3 * (T[-1][1] - T[0][1])))
+
+acc = {}
+
+
+def wrap(obj, name, label):
+    f = getattr(obj, name)
+
+    def g(*a, **k):
+        t0 = time.perf_counter()
+        r = f(*a, **k)
+        acc[label] = acc.get(label, 0.0) + time.perf_counter() - t0
+        return r
+    setattr(obj, name, g)
+
+
+wrap(eng, "align_dense", "C igd_align_dense")
+wrap(eng, "align", "C igd_align_batch (detail)")
+wrap(eng, "scan_rss", "C igd_scan + fetch")
+wrap(S, "align_fragment_to_genes", "align_fragment_to_genes")
+wrap(I, "align_fragment_to_genes", "align_fragment_to_genes")
+wrap(I, "compute_alignments", "compute_alignments")
+wrap(I, "vj_gene_rows", "vj_gene_rows")
+wrap(I, "d_gene_rows", "d_gene_rows")
+wrap(I, "combine_D_RSS", "combine_D_RSS")
+wrap(I, "get_s_fragment_from_RSS", "get_s_fragment_from_RSS")
+wrap(I, "RssScan", "RssScan()")
+
+for rep in range(4):
+    acc.clear()
+    k0 = eng.align_ms_total
+    eng.sync()
+    t0 = time.perf_counter()
+    I.detect(eng, seqs, canon, order="canonical", load=False)
+    eng.sync()
+    total = time.perf_counter() - t0
+    if rep == 3:
+        for k, v in acc.items():
+            print("%-34s %7.2f ms" % (k, 1e3 * v))
+        print("gotoh kernels (CUDA events)        %7.2f ms" % (eng.align_ms_total - k0))
+        print("detect() total                     %7.2f ms" % (1e3 * total))

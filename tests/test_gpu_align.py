@@ -169,3 +169,26 @@ def test_align_dense_equals_oracle(engine):
         assert np.array_equal(got["score"].ravel(), want["score"].astype(np.int64))
         assert np.array_equal(got["matches"].ravel(), want["matches"])
         assert np.array_equal(got["alen"].ravel(), want["end"] - want["start"])
+
+
+def test_score_fragments_equals_reference_loops(engine):
+    """igd_score_fragments = align_fragment_to_genes (py/IGDetective.py:319-360): both orientations,
+    the forward one only on strictly more matches, float64 PI; duplicates, lower case, IUPAC letters,
+    an empty fragment ('A' * len(gene)) and the pair-table fallback (a gene longer than 511)"""
+    rng = np.random.default_rng(21)
+    genes = list(canonical("combined_reference_genes")["V"].values())[:40]
+    frags = [rand_seq(rng, 350) for _ in range(3)]
+    frags += [(rand_seq(rng, 100) + synth.mutate(rng, genes[i], 0.1, 0.02))[-350:] for i in (1, 5, 9)]
+    frags += [O.revcomp((rand_seq(rng, 80) + synth.mutate(rng, genes[7], 0.05, 0.01))[-350:])]
+    frags += [frags[0], frags[4].lower(), "", rand_seq(rng, 60, "ACGTNRY"), "acgtn" * 30, rand_seq(rng, 1), ""]
+    for gl in (genes, genes[:6] + [rand_seq(rng, 600)]):
+        want_pi, want_len = O.align_fragment_to_genes(frags, gl, threads=8)
+        pi, ln, dirs = engine.score_fragments(frags, gl, direction=True)
+        assert pi.dtype == np.float64 and pi.shape == (len(frags), len(gl))
+        assert np.array_equal(pi, want_pi)            # bit-exact float64
+        assert np.array_equal(ln, want_len)
+        pairs = [(f if len(f) else "A" * len(g), k) for f in frags for k, g in enumerate(gl)]
+        want_dir = [d for d, _, _ in O.compute_alignment_batch(frags, gl, pairs, threads=8)]
+        assert [chr(c) for c in dirs.ravel()] == want_dir
+    assert engine.score_fragments([], genes)[0].shape == (0, len(genes))
+    assert engine.score_fragments(["", ""], genes[:3])[0].shape == (2, 3)
