@@ -206,7 +206,7 @@ def gpu_arm(a):
         "roofline": {"kernel": "gotoh_packed_kernel<32,11>", "bound": "alu", "achieved": kstat["gcups"] * kstat["ops_per_cell"] / 1e3,
                      "peak": int_peak, "unit": "T lane-ops/s", "frac": kstat["gcups"] * kstat["ops_per_cell"] / 1e3 / int_peak,
                      # dram bytes of one launch of this shape from the ncu --set full capture in profiles/ (inputs are KB per pair)
-                     "traffic": 1068288 if a.mbases == 100.0 else None,
+                     "traffic": 1378816 if a.mbases == 100.0 else None,
                      "gcups": kstat["gcups"], "alu_ops_per_cell": kstat["ops_per_cell"],
                      "peak_source": "148 SMs x 64 ALU lanes/clk x SM clock sampled during the run"},
         # the HBM-bound kernel of the path (north star: scan vs HBM roofline), 0.25 algorithmic bytes per base

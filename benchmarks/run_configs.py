@@ -203,19 +203,44 @@ def config4(eng, canon, scale):
         if i % 3 == 0:
             w = w[:250] + w[250:600].lower() + w[600:]          # soft-masked stretch
         wf.append(w)
+    # under torchrun every rank builds the same candidate lists and scores one contiguous block of each,
+    # cut at equal DP cells (shard.partition_by_cost); the small per-candidate results are all-gathered
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        from igdetective_b200 import shard
+        shard.all_gather_lists([0])                             # first object collective pays communicator set-up
+        res["config"] += ", candidates sharded over %d GPUs by DP cells" % world
+        res["n_gpus"] = world
     for name, frs, gl, fn in (("V_flank_350", vf, vlist, "A"), ("J_flank_70", jf, jlist, "A"), ("window_800", wf, list(gv.items()), "B")):
+        lo, hi = (0, len(frs)) if world == 1 else shard.partition_by_cost([len(f) for f in frs], world)[rank]
+        if world > 1:
+            dist.barrier(); torch.cuda.synchronize()
         c0, m0, wall = eng.align_cells_total, eng.align_ms_total, time.perf_counter()
-        for b0 in range(0, len(frs), 512):                      # batches bound the pair tables (~1.2 M pairs)
-            chunk = frs[b0:b0 + 512]
+        small = []
+        for b0 in range(lo, hi, 512):                           # batches bound the result matrices (~1.2 M pairs)
+            chunk = frs[b0:min(hi, b0 + 512)]
             if fn == "A":
-                align_fragment_to_genes(chunk, gl, engine=eng)
+                pi, ln = align_fragment_to_genes(chunk, gl, engine=eng)
+                best = np.argmax(pi, axis=1)
+                small += [(int(b), float(pi[i, b]), float(ln[i, b])) for i, b in enumerate(best)]
             else:
-                window_alignments(eng, chunk, gl)
+                small += [(al.gene_seq, al.gene_id, al.pi, sd) for al, sd in window_alignments(eng, chunk, gl)]
+        if world > 1:
+            small = shard.all_gather_lists(small)
+        assert len(small) == len(frs)
         wall = time.perf_counter() - wall
         cells, ms = eng.align_cells_total - c0, eng.align_ms_total - m0
+        if world > 1:
+            mx = torch.tensor([wall, ms], dtype=torch.float64, device="cuda"); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = torch.tensor([float(cells)], dtype=torch.float64, device="cuda"); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            wall, ms, cells = mx[0].item(), mx[1].item(), sm[0].item()
         res[name] = {"cells": int(cells), "kernel_s": ms / 1e3, "gcups_kernel": cells / ms / 1e6 if ms else 0.0,
                      "wall_s": wall, "gcups_wall": cells / wall / 1e9}
-    print(json.dumps(res), flush=True)
+    if rank == 0:
+        print(json.dumps(res), flush=True)
 
 
 def ingest(eng, motifs, canon, scale):

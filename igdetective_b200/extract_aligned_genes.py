@@ -11,7 +11,7 @@ import pandas as pd
 from .datafiles import load_gene_records
 from .engine import Engine
 from .fasta import NativeFasta, read_fasta
-from .scoring import window_alignments
+from .scoring import Alignment, window_alignments
 
 _BASES = "TCAG"
 _AAS = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
@@ -63,21 +63,41 @@ def ProcessSamFile(sam_file):
     return position_dict
 
 
-def find_genes(engine, contig_dict, position_dict, genes, gene_len=400, batch=256):
+def find_genes(engine, contig_dict, position_dict, genes, gene_len=400, batch=256, rank=0, world=1, group=None):
     """:156-184.  Whether a position is used depends on whether the previous used position produced
-    a gene (prev_pos moves only then), so windows are scored in batches of candidates whose
-    acceptance cannot interact, i.e. sequentially resolved after one GPU batch per contig sweep."""
+    a gene (prev_pos moves only then), so every position's window is scored first (independent units,
+    one GPU batch per `batch` windows) and the reference's sequential rule is replayed afterwards.
+    With world > 1 (one process per GPU) the windows are split into contiguous blocks of equal DP cells
+    (shard.partition_by_cost), every rank scores its block, and one all-gather of the small result
+    tuples gives every rank the full list: no data-path collective, same output for any world size."""
+    from . import shard
     df = {k: [] for k in ('Contig', 'Pos', 'Seq', 'AASeq', 'PI', 'BestHit', 'Productive', 'Strand')}
+    items = [(c_id, p) for c_id in position_dict for p in sorted(position_dict[c_id])]
+    glen = sum(len(g[1]) for g in genes)
+
+    def window(c_id, p):
+        s = contig_dict[c_id]
+        return s[max(0, p - gene_len):min(len(s), p + gene_len)]
+    if world > 1:
+        costs = [(min(len(contig_dict[c]), p + gene_len) - max(0, p - gene_len)) * glen for c, p in items]
+        lo, hi = shard.partition_by_cost(costs, world)[rank]
+    else:
+        lo, hi = 0, len(items)
+    mine = []
+    for b0 in range(lo, hi, batch):
+        chunk = items[b0:min(hi, b0 + batch)]
+        for a, strand in window_alignments(engine, [window(c, p) for c, p in chunk], genes):
+            mine.append((a.gene_seq, a.gene_id, a.pi, strand))
+    everything = shard.all_gather_lists(mine, group) if world > 1 else mine
+    scored = {}
+    for (c_id, p), (seq, gid, pi, strand) in zip(items, everything):
+        a = Alignment()
+        if seq != "":
+            a.Initiate(seq, gid, pi)
+        scored[(c_id, p)] = (a, strand)
     for c_id in position_dict:
-        contig_seq = contig_dict[c_id]
         positions = sorted(position_dict[c_id])
-        # score every position's window once (a superset of the windows the reference aligns) ...
-        results = {}
-        for b0 in range(0, len(positions), batch):
-            chunk = positions[b0:b0 + batch]
-            windows = [contig_seq[max(0, p - gene_len):min(len(contig_seq), p + gene_len)] for p in chunk]
-            for p, r in zip(chunk, window_alignments(engine, windows, genes)):
-                results[p] = r
+        results = {p: scored[(c_id, p)] for p in positions}
         # ... then replay the reference's sequential skip rule
         prev_pos = -1
         for pos in positions:
@@ -94,17 +114,39 @@ def find_genes(engine, contig_dict, position_dict, genes, gene_len=400, batch=25
     return df
 
 
+def _dist_rank_world():
+    """(rank, world) of a torchrun launch (one process per GPU), (0, 1) otherwise."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
 def main(genome_fasta, gene_fasta, output_dir, engine=None, sam_file=None, device=0):
-    PrepareOutputDir(output_dir)
-    if sam_file is None:
-        print('Running minimap...')
-        print('Alignment of IG genes ' + gene_fasta + ' to ' + genome_fasta)
-        sam_file = os.path.join(output_dir, 'alignment.sam')
-        os.system('minimap2 -a ' + genome_fasta + ' ' + gene_fasta + ' -o ' + sam_file + '> /dev/null 2>&1')
-    print('Processing SAM file...')
+    """py/extract_aligned_genes.py:129-194.  Inside an initialised torch.distributed group the windows
+    are scored in shards (find_genes) and rank 0 alone runs minimap2 and writes the outputs."""
+    rank, world = _dist_rank_world()
+    if rank == 0:
+        PrepareOutputDir(output_dir)
+        if sam_file is None:
+            print('Running minimap...')
+            print('Alignment of IG genes ' + gene_fasta + ' to ' + genome_fasta)
+            sam_file = os.path.join(output_dir, 'alignment.sam')
+            os.system('minimap2 -a ' + genome_fasta + ' ' + gene_fasta + ' -o ' + sam_file + '> /dev/null 2>&1')
+    if world > 1:
+        import torch.distributed as dist
+        box = [sam_file]
+        dist.broadcast_object_list(box, src=0)      # also the barrier after minimap2
+        sam_file = box[0]
+    if rank == 0:
+        print('Processing SAM file...')
     position_dict = ProcessSamFile(sam_file)
     if len(position_dict) == 0:
-        print('no matches were found')
+        if rank == 0:
+            print('no matches were found')
         return
     if str(genome_fasta).endswith(".gz"):
         contig_dict = {rid: s for rid, s in read_fasta(genome_fasta) if rid in position_dict}
@@ -115,10 +157,12 @@ def main(genome_fasta, gene_fasta, output_dir, engine=None, sam_file=None, devic
     if own:
         engine = Engine(device)
     try:
-        df = find_genes(engine, contig_dict, position_dict, genes)
+        df = find_genes(engine, contig_dict, position_dict, genes, rank=rank, world=world)
     finally:
         if own:
             engine.close()
+    if rank != 0:
+        return
     df = pd.DataFrame(df)
     df.to_csv(os.path.join(output_dir, 'genes.tsv'), index=False, sep='\t')
     print('# detected genes: ' + str(len(df)))

@@ -19,6 +19,34 @@ def partition_contigs(lengths, world_size):
     return [sorted(x) for x in out]
 
 
+def partition_by_cost(costs, world_size):
+    """Scoring shards ("partition the pair list evenly by sum of cells"): contiguous
+    blocks of the item list with near-equal total cost.  Returns [(lo, hi) of rank r]; the blocks keep
+    the list order, so concatenating the per-rank results in rank order restores it."""
+    total = float(sum(costs))
+    cuts, acc, r = [0], 0.0, 1
+    for i, c in enumerate(costs):
+        acc += c
+        while r < world_size and acc >= total * r / world_size:
+            cuts.append(i + 1)
+            r += 1
+    while len(cuts) < world_size:
+        cuts.append(len(costs))
+    cuts.append(len(costs))
+    return [(cuts[k], cuts[k + 1]) for k in range(world_size)]
+
+
+def all_gather_lists(items, group=None):
+    """Concatenation, in rank order, of every rank's list (torch.distributed all_gather_object; gloo or nccl).
+    With partition_by_cost blocks this is the single-process list on every rank."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(items)
+    bucket = [None] * dist.get_world_size(group)
+    dist.all_gather_object(bucket, list(items), group=group)
+    return [x for part in bucket for x in part]
+
+
 def merge_rows(per_rank_rows, contig_order):
     """per_rank_rows: list over ranks of {gene type: rows}; every row starts with (contig id, strand).
     Returns {gene type: rows} ordered as a single-process run emits them: strand '+' before '-',

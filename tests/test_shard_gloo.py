@@ -64,3 +64,66 @@ def test_two_rank_gather_equals_single_process():
         assert p.exitcode == 0
     single = shard.merge_rows([_rows_for(IDS)], IDS)
     assert merged == single
+
+
+# ---- scoring shards: the iterative stage's windows split by DP cells over the ranks --------------
+import numpy as np  # noqa: E402
+
+from igdetective_b200 import extract_aligned_genes as X  # noqa: E402
+from igdetective_b200.scoring import Alignment  # noqa: E402
+
+_RNG = np.random.default_rng(5)
+CONTIGS = {"a": "".join("ACGT"[i] for i in _RNG.integers(0, 4, 30_000)),
+           "b": "".join("ACGT"[i] for i in _RNG.integers(0, 4, 900)),
+           "c": "".join("ACGT"[i] for i in _RNG.integers(0, 4, 12_000))}
+POSITIONS = {"a": [50, 120, 700, 5000, 5100, 5600, 29_990], "b": [10, 450, 880], "c": [6000, 6300, 6900, 11_000]}
+GENES = [("g%d" % i, "ACGT" * (70 + i)) for i in range(5)]
+
+
+def _fake_window_alignments(engine, windows, genes):
+    """stand-in for the GPU batch: a result that depends only on the window text"""
+    out = []
+    for w in windows:
+        a = Alignment()
+        h = sum(map(ord, w)) % 7
+        if h:
+            a.Initiate(w[h:h + 60].upper(), genes[h % len(genes)][0], 60.0 + h)
+        out.append((a, "+" if h % 2 else "-"))
+    return out
+
+
+def _score_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X.window_alignments = _fake_window_alignments
+    df = X.find_genes(None, CONTIGS, POSITIONS, GENES, batch=3, rank=rank, world=world)
+    q.put((rank, df))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_partition_by_cost():
+    for world in (1, 2, 3, 8):
+        for costs in ([1] * 10, [5, 1, 1, 1, 1, 1], [], [3], list(range(1, 40))):
+            parts = shard.partition_by_cost(costs, world)
+            assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == len(costs)
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            if costs:
+                assert max(sum(costs[lo:hi]) for lo, hi in parts) <= sum(costs) / world + max(costs)
+
+
+def test_two_rank_window_scoring_equals_single_process(monkeypatch):
+    monkeypatch.setattr(X, "window_alignments", _fake_window_alignments)
+    single = X.find_genes(None, CONTIGS, POSITIONS, GENES, batch=3)
+    assert len(single["Pos"]) >= 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_score_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == single and got[1] == single
