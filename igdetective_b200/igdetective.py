@@ -86,11 +86,13 @@ def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
     # the reference runs the same computation twice ('AFFINE' and 'MAXK', :467-468); once is enough
     pi_mat, len_mat = align_fragment_to_genes(flat, glist, "AFFINE", gene, engine=engine)
     winners, k = [], 0
+    best_all = np.argmax(pi_mat, axis=1).tolist() if len(flat) else []        # first maximum, like :469
+    rows_idx = np.arange(len(best_all))
+    pi_best, len_best = pi_mat[rows_idx, best_all], len_mat[rows_idx, best_all]
     for strand in (FWD, REV):
         for contig in fragments[strand]:
             for i, frag in enumerate(fragments[strand][contig]):
-                best = int(np.argmax(pi_mat[k]))
-                pi, maxk = pi_mat[k][best], len_mat[k][best]
+                best, pi, maxk = best_all[k], pi_best[k], len_best[k]
                 k += 1
                 if pi >= PI_CUTOFF["strict"][gene] or (pi >= PI_CUTOFF["relax"][gene] and maxk >= MAXK_CUTOFF[gene]):
                     winners.append((strand, contig, i, frag, best, pi, maxk))
