@@ -45,7 +45,7 @@ class IgdError(RuntimeError):
 EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "igd_sync", "igd_get_timing",
            "igd_set_motifs", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
-           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments")
+           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows")
 
 _lib = None
 
@@ -80,6 +80,8 @@ def load():
     lib.igd_align_dense.restype = ctypes.c_int
     lib.igd_score_fragments.argtypes = [vp, vp, vp, i32, vp, vp, i32, ctypes.POINTER(Scoring), vp, vp, vp]
     lib.igd_score_fragments.restype = ctypes.c_int
+    lib.igd_score_windows.argtypes = [vp, vp, vp, i32, vp, vp, i32, ctypes.POINTER(Scoring), vp, vp, vp, vp, vp]
+    lib.igd_score_windows.restype = ctypes.c_int
     lib.igd_fasta_open.restype = vp
     lib.igd_fasta_open.argtypes = [ctypes.c_char_p]
     lib.igd_fasta_close.restype = None

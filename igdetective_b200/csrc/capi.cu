@@ -844,7 +844,7 @@ int igd_align_dense(igd_handle *h,
 
 } // extern "C"
 
-// str(Seq(s).reverse_complement()) for upper-cased input (Bio.Seq's IUPAC table, as fasta.py:_COMP);
+// str(Seq(s).reverse_complement()): Bio.Seq's IUPAC table, case preserving (as fasta.py:_COMP);
 // bytes outside the table stay as they are.
 static uint8_t g_comp[256];
 static bool g_comp_ready = false;
@@ -852,7 +852,7 @@ static void init_comp()
 {
     if (g_comp_ready) return;
     for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
-    const char *from = "ACGTMRWSYKVHDBXNU", *to = "TGCAKYWSRMBDHVXNA";
+    const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxnUu", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxnAa";
     for (int i = 0; from[i]; ++i) g_comp[(uint8_t)from[i]] = (uint8_t)to[i];
     g_comp_ready = true;
 }
@@ -978,6 +978,87 @@ int igd_score_fragments(igd_handle *h,
             if (dd) dd[g] = (w & 0x80000000u) ? '+' : '-';
         }
     }
+    return IGD_OK;
+}
+
+int igd_score_windows(igd_handle *h,
+                      const uint8_t *win, const int32_t *win_off, int32_t n_win,
+                      const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                      const igd_scoring *sc, int32_t *best, double *pi, int32_t *start, int32_t *end, int32_t *ient)
+{
+    if (!h || !win_off || !gene_off || !sc || n_win < 0 || n_gene < 0 || !best || !pi || !start || !end || !ient) {
+        igd_set_error("bad arguments to igd_score_windows"); return IGD_ERR_ARG;
+    }
+    for (int w = 0; w < n_win; ++w) { best[w] = -1; pi[w] = 0.0; start[w] = end[w] = ient[w] = 0; }
+    if ((int64_t)n_win * n_gene == 0) return IGD_OK;
+    init_comp();
+    // targets 2w / 2w+1 = window w as it is (raw case) / its reverse complement
+    const size_t wbytes = (size_t)win_off[n_win] - (size_t)win_off[0];
+    std::vector<uint8_t> tgt(2 * wbytes);
+    std::vector<int32_t> toff((size_t)2 * n_win + 1);
+    size_t pos = 0;
+    toff[0] = 0;
+    for (int w = 0; w < n_win; ++w) {
+        const int n = win_off[w + 1] - win_off[w];
+        if (n < 0) { igd_set_error("window offsets must ascend"); return IGD_ERR_ARG; }
+        const uint8_t *src = win + win_off[w];
+        memcpy(tgt.data() + pos, src, (size_t)n); pos += (size_t)n;
+        toff[(size_t)2 * w + 1] = (int32_t)pos;
+        for (int k = n - 1; k >= 0; --k) tgt[pos++] = g_comp[src[k]];
+        toff[(size_t)2 * w + 2] = (int32_t)pos;
+    }
+    std::vector<int4> sel((size_t)n_win);
+    float ms_total = 0.f; int launches = 0; uint64_t cells = 0;
+    bool launched = false;
+    int rc;
+    if ((rc = dense_launch(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, sc, &launched))) return rc;
+    if (launched) {
+        if ((rc = igd_reserve(h, S_PICK, (size_t)n_win * sizeof(int4)))) return rc;
+        if ((rc = igd_launch_select_windows(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_TGTOFF],
+                                            (const int32_t *)h->d_scratch[S_QRYOFF], n_win, n_gene, (int4 *)h->d_scratch[S_PICK]))) return rc;
+        IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+        IGD_CUDA(cudaMemcpyAsync(sel.data(), h->d_scratch[S_PICK], (size_t)n_win * sizeof(int4), cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+        IGD_CUDA(cudaEventElapsedTime(&h->timing.align_ms, h->ev0, h->ev1));
+    } else {                                           // some pair does not fit the packed kernels: pair-table path
+        const size_t np = (size_t)2 * n_win * n_gene;
+        std::vector<int32_t> s_(np), m_(np), l_(np);
+        if ((rc = igd_align_dense(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, sc, s_.data(), m_.data(), l_.data()))) return rc;
+        for (int w = 0; w < n_win; ++w) {
+            long long bn = 0, bd = 1; int bi = -1, bm = 0;
+            for (int k = 0; k < 2 * n_gene; ++k) {
+                const size_t i = (size_t)(2 * w + k / n_gene) * n_gene + (size_t)(k % n_gene);
+                if (m_[i] < 1) continue;
+                const long long num = m_[i] - 1, den = l_[i];
+                if (bi < 0 || num * bd >= bn * den) { bn = num; bd = den; bi = k; bm = m_[i]; }
+            }
+            sel[(size_t)w] = make_int4(bi, bm, (int)bd, 0);
+        }
+    }
+    ms_total += h->timing.align_ms; launches += h->timing.align_launches; cells += h->timing.align_cells;
+    // the winner of each window is aligned once more for its range and query sequence (:95-99 use the BioAlign object)
+    std::vector<int32_t> pt, pq, who;
+    for (int w = 0; w < n_win; ++w) {
+        const int k = sel[(size_t)w].x;
+        if (k < 0) continue;
+        pt.push_back(2 * w + k / n_gene); pq.push_back(k % n_gene); who.push_back(w);
+    }
+    if (!pt.empty()) {
+        const size_t n = pt.size();
+        std::vector<int32_t> s_(n), m_(n), l_(n), st_(n), ie_(n);
+        if ((rc = igd_align_batch(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, pt.data(), pq.data(), (int64_t)n,
+                                  sc, s_.data(), m_.data(), l_.data(), st_.data(), ie_.data()))) return rc;
+        ms_total += h->timing.align_ms; launches += h->timing.align_launches; cells += h->timing.align_cells;
+        for (size_t i = 0; i < n; ++i) {
+            const int w = who[i];
+            const int4 v = sel[(size_t)w];
+            if (m_[i] != v.y || l_[i] != v.z) { igd_set_error("internal: packed and two-register kernels disagree"); return IGD_ERR_INTERNAL; }
+            best[w] = v.x;
+            pi[w] = (double)(v.y - 1) / (double)v.z * 100.0;
+            start[w] = st_[i]; end[w] = st_[i] + l_[i]; ient[w] = ie_[i];
+        }
+    }
+    h->timing.align_ms = ms_total; h->timing.align_launches = launches; h->timing.align_cells = cells;
     return IGD_OK;
 }
 

@@ -107,6 +107,9 @@ struct igd_align_job {
 };
 int igd_align_bucket_of(int target_len);
 // out[u][q] = matches | alen << 10 | forward << 31 of the better orientation of fragment u (rows 2u, 2u+1 of pay)
+// out[w] = {o * n_qry + g of the last maximal PI >= 0 over [window, RC] x genes, or -1; matches; len; 0}
+int igd_launch_select_windows(igd_handle *h, const uint32_t *d_pay, const int32_t *d_tgt_off, const int32_t *d_qry_off,
+                              int32_t n_win, int32_t n_qry, int4 *d_out);
 int igd_launch_pick(igd_handle *h, const uint32_t *d_pay, const int32_t *d_qry_off, int32_t n_unique, int32_t n_qry,
                     uint32_t *d_out);
 int igd_launch_gotoh(igd_handle *h, const igd_align_job &job);

@@ -450,6 +450,50 @@ pick_orientation_kernel(const uint32_t *pay, const int32_t *qry_off, int n_uniqu
     }
 }
 
+// extract_aligned_genes.ComputeAlignment's scan (py/extract_aligned_genes.py:89-100) over
+// [window, RC(window)] x genes in that order, keeping the LAST maximum of PI = (matches-1)/len*100 among
+// PI >= 0 (best_pi starts at 0, the test is >=).  Fractions are compared exactly by cross-multiplication
+// (equal rationals give equal float64 PI, different ones differ by far more than an ulp).
+// One warp per window; pay rows 2w / 2w+1 = window w / its reverse complement.  out[w] = {index o*G+g or -1, matches, len, 0}.
+__global__ void __launch_bounds__(256)
+select_window_best_kernel(const uint32_t *pay, const int32_t *tgt_off, const int32_t *qry_off, int n_win, int n_qry, int4 *out)
+{
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= n_win) return;
+    long long bn = 0, bd = 1; int bi = -1, bm = 0;
+    for (int k = lane; k < 2 * n_qry; k += 32) {
+        const int o = k >= n_qry ? 1 : 0, g = k - o * n_qry, t = 2 * w + o;
+        if (tgt_off[t + 1] == tgt_off[t]) continue;                 // empty target: no matches, PI < 0
+        const uint32_t p = pay[(size_t)t * n_qry + g];
+        const int m = (int)(p & 1023u);
+        if (m < 1) continue;
+        const long long num = m - 1, den = (qry_off[g + 1] - qry_off[g]) + (int)((p >> 10) & 1023u);
+        if (bi < 0 || num * bd >= bn * den) { bn = num; bd = den; bi = k; bm = m; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long on = __shfl_xor_sync(0xffffffffu, bn, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o), om = __shfl_xor_sync(0xffffffffu, bm, o);
+        if (oi >= 0) {
+            const long long l = on * bd, r = bn * od;
+            if (bi < 0 || l > r || (l == r && oi > bi)) { bn = on; bd = od; bi = oi; bm = om; }
+        }
+    }
+    if (lane == 0) out[w] = make_int4(bi, bm, (int)bd, 0);
+}
+
+int igd_launch_select_windows(igd_handle *h, const uint32_t *d_pay, const int32_t *d_tgt_off, const int32_t *d_qry_off,
+                              int32_t n_win, int32_t n_qry, int4 *d_out)
+{
+    const unsigned blocks = (unsigned)(((size_t)n_win * 32 + 255) / 256);
+    select_window_best_kernel<<<blocks ? blocks : 1, 256, 0, h->stream>>>(d_pay, d_tgt_off, d_qry_off, n_win, n_qry, d_out);
+    h->timing.total_launches++;
+    h->timing.align_launches++;
+    IGD_CUDA(cudaGetLastError());
+    return IGD_OK;
+}
+
 int igd_launch_pick(igd_handle *h, const uint32_t *d_pay, const int32_t *d_qry_off, int32_t n_unique, int32_t n_qry,
                     uint32_t *d_out)
 {

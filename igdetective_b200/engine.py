@@ -229,6 +229,33 @@ class Engine:
         self.d2h_bytes += 4 * F * G
         return (pi, alen, dirs) if direction else (pi, alen)
 
+    def score_windows(self, windows, genes, scoring=None):
+        """extract_aligned_genes.ComputeAlignment for many raw-case windows (igd_score_windows): dict of
+        per-window arrays best (orientation * G + gene, -1 = none), pi (float64), start, end, ient."""
+        wb, wo = windows if isinstance(windows, tuple) else concat(windows)
+        gb, go = genes if isinstance(genes, tuple) else concat(genes)
+        wb = np.ascontiguousarray(wb, np.uint8)
+        gb = np.ascontiguousarray(gb, np.uint8)
+        wo = np.ascontiguousarray(wo, np.int32)
+        go = np.ascontiguousarray(go, np.int32)
+        W, G = len(wo) - 1, len(go) - 1
+        sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
+        res = {k: np.zeros(W, np.int32) for k in ("best", "start", "end", "ient")}
+        res["best"][:] = -1
+        res["pi"] = np.zeros(W, np.float64)
+        if W and G:
+            _lib.check(self._lib.igd_score_windows(
+                self._h, wb.ctypes.data if wb.size else None, wo.ctypes.data, W,
+                gb.ctypes.data if gb.size else None, go.ctypes.data, G, ctypes.byref(sc),
+                res["best"].ctypes.data, res["pi"].ctypes.data, res["start"].ctypes.data,
+                res["end"].ctypes.data, res["ient"].ctypes.data))
+            t = self.timing()
+            self.align_ms_total += t["align_ms"]
+            self.align_cells_total += t["align_cells"]
+        self.h2d_bytes += 2 * wb.nbytes + 2 * wo.nbytes + gb.nbytes + go.nbytes
+        self.d2h_bytes += 16 * W + 16 * W
+        return res
+
     def sync(self):
         _lib.check(self._lib.igd_sync(self._h))
 

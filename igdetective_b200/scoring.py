@@ -104,39 +104,18 @@ def window_alignments(engine, windows, genes):
     [window, RC(window)] x genes, keeping the LAST maximum of PI (>=, from 0).
     Returns [(Alignment, strand)]."""
     G = len(genes)
-    targets = []
-    for w in windows:
-        targets.append(w)
-        targets.append(reverse_complement(w))
-    W = len(windows)
-    out = []
-    if W == 0 or G == 0:
+    if len(windows) == 0 or G == 0:
         return [(Alignment(), "") for _ in windows]
-    r = engine.align_dense(targets, [g[1] for g in genes])
-    pi = pi_from(r["matches"], r["alen"]).reshape(W, 2 * G)
-    # last index attaining the maximum, provided the maximum is >= 0 (best_pi starts at 0)
-    best = 2 * G - 1 - np.argmax(pi[:, ::-1], axis=1)
-    need = []
-    for w in range(W):
-        if pi[w, best[w]] >= 0:
-            need.append((w, int(best[w])))
-    detail = {}
-    if need:
-        dt = [2 * w + b // G for w, b in need]
-        dq = [b % G for w, b in need]
-        d = engine.align(targets, [g[1] for g in genes], dt, dq, detail=True)
-        for i, (w, b) in enumerate(need):
-            detail[w] = (b, d["start"][i], d["end"][i], d["ient"][i])
-    for w in range(W):
+    windows = [str(w) for w in windows]
+    r = engine.score_windows(windows, [g[1] for g in genes])
+    out = []
+    for w, b in enumerate(r["best"].tolist()):
         a = Alignment()
-        if w not in detail:
+        s, e, ie = int(r["start"][w]), int(r["end"][w]), int(r["ient"][w])
+        if b < 0 or e - s == 0:
             out.append((a, ""))
             continue
-        b, s, e, ie = detail[w]
-        if e - s == 0:
-            out.append((a, ""))
-            continue
-        seq = targets[2 * w + b // G][int(s):int(ie)].upper()
-        a.Initiate(seq, genes[b % G][0], float(pi[w, b]))
+        query = windows[w] if b < G else reverse_complement(windows[w])
+        a.Initiate(query[s:ie].upper(), genes[b % G][0], float(r["pi"][w]))
         out.append((a, "+-"[b // G]))
     return out

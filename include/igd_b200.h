@@ -31,6 +31,7 @@ extern "C" {
 #define IGD_ERR_TOO_LONG    -4   /* sequence longer than the kernel limits below */
 #define IGD_ERR_UNSUPPORTED -5   /* scoring scheme outside what the kernel implements */
 #define IGD_ERR_CAPACITY    -6   /* output buffer too small */
+#define IGD_ERR_INTERNAL    -7   /* two kernels of the library disagree: a bug, never a property of the input */
 
 #define IGD_MAX_TARGET_LEN  1023 /* fragment / window rows held in registers (32 lanes x 32); 10-bit payload fields */
 #define IGD_MAX_QUERY_LEN   1023 /* gene columns; bounded by the 10-bit payload fields */
@@ -190,6 +191,21 @@ int igd_score_fragments(igd_handle *h,
                         const uint8_t *frag, const int32_t *frag_off, int32_t n_frag,
                         const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
                         const igd_scoring *sc, double *pi, double *alen, uint8_t *direction);
+
+/* Replaces extract_aligned_genes.ComputeAlignment(aligner, [window, RC(window)], ['+', '-'], gene_seqs),
+ * py/extract_aligned_genes.py:85-105, for many windows at once.  Windows are raw case (the DP compares
+ * raw bytes, the match count upper-cased ones, :12-13); the reverse complement keeps the case.  Per
+ * window, over the reference's scan order (orientation-major, genes inner) the LAST alignment with
+ * maximal PI among PI >= 0 is kept (best_pi starts at 0 and the test is >=, :96-100):
+ *   best   orientation * n_gene + gene index, or -1 when no alignment has PI >= 0 (Alignment stays empty)
+ *   pi     its PI, float64 (matches-1)/len*100
+ *   start, end   BioAlign.AlignmentRange() ; ient: QuerySeq() == upper(chosen query[start:ient])
+ * The dense batch runs in the packed kernels, the choice is made on the device, and only the winners
+ * go through the two-register kernel for their range. */
+int igd_score_windows(igd_handle *h,
+                      const uint8_t *win, const int32_t *win_off, int32_t n_win,
+                      const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                      const igd_scoring *sc, int32_t *best, double *pi, int32_t *start, int32_t *end, int32_t *ient);
 
 #ifdef __cplusplus
 }

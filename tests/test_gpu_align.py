@@ -192,3 +192,34 @@ def test_score_fragments_equals_reference_loops(engine):
         assert [chr(c) for c in dirs.ravel()] == want_dir
     assert engine.score_fragments([], genes)[0].shape == (0, len(genes))
     assert engine.score_fragments(["", ""], genes[:3])[0].shape == (2, 3)
+
+
+def test_score_windows_equals_reference_loop(engine):
+    """igd_score_windows = extract_aligned_genes.ComputeAlignment (py/extract_aligned_genes.py:85-105):
+    raw-case windows, both orientations, LAST maximum of PI among PI >= 0; soft-masked stretches, a
+    window with no match at all, duplicated genes (ties resolved towards the later one), short
+    windows at a contig end, and the pair-table fallback (a gene longer than 511)"""
+    from igdetective_b200.scoring import window_alignments
+    rng = np.random.default_rng(33)
+    gl = list(canonical("combined_reference_genes")["V"].items())[:30]
+    genes = [(k, v.upper()) for k, v in gl]
+    genes += [("dup_of_3", genes[3][1]), ("dup_of_7", genes[7][1])]          # equal PI: the later gene must win
+    wins = []
+    for i in range(10):
+        g = genes[int(rng.integers(len(genes)))][1]
+        w = (rand_seq(rng, 300) + synth.mutate(rng, g, 0.1, 0.01) + rand_seq(rng, 500))[:800]
+        if i % 2:
+            w = w[:250] + w[250:600].lower() + w[600:]
+        if i % 3 == 0:
+            w = O.revcomp(w)
+        wins.append(w)
+    wins += [rand_seq(rng, 800), "N" * 50, rand_seq(rng, 37), genes[3][1], rand_seq(rng, 1)]
+    for gs in (genes, genes[:4] + [("long", rand_seq(rng, 600))]):
+        got = window_alignments(engine, wins, gs)
+        for w, (a, strand) in zip(wins, got):
+            want = O.window_best_alignment(w, gs, threads=4)
+            if want is None:
+                assert a.Empty() and strand == "", (w[:30], a.gene_seq[:30])
+            else:
+                assert (a.gene_seq, a.gene_id, a.pi, strand) == want, (w[:30], a.gene_id, want[1])
+    assert window_alignments(engine, [], genes) == []
