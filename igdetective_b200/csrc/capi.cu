@@ -517,6 +517,14 @@ int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity)
 
 // Can every intermediate DP value of an nA x nB pair be held in the packed kernel's 12-bit score
 // field, with the sentinel (-2000) below everything reachable and one extension short of wrapping?
+// 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
+static int case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t qbytes)
+{
+    for (size_t i = 0; i < qbytes; ++i) if ((unsigned)(qry[i] - 'a') < 26u) return 2;
+    for (size_t i = 0; i < tbytes; ++i) if ((unsigned)(tgt[i] - 'a') < 26u) return 1;
+    return 0;
+}
+
 static bool packed_scheme_ok(const igd_scoring *sc)
 {
     const int g[] = {sc->target_internal_open, sc->target_internal_extend, sc->query_internal_open,
@@ -569,9 +577,7 @@ int igd_align_batch(igd_handle *h,
 
     // validate, bucket by target length and kernel, detect lower-case letters
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
-    bool mixed = false;
-    for (size_t i = 0; i < tbytes && !mixed; ++i) mixed = (unsigned)(tgt[i] - 'a') < 26u;
-    for (size_t i = 0; i < qbytes && !mixed; ++i) mixed = (unsigned)(qry[i] - 'a') < 26u;
+    const int mixed = case_mix(tgt, tbytes, qry, qbytes);
     const bool detail = start || ient;
     const bool packed_ok = !detail && packed_scheme_ok(sc);
     constexpr int NB = 6;
@@ -744,10 +750,8 @@ static int dense_launch(igd_handle *h,
     if (!fast) return IGD_OK;
     IGD_CUDA(cudaSetDevice(h->device));
     h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
-    bool mixed = false;
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
-    for (size_t i = 0; i < tbytes && !mixed; ++i) mixed = (unsigned)(tgt[i] - 'a') < 26u;
-    for (size_t i = 0; i < qbytes && !mixed; ++i) mixed = (unsigned)(qry[i] - 'a') < 26u;
+    const int mixed = case_mix(tgt, tbytes, qry, qbytes);
     int rc;
     if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
     if ((rc = igd_reserve(h, S_TGTOFF, (size_t)(n_tgt + 1) * 4))) return rc;

@@ -98,7 +98,7 @@ struct igd_align_job {
     const int4 *d_runs;         // runs of this bucket (packed kernel): {target, first query, count, first output slot}
     int32_t n_work;
     int bucket;                 // kernel shape selector
-    bool mixed_case;
+    int mixed_case;             // 0: no lower-case letters; 1: only in targets; 2: in queries (and maybe targets)
     int packed;                 // 0: two-register kernel; 1 / 2: single-register kernel, short / long field layout
     int pay_mode;               // 0: (matches, internal Ix, lead)   1: (matches, internal Ix, trailing Ix)
     igd_scoring sc;

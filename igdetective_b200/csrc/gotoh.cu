@@ -203,15 +203,19 @@ struct PackedParams {
 // and re-initialises its column state while the lanes below are still finishing the previous gene.
 //
 // FPINC: the substitution increment is computed on the FMA pipe instead of the saturated ALU pipe.
-// Letters are held as floats (MIXED: raw + 256 * upper-cased, so equal raw bytes give a difference of
-// 0 and equal letters of different case a difference of +-32, nothing else does); eq = sat(1 - d*d)
-// is exactly 1.0 or 0.0, and the increment words are used as float BIT PATTERNS: a non-negative
+// Letters are held as floats; eq = sat(1 - d*d) is exactly 1.0 or 0.0, and the increment words are used as float BIT PATTERNS: a non-negative
 // integer below 2^24 is the bit pattern of the float n * 2^-149, whose sums are exact, so
 // fma(eq, match - mismatch, mismatch) yields the integer increment bit for bit (FADD + FFMA.SAT + FFMA
 // replace ISETP + SEL).  The host selects FPINC only when both increments lie in [0, 2^24).
+// With lower-case letters the DP compares raw bytes and the match count upper-cased ones: equal letters
+// of the same case are a match, equal letters of different case only count (mismatch + 1), so
+// inc = mismatch + [up(a) == up(b)] * (same case ? match - mismatch : 1).  The letters are upper-cased
+// once, the factor is a per-row constant (MIXED = 1: queries are all upper case) that a lower-case query
+// letter swaps by one more FFMA per cell (MIXED = 2).
 // resident CTAs per SM the register allocation aims for: 6 for the shapes that fit 80 registers
 constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : 1; }
-template <int G, int C, bool MIXED, bool LONG, bool FPINC>
+// MIXED: 0 = no lower-case letter anywhere; 1 = only targets may hold lower-case letters; 2 = queries may too.
+template <int G, int C, int MIXED, bool LONG, bool FPINC>
 __global__ void __launch_bounds__(GT_THREADS, packed_min_blocks(C))
 gotoh_packed_kernel(const PackedParams P)
 {
@@ -246,7 +250,7 @@ gotoh_packed_kernel(const PackedParams P)
         for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
 
         unsigned a[C];
-        float af[C];
+        float af[C], wdr[C];
         const float wx = __int_as_float(P.inc_mismatch), wd = __int_as_float(P.inc_match) - __int_as_float(P.inc_mismatch);
         const float w1 = __int_as_float(1);
         int D[C], Y[C], E[C];                                 // D(i, j-1) with priority, Iy(i, j-1) clean, D(i-1, j-1) clean
@@ -256,7 +260,8 @@ gotoh_packed_kernel(const PackedParams P)
             const int i = i0 + r + 1;
             const unsigned ch = (have && i <= nA) ? A[i - 1] : 0u;
             a[r] = MIXED ? (ch | (up8(ch) << 8)) : ch;
-            af[r] = (float)a[r];
+            af[r] = (float)(MIXED ? up8(ch) : ch);
+            wdr[r] = (ch - 'a' < 26u) ? w1 : wd;
             D[r] = P.qeo + P.qee * (i - 1) + PK_PR;           // D(i,0) = Ix(i,0), priority 1
             Y[r] = PK_NEG;
             E[r] = (i == 1) ? 0 : P.qeo + P.qee * (i - 2);    // clean D(i-1, 0)
@@ -274,7 +279,9 @@ gotoh_packed_kernel(const PackedParams P)
                 if (l == 0) { upD = P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j), priority 0
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
-                const float bf = (float)b;
+                const float bf = (float)(MIXED ? up8(braw) : braw);
+                const bool blow = MIXED == 2 && (braw - 'a' < 26u);
+                const float bsg = blow ? -1.0f : 1.0f, bof = blow ? wd + w1 : 0.0f;   // swaps wd <-> 1 in wdr[r]
                 const bool lastcol = (j == nB);
                 // an Ix move in an internal column counts one internal-Ix unit: the unit rides on the
                 // gap score constants, so both candidates carry it into the max
@@ -287,10 +294,10 @@ gotoh_packed_kernel(const PackedParams P)
                     if (FPINC) {
                         const float dd = af[r] - bf;
                         const float eq = __saturatef(fmaf(-dd, dd, 1.0f));
-                        if (MIXED) {
-                            const float du = fabsf(dd) - 32.0f;
-                            const float eu = __saturatef(fmaf(-du, du, 1.0f));
-                            inc = __float_as_int(fmaf(eq, wd, fmaf(eu, w1, wx)));
+                        if (MIXED == 2) {
+                            inc = __float_as_int(fmaf(eq, fmaf(wdr[r], bsg, bof), wx));
+                        } else if (MIXED == 1) {
+                            inc = __float_as_int(fmaf(eq, wdr[r], wx));
                         } else {
                             inc = __float_as_int(fmaf(eq, wd, wx));
                         }
@@ -340,7 +347,7 @@ gotoh_packed_kernel(const PackedParams P)
 }
 
 template <int G, int C, bool LONG>
-int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
+int launch_packed(igd_handle *h, const PackedParams &P, int mixed)
 {
     const unsigned warps_needed = (unsigned)((P.n_runs + (32 / G) - 1) / (32 / G));
     unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);
@@ -352,11 +359,12 @@ int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
     static const bool fp_allowed = !(getenv("IGD_GOTOH_FPINC") && atoi(getenv("IGD_GOTOH_FPINC")) == 0);
     const bool fp = fp_allowed && P.inc_match >= 0 && P.inc_match < (1 << 24) && P.inc_mismatch >= 0 && P.inc_mismatch + 1 < (1 << 24);
     if (fp) {
-        if (mixed) gotoh_packed_kernel<G, C, true, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
-        else       gotoh_packed_kernel<G, C, false, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
-    } else {
-        if (mixed) gotoh_packed_kernel<G, C, true, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
-        else       gotoh_packed_kernel<G, C, false, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        if (mixed == 2)      gotoh_packed_kernel<G, C, 2, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        else if (mixed == 1) gotoh_packed_kernel<G, C, 1, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        else                 gotoh_packed_kernel<G, C, 0, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+    } else {                 // the integer form compares raw and upper-cased bytes directly: one MIXED instance
+        if (mixed) gotoh_packed_kernel<G, C, 2, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
+        else       gotoh_packed_kernel<G, C, 0, LONG, false><<<blocks, GT_THREADS, 0, h->stream>>>(P);
     }
     h->timing.total_launches++;
     h->timing.align_launches++;
@@ -365,7 +373,7 @@ int launch_packed(igd_handle *h, const PackedParams &P, bool mixed)
 }
 
 template <int G, int C>
-int launch(igd_handle *h, const GotohParams &P, bool mixed)
+int launch(igd_handle *h, const GotohParams &P, int mixed)
 {
     const unsigned warps_needed = (unsigned)((P.n_work + (32 / G) - 1) / (32 / G));
     unsigned blocks = (warps_needed + (GT_THREADS / 32) - 1) / (GT_THREADS / 32);

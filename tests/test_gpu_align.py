@@ -223,3 +223,24 @@ def test_score_windows_equals_reference_loop(engine):
             else:
                 assert (a.gene_seq, a.gene_id, a.pi, strand) == want, (w[:30], a.gene_id, want[1])
     assert window_alignments(engine, [], genes) == []
+
+
+def test_align_lower_case_on_either_side(engine):
+    """lower-case letters in the queries, in the targets, in both (same letter: same case is a match, different
+    case only counts), with IUPAC letters in between -- every case class of the packed kernel"""
+    rng = np.random.default_rng(44)
+    base = [rand_seq(rng, n) for n in (350, 120, 33, 800)]
+
+    def mask(s, p):
+        m = rng.random(len(s)) < p
+        return "".join(c.lower() if k else c for c, k in zip(s, m))
+    rel = [synth.mutate(rng, base[0], 0.1, 0.02), synth.mutate(rng, base[1], 0.05, 0.0), base[2], base[0][50:300]]
+    for tp, qp in ((0.0, 0.4), (0.4, 0.0), (0.5, 0.5), (1.0, 1.0)):
+        targets = [mask(s, tp) for s in base] + ["acgtNNacgtRYACGT" * 5]
+        queries = [mask(s, qp) for s in rel] + ["ACGTnnACGTryacgt" * 3]
+        pt, pq = np.meshgrid(np.arange(len(targets)), np.arange(len(queries)), indexing="ij")
+        compare(engine, targets, queries, pt.ravel(), pq.ravel())
+        want = O.align_stats(targets, queries, pt.ravel(), pq.ravel(), threads=8)
+        got = engine.align_dense(targets, queries)
+        assert np.array_equal(got["matches"].ravel(), want["matches"])
+        assert np.array_equal(got["alen"].ravel(), want["end"] - want["start"])
