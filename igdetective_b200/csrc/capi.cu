@@ -77,6 +77,7 @@ igd_handle *igd_create(int device)
            && cudaMalloc(&h->d_lut7, 16384) == cudaSuccess && cudaMalloc(&h->d_lut9, 262144) == cudaSuccess
            && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
     if (!ok) { igd_cuda_fail(cudaGetLastError(), "igd_create allocations"); igd_destroy(h); return nullptr; }
+    if (igd_probe_fp_increment(h, &h->fp_increment_ok) != IGD_OK) { igd_destroy(h); return nullptr; }
     return h;
 }
 

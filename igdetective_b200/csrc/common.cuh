@@ -34,6 +34,7 @@ struct igd_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 148;
+    bool fp_increment_ok = false;  // exact denormal arithmetic verified on this device (gotoh.cu, FPINC)
 
     // motif tables (kernel index order: (hi bits << k) | lo bits, first base = bit 0)
     uint8_t *d_lut7 = nullptr;    // 16384 flags: bit t = strand +, bit 4+t = strand -
@@ -106,6 +107,7 @@ struct igd_align_job {
     unsigned int *d_counter;
 };
 int igd_align_bucket_of(int target_len);
+int igd_probe_fp_increment(igd_handle *h, bool *ok);
 // out[u][q] = matches | alen << 10 | forward << 31 of the better orientation of fragment u (rows 2u, 2u+1 of pay)
 // out[w] = {o * n_qry + g of the last maximal PI >= 0 over [window, RC] x genes, or -1; matches; len; 0}
 int igd_launch_select_windows(igd_handle *h, const uint32_t *d_pay, const int32_t *d_tgt_off, const int32_t *d_qry_off,

@@ -357,7 +357,7 @@ int launch_packed(igd_handle *h, const PackedParams &P, int mixed)
     if (blocks < 1) blocks = 1;
     // increments usable as float bit patterns (see FPINC above); IGD_GOTOH_FPINC=0 forces the integer form
     static const bool fp_allowed = !(getenv("IGD_GOTOH_FPINC") && atoi(getenv("IGD_GOTOH_FPINC")) == 0);
-    const bool fp = fp_allowed && P.inc_match >= 0 && P.inc_match < (1 << 24) && P.inc_mismatch >= 0 && P.inc_mismatch + 1 < (1 << 24);
+    const bool fp = fp_allowed && h->fp_increment_ok && P.inc_match >= 0 && P.inc_match < (1 << 24) && P.inc_mismatch >= 0 && P.inc_mismatch + 1 < (1 << 24);
     if (fp) {
         if (mixed == 2)      gotoh_packed_kernel<G, C, 2, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
         else if (mixed == 1) gotoh_packed_kernel<G, C, 1, LONG, true><<<blocks, GT_THREADS, 0, h->stream>>>(P);
@@ -440,6 +440,29 @@ static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
     }
     igd_set_error("bad packed align bucket %d (layout %d)", job.bucket, job.packed);
     return IGD_ERR_ARG;
+}
+
+// The FPINC instances rely on exact denormal arithmetic (no flush-to-zero): checked once per handle with the
+// very operations the kernel uses; a failure only switches the library to the integer form.
+__global__ void probe_denormal_kernel(int a, int b, int *out)
+{
+    const float wx = __int_as_float(b), wd = __int_as_float(a) - __int_as_float(b), w1 = __int_as_float(1);
+    const float eq = __saturatef(fmaf(-0.0f, 0.0f, 1.0f)), ne = __saturatef(fmaf(-3.0f, 3.0f, 1.0f));
+    out[0] = __float_as_int(fmaf(eq, wd, wx));                       // a
+    out[1] = __float_as_int(fmaf(ne, wd, wx));                       // b
+    out[2] = __float_as_int(fmaf(eq, fmaf(wd, -1.0f, wd + w1), wx)); // b + 1
+}
+
+int igd_probe_fp_increment(igd_handle *h, bool *ok)
+{
+    const int a = (2 << 21) + (1 << 20) + 1, b = 1 << 20;
+    int *d = (int *)h->d_count + 96, host[3] = {0, 0, 0};          // scratch words past the counters in use
+    probe_denormal_kernel<<<1, 1, 0, h->stream>>>(a, b, d);
+    IGD_CUDA(cudaGetLastError());
+    IGD_CUDA(cudaMemcpyAsync(host, d, sizeof(host), cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    *ok = host[0] == a && host[1] == b && host[2] == b + 1;
+    return IGD_OK;
 }
 
 // ComputeAlignment's choice between the two orientations of a fragment (py/IGDetective.py:314-317):
