@@ -43,7 +43,7 @@ class IgdError(RuntimeError):
 
 
 EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "igd_sync", "igd_get_timing",
-           "igd_set_motifs", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
+           "igd_set_motifs", "igd_center_bitmap", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
            "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows")
 
@@ -69,6 +69,7 @@ def load():
     lib.igd_sync.argtypes = [vp]
     lib.igd_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     lib.igd_set_motifs.argtypes = [vp, vp, vp]
+    lib.igd_center_bitmap.argtypes = [vp, vp]
     lib.igd_load_contigs.argtypes = [vp, vp, vp, i32]
     lib.igd_scan.argtypes = [vp, vp, u64p]
     lib.igd_fetch_hits.argtypes = [vp, vp, ctypes.c_uint64]
@@ -93,7 +94,7 @@ def load():
     lib.igd_load_fasta.argtypes = [vp, vp]
     for name in ("igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense"):
         getattr(lib, name).restype = ctypes.c_int
-    for name in ("igd_sync", "igd_get_timing", "igd_set_motifs", "igd_load_contigs", "igd_scan",
+    for name in ("igd_sync", "igd_get_timing", "igd_set_motifs", "igd_center_bitmap", "igd_load_contigs", "igd_scan",
                  "igd_fetch_hits", "igd_scan_kmers", "igd_fetch_kmer_hits", "igd_align_batch"):
         getattr(lib, name).restype = ctypes.c_int
     _lib = lib

@@ -75,7 +75,7 @@ igd_handle *igd_create(int device)
            && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess
            && cudaMalloc(&h->d_count, 64 * sizeof(unsigned long long)) == cudaSuccess
            && cudaMalloc(&h->d_lut7, 16384) == cudaSuccess && cudaMalloc(&h->d_lut9, 262144) == cudaSuccess
-           && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
+           && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any9c, 32768) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
     if (!ok) { igd_cuda_fail(cudaGetLastError(), "igd_create allocations"); igd_destroy(h); return nullptr; }
     if (igd_probe_fp_increment(h, &h->fp_increment_ok) != IGD_OK) { igd_destroy(h); return nullptr; }
     return h;
@@ -86,7 +86,7 @@ void igd_destroy(igd_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any7);
+    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any9c); cudaFree(h->d_any7);
     cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
@@ -131,6 +131,26 @@ static inline unsigned revcomp_index(unsigned nat, int k)
     return r;
 }
 
+// Centre bitmap of the RSS scan: bit c (kernel index order) is set iff the 9-mer c, or a 9-mer that
+// overlaps it shifted by one base to the left or to the right, is in some nonamer set on either strand.
+// The three candidate nonamers of a spacer window (s-1, s, s+1; py/IGDetective.py:162-168) start at
+// x, x+1, x+2, so the 9-mer at x+1 missing from this bitmap proves that none of the three is a motif.
+int igd_center_bitmap(const uint8_t *flags9, uint32_t *bitmap)
+{
+    if (!flags9 || !bitmap) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    memset(bitmap, 0, 32768);
+    auto set = [&](unsigned nat) { const unsigned ki = kernel_index(nat & 0x3ffffu, 9); bitmap[ki >> 5] |= 1u << (ki & 31); };
+    for (unsigned nat = 0; nat < 262144u; ++nat) {
+        if (!flags9[nat] && !flags9[revcomp_index(nat, 9)]) continue;
+        set(nat);
+        for (unsigned a = 0; a < 4; ++a) {
+            set((nat << 2) | a);                 // member starts one base before the centre
+            set((nat >> 2) | (a << 16));         // member starts one base after the centre
+        }
+    }
+    return IGD_OK;
+}
+
 int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
 {
     if (!h || !flags7 || !flags9) { igd_set_error("null argument"); return IGD_ERR_ARG; }
@@ -164,6 +184,9 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
     IGD_CUDA(cudaMemcpyAsync(h->d_lut9, l9.data(), 262144, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_any7, a7.data(), 2048, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_any9, a9.data(), 32768, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint32_t> a9c(8192);
+    igd_center_bitmap(flags9, a9c.data());
+    IGD_CUDA(cudaMemcpyAsync(h->d_any9c, a9c.data(), 32768, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
     h->motifs_set = true;
     return IGD_OK;
@@ -384,7 +407,7 @@ static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint6
     IGD_CUDA(cudaSetDevice(h->device));
     h->timing.scan_launches = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
-        IGD_CUDA(cudaMemsetAsync(h->d_count, 0, sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaMemsetAsync(h->d_count, 0, 2 * sizeof(unsigned long long), h->stream));   // hits, strip counter
         IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
         int rc = (kind == 1) ? igd_launch_rss_scan(h, spacer) : igd_launch_kmer_scan(h, k);
         if (rc) return rc;

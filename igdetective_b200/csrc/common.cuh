@@ -40,6 +40,7 @@ struct igd_handle {
     uint8_t *d_lut7 = nullptr;    // 16384 flags: bit t = strand +, bit 4+t = strand -
     uint8_t *d_lut9 = nullptr;    // 262144 flags
     uint32_t *d_any9 = nullptr;   // 262144-bit bitmap: lut9 != 0
+    uint32_t *d_any9c = nullptr;  // 262144-bit bitmap: the 9-mer or a neighbour shifted by one base is in lut9 (igd_center_bitmap)
     uint32_t *d_any7 = nullptr;   // 16384-bit bitmap: lut7 != 0
     bool motifs_set = false;
     bool consensus_prefilter = false;   // every heptamer flag entry matches CAC.GTG in >= 4 of 6 positions

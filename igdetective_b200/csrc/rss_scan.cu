@@ -421,6 +421,317 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     }
 }
 
+// ================================================================================================
+// v5: one persistent CTA of 24 warps per SM; every warp streams its own strips of R rows through a
+// private double buffer (own TMA bulk copies, own mbarriers, strips handed out by a global atomic
+// counter) -- no CTA-wide coupling after the prologue.  The motif tables are shared by the whole SM:
+// the exact 7-mer flags (16 KB) and the 32 KB "centre" bitmap any9c.
+//   any9c[c] = 1 iff the 9-mer c, or a 9-mer overlapping it shifted by one base to either side, is
+//   in some nonamer set (either strand).  The three candidate nonamers of a window (spacer s-1, s,
+//   s+1) start at x, x+1, x+2, so ONE look-up of the 9-mer at x+1 rules the window out for ~95 % of
+//   the (heptamer, window) pairs; a 32-position fetch serves the centres of all windows on one side
+//   of the heptamer.  Pairs that pass go to a per-warp queue of GLOBAL positions that survives across
+//   strips and is resolved exactly (nonamer flags, validity plane, the reference's ranking) in full
+//   rounds of 32 from L2.
+constexpr int V5_WARPS = 24;
+constexpr int V5_THREADS = V5_WARPS * 32;
+constexpr int V5_MAXROWS = 4;
+constexpr int V5_BUF_BYTES_MAX = (32 * V5_MAXROWS + 2) * 16;    // 2080
+constexpr int V5_BUF_STRIDE = 2176;                             // 128-byte aligned
+constexpr int V5_WQCAP = 256;                                   // per-warp heptamer-hit queue (stage positions)
+constexpr int V5_SQCAP = 64;                                    // per-warp queue of (global position, window) pairs
+
+struct ScanParams5 {
+    const uint4 *planes;
+    const unsigned long long *inv;
+    const uint32_t *invsum;
+    const uint8_t *lut7;
+    const uint8_t *lut9;
+    const uint32_t *any9c;
+    unsigned long long n_chunks;
+    unsigned long long n_strips;
+    int rows;                      // rows (32 chunks each) per strip: 1, 2 or 4
+    int nwin;                      // distinct (side, spacer) nonamer windows, <= 8, ascending offset
+    int woff[8];                   // first candidate nonamer start relative to the heptamer start
+    unsigned wmask[8];             // heptamer flag bits whose nonamers live in that window
+    int wnew[8];                   // window opens a new fetch group
+    int wbase[8];                  // fetch start of the window's group relative to the heptamer start
+    unsigned wgrp[8];              // windows of the group (bitmask over w)
+    int wsh[8];                    // position of the window's centre 9-mer inside the group's fetch
+    unsigned long long *hits;
+    unsigned long long cap;
+    unsigned long long *count;     // [0] hits, [1] strip counter
+};
+
+// 32 consecutive positions of both bit-planes starting at global base g (rare path, served by L2)
+__device__ __forceinline__ void gwin32x2(const ScanParams5 &P, unsigned long long g, unsigned &lo, unsigned &hi)
+{
+    const unsigned long long r = g >> 6;
+    const unsigned long long r1 = (r + 1 < P.n_chunks) ? r + 1 : r;
+    const uint4 a = __ldg(&P.planes[r]);
+    const uint4 b = __ldg(&P.planes[r1]);
+    const unsigned s = (unsigned)g & 63u;
+    const bool up = s >= 32u;
+    lo = __funnelshift_r(up ? a.y : a.x, up ? b.x : a.y, s);
+    hi = __funnelshift_r(up ? a.w : a.z, up ? b.z : a.w, s);
+}
+
+__device__ __forceinline__ bool window_valid5(const ScanParams5 &P, unsigned long long g, int k)
+{
+    const unsigned long long c0 = g >> 6, c1 = (g + k - 1) >> 6;
+    const int b0 = (int)(g & 63);
+    if ((__ldg(&P.invsum[c0 >> 5]) >> (c0 & 31)) & 1u) {
+        const unsigned long long m = __ldg(&P.inv[c0]);
+        const int n0 = (b0 + k > 64) ? 64 - b0 : k;
+        if (m & (((1ull << n0) - 1ull) << b0)) return false;
+    }
+    if (c1 != c0 && ((__ldg(&P.invsum[c1 >> 5]) >> (c1 & 31)) & 1u)) {
+        const unsigned long long m = __ldg(&P.inv[c1]);
+        if (m & ((1ull << (b0 + k - 64)) - 1ull)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ unsigned hept_flags5(const ScanParams5 &P, const uint8_t *s_lut7, unsigned long long g)
+{
+    unsigned lo, hi;
+    gwin32x2(P, g, lo, hi);
+    const unsigned f = s_lut7[((hi & 127u) << 7) | (lo & 127u)];
+    if (!f) return 0;
+    return window_valid5(P, g, 7) ? f : 0;
+}
+
+__device__ __forceinline__ void emit5(const ScanParams5 &P, unsigned long long gq, int t, int strand, int d)
+{
+    const unsigned long long i = atomicAdd(P.count, 1ull);
+    if (i < P.cap) P.hits[i] = (gq << 8) | ((unsigned long long)t << 4) | ((unsigned long long)strand << 3) | (unsigned long long)d;
+}
+
+// Exact resolution of up to 32 (heptamer position, window) pairs: nonamer flags of the three candidate
+// starts, validity, and the reference's ranking (py/IGDetective.py:162-175, inverted for the nonamer-first
+// types as in the header of this file).
+__device__ __noinline__ void slow_round5(const ScanParams5 &P, const uint8_t *s_lut7, unsigned long long item, bool active)
+{
+    if (!active) return;
+    const unsigned long long gq = item >> 3;
+    const int w = (int)(item & 7ull);
+    unsigned lo, hi;
+    gwin32x2(P, gq, lo, hi);
+    unsigned fm = s_lut7[((hi & 127u) << 7) | (lo & 127u)] & P.wmask[w];
+    if (!fm) return;
+    const int wo = P.woff[w];
+    const unsigned long long x = gq + (long long)wo;
+    gwin32x2(P, x, lo, hi);
+    unsigned nf0 = __ldg(&P.lut9[((hi & 511u) << 9) | (lo & 511u)]);
+    unsigned nf1 = __ldg(&P.lut9[(((hi >> 1) & 511u) << 9) | ((lo >> 1) & 511u)]);
+    unsigned nf2 = __ldg(&P.lut9[(((hi >> 2) & 511u) << 9) | ((lo >> 2) & 511u)]);
+    if (!((nf0 | nf1 | nf2) & fm)) return;
+    if (!window_valid5(P, gq, 7)) return;
+    if (nf0 && !window_valid5(P, x, 9)) nf0 = 0;
+    if (nf1 && !window_valid5(P, x + 1, 9)) nf1 = 0;
+    if (nf2 && !window_valid5(P, x + 2, 9)) nf2 = 0;
+    const bool right = wo > 0;
+    unsigned hm2 = 0, hm1 = 0, hp1 = 0, hp2 = 0; bool have_nb = false;
+    while (fm) {
+        const int fb = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const unsigned bit = 1u << fb;
+        const unsigned n = ((nf0 & bit) ? 1u : 0u) | ((nf1 & bit) ? 2u : 0u) | ((nf2 & bit) ? 4u : 0u);
+        if (!n) continue;
+        const int t = fb & 3, strand = fb >> 2;
+        const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
+        // window positions ascend; on the right they are spacers s-1, s, s+1, on the left s+1, s, s-1
+        const unsigned bm = right ? 1u : 4u, bp = right ? 4u : 1u;
+        if (hept_first) {                                      // the heptamer picks: s, then s-1, then s+1
+            emit5(P, gq, t, strand, (n & 2u) ? 0 : ((n & bm) ? 1 : 2));
+        } else {                                               // each nonamer picks its best-ranked heptamer
+            if (!have_nb && (n & 5u)) {
+                hm2 = hept_flags5(P, s_lut7, gq - 2); hm1 = hept_flags5(P, s_lut7, gq - 1);
+                hp1 = hept_flags5(P, s_lut7, gq + 1); hp2 = hept_flags5(P, s_lut7, gq + 2);
+                have_nb = true;
+            }
+            if (n & 2u) emit5(P, gq, t, strand, 0);
+            if (strand == 0) {      // nonamer p = q-9-s' ranks heptamers p+9+s, +s-1, +s+1
+                if ((n & bm) && !(hp1 & bit)) emit5(P, gq, t, 0, 1);
+                if ((n & bp) && !(hm1 & bit) && !(hm2 & bit)) emit5(P, gq, t, 0, 2);
+            } else {                // reverse strand: nonamer n = q+7+s' ranks heptamers n-s-7, +1, -1
+                if ((n & bm) && !(hm1 & bit)) emit5(P, gq, t, 1, 1);
+                if ((n & bp) && !(hp1 & bit) && !(hp2 & bit)) emit5(P, gq, t, 1, 2);
+            }
+        }
+    }
+}
+
+// One round of up to 32 queued heptamer hits (lane `active` holds stage position q): the heptamer's flags
+// say which windows matter; one centre look-up per window decides whether the pair is looked at exactly.
+// nsq = pairs waiting in sq (warp-uniform, < 32 on entry and on return).
+__device__ __forceinline__ int hits_round5(const ScanParams5 &P, const uint32_t *sw, const uint8_t *s_lut7,
+                                           const uint8_t *s_need, const uint32_t *s_any9c, unsigned long long g0,
+                                           int q, bool active, unsigned long long *sq, int nsq)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned need = 0, lo = 0, hi = 0;
+    if (active) {
+        swin32x2(sw, q, lo, hi);
+        need = s_need[s_lut7[((hi & 127u) << 7) | (lo & 127u)]];
+    }
+    for (int w = 0; w < P.nwin; ++w) {
+        if (P.wnew[w] && (need & P.wgrp[w])) swin32x2(sw, q + P.wbase[w], lo, hi);
+        bool pass = false;
+        if ((need >> w) & 1u) {
+            const int sh = P.wsh[w];
+            const unsigned idx = (((hi >> sh) & 511u) << 9) | ((lo >> sh) & 511u);
+            pass = (s_any9c[idx >> 5] >> (idx & 31u)) & 1u;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            if (pass) sq[nsq + __popc(m & ((1u << lane) - 1u))] = ((g0 + (unsigned long long)q) << 3) | (unsigned long long)w;
+            nsq += __popc(m);
+            __syncwarp();
+            if (nsq >= 32) {
+                nsq -= 32;
+                slow_round5(P, s_lut7, sq[nsq + lane], true);
+                __syncwarp();
+            }
+        }
+    }
+    return nsq;
+}
+
+static constexpr size_t kScan5Smem = (size_t)V5_WARPS * 2 * V5_BUF_STRIDE + 16384 + 32768 + (size_t)V5_WARPS * V5_WQCAP * 4
+                                     + (size_t)V5_WARPS * V5_SQCAP * 8 + 256 + (size_t)V5_WARPS * 2 * 8 + 16;
+
+template <bool PREFILTER>
+__global__ void __launch_bounds__(V5_THREADS, 1)
+rss_scan5_kernel(const __grid_constant__ ScanParams5 P)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *s_buf = smem;                                             // V5_WARPS * 2 * V5_BUF_STRIDE
+    uint8_t *s_lut7 = smem + V5_WARPS * 2 * V5_BUF_STRIDE;                   // 16384
+    uint32_t *s_any9c = (uint32_t *)(s_lut7 + 16384);                        // 32768
+    unsigned *s_wq = s_any9c + 8192;                                         // V5_WARPS * V5_WQCAP
+    unsigned long long *s_sq = (unsigned long long *)(s_wq + V5_WARPS * V5_WQCAP);   // V5_WARPS * V5_SQCAP
+    uint8_t *s_need = (uint8_t *)(s_sq + V5_WARPS * V5_SQCAP);               // 256
+    uint64_t *s_full = (uint64_t *)(s_need + 256);                           // V5_WARPS * 2
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t *full = s_full + 2 * warp;
+    if (lane == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    // strips are handed out by a global counter; the warp's first copy is in flight during the prologue
+    const unsigned rows = (unsigned)P.rows;
+    const unsigned strip_chunks = rows * 32u;
+    const unsigned buf_bytes = (strip_chunks + 2u) * 16u;
+    unsigned char *buf0 = s_buf + (size_t)warp * 2 * V5_BUF_STRIDE;
+    unsigned long long s_cur = 0, s_nxt = 0;
+    if (lane == 0) {
+        s_cur = atomicAdd(&P.count[1], 1ull);
+        s_nxt = atomicAdd(&P.count[1], 1ull);
+        if (s_cur < P.n_strips) {
+            mbar_expect_tx(&full[0], buf_bytes);
+            bulk_g2s(buf0, P.planes + s_cur * strip_chunks, buf_bytes, &full[0]);
+        }
+    }
+    s_cur = __shfl_sync(0xffffffffu, s_cur, 0);
+    {   // motif tables -> shared memory (L2-resident after the first CTA)
+        const uint4 *src7 = (const uint4 *)P.lut7; uint4 *dst7 = (uint4 *)s_lut7;
+        for (int i = tid; i < 16384 / 16; i += V5_THREADS) dst7[i] = __ldg(&src7[i]);
+        const uint4 *src9 = (const uint4 *)P.any9c; uint4 *dst9 = (uint4 *)s_any9c;
+        for (int i = tid; i < 32768 / 16; i += V5_THREADS) dst9[i] = __ldg(&src9[i]);
+    }
+    for (int f = tid; f < 256; f += V5_THREADS) {
+        unsigned need = 0;
+        for (int w = 0; w < P.nwin; ++w) need |= ((unsigned)f & P.wmask[w]) ? (1u << w) : 0u;
+        s_need[f] = (uint8_t)need;
+    }
+    __syncthreads();
+
+    unsigned *wq = s_wq + warp * V5_WQCAP;
+    unsigned long long *sq = s_sq + warp * V5_SQCAP;
+    int nsq = 0;
+    for (unsigned it = 0; s_cur < P.n_strips; ++it) {
+        unsigned long long s_nn = 0;
+        if (lane == 0) {
+            // the other buffer was read during iteration it-1 (all lanes passed the __syncwarp at its end)
+            if (s_nxt < P.n_strips) {
+                mbar_expect_tx(&full[(it + 1) & 1u], buf_bytes);
+                bulk_g2s(buf0 + ((it + 1) & 1u) * V5_BUF_STRIDE, P.planes + s_nxt * strip_chunks, buf_bytes, &full[(it + 1) & 1u]);
+            }
+            s_nn = atomicAdd(&P.count[1], 1ull);
+        }
+        __syncwarp();
+        while (!mbar_try_wait(&full[it & 1u], (it >> 1) & 1u)) { }
+
+        const uint4 *rec = (const uint4 *)(buf0 + (it & 1u) * V5_BUF_STRIDE);
+        const uint32_t *sw = (const uint32_t *)rec;
+        const unsigned long long g0 = s_cur * (unsigned long long)(strip_chunks * IGD_CHUNK_BASES);   // record 0 = chunk s_cur * strip_chunks
+        int nq = 0;
+        for (unsigned r0 = 0; r0 < rows; r0 += 2) {
+            // ---- phase A: exact heptamer hits of the 64 windows starting in this lane's chunk of each row
+            unsigned long long hm[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                hm[k] = 0;
+                if (r0 + k < rows) {
+                    const int c = (int)(r0 + k) * 32 + lane + 1;             // stage record of the chunk
+                    const uint4 r = rec[c];
+                    const uint4 n = rec[c + 1];
+                    uint32_t cand0 = 0xffffffffu, cand1 = 0xffffffffu;
+                    if (PREFILTER) {
+                        const Ind i0 = indicators(r.x, r.z), i1 = indicators(r.y, r.w), i2 = indicators(n.x, n.z);
+                        cand0 = consensus_ge4(i0, i1);
+                        cand1 = consensus_ge4(i1, i2);
+                    }
+                    const uint32_t hit0 = lut_filter(cand0, r.x, r.y, r.z, r.w, s_lut7);
+                    const uint32_t hit1 = lut_filter(cand1, r.y, n.x, r.w, n.z, s_lut7);
+                    hm[k] = (unsigned long long)hit0 | ((unsigned long long)hit1 << 32);
+                }
+            }
+            // ---- compaction into the warp queue (a pass queues at most what fits), full rounds as they form
+            for (;;) {
+                const int cnt = __popcll(hm[0]) + __popcll(hm[1]);
+                if (!__any_sync(0xffffffffu, cnt != 0)) break;
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                const int space = V5_WQCAP - nq;
+                int off = incl - cnt;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int c = (int)(r0 + k) * 32 + lane + 1;
+                    while (hm[k] && off < space) {
+                        const int b = __ffsll((long long)hm[k]) - 1;
+                        hm[k] &= hm[k] - 1;
+                        wq[nq + off] = (unsigned)(c * 64 + b);
+                        ++off;
+                    }
+                }
+                nq += min(tot, space);
+                __syncwarp();
+                while (nq >= 32) {
+                    nq -= 32;
+                    nsq = hits_round5(P, sw, s_lut7, s_need, s_any9c, g0, (int)wq[nq + lane], true, sq, nsq);
+                }
+                __syncwarp();
+                if (tot <= space) break;
+            }
+        }
+        if (nq > 0) nsq = hits_round5(P, sw, s_lut7, s_need, s_any9c, g0, lane < nq ? (int)wq[lane] : 0, lane < nq, sq, nsq);
+        __syncwarp();
+        s_cur = __shfl_sync(0xffffffffu, s_nxt, 0);
+        s_nxt = s_nn;
+    }
+    if (nsq > 0) slow_round5(P, s_lut7, sq[lane < nsq ? lane : 0], lane < nsq);
+}
+
 // ---- K1a: plain k-mer membership (find_valid_motif_idx for all sets of one k at once) ----------
 struct KmerParams {
     const uint4 *planes;
@@ -471,7 +782,7 @@ kmer_scan_kernel(const KmerParams P)
 
 static const size_t kScanSmem = NSTAGE * STAGE_STRIDE + 16384 + (SCAN_ANY9_SMEM ? 32768 : 0) + SCAN_WARPS * (WQCAP + IQCAP) * 4 + 256 + 2 * NSTAGE * 8 + 16;
 
-int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
+static int launch_rss_scan_v4(igd_handle *h, const int32_t spacer[4])
 {
     ScanParams P;
     P.planes = h->d_planes; P.inv = h->d_inv; P.invsum = h->d_invsum;
@@ -502,6 +813,61 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
     if (blocks > h->n_tiles) blocks = h->n_tiles;
     if (blocks < 1) blocks = 1;
     kernel<<<(unsigned)blocks, SCAN_THREADS, kScanSmem, h->stream>>>(P);
+    h->timing.total_launches++;
+    IGD_CUDA(cudaGetLastError());
+    return IGD_OK;
+}
+
+int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
+{
+    if (getenv("IGD_SCAN_V4")) return launch_rss_scan_v4(h, spacer);
+    ScanParams5 P;
+    P.planes = h->d_planes; P.inv = h->d_inv; P.invsum = h->d_invsum;
+    P.lut7 = h->d_lut7; P.lut9 = h->d_lut9; P.any9c = h->d_any9c;
+    P.n_chunks = h->n_chunks;
+    // one window per distinct (side, spacer): right of the heptamer for (heptamer-first, +) and
+    // (nonamer-first, -), left of it for the other two combinations; kept in ascending offset order
+    P.nwin = 0;
+    for (int side = 1; side >= 0; --side)
+        for (int t = 0; t < 4; ++t) {
+            const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
+            const unsigned bit = side == 0 ? (hept_first ? (1u << t) : (16u << t)) : (hept_first ? (16u << t) : (1u << t));
+            const int off = side == 0 ? 7 + spacer[t] - 1 : -9 - spacer[t] - 1;
+            int w = 0;
+            while (w < P.nwin && P.woff[w] != off) ++w;
+            if (w == P.nwin) {
+                int at = P.nwin;                                   // insertion sort by offset
+                while (at > 0 && P.woff[at - 1] > off) { P.woff[at] = P.woff[at - 1]; P.wmask[at] = P.wmask[at - 1]; --at; }
+                P.woff[at] = off; P.wmask[at] = 0; P.nwin++;
+                w = at;
+            }
+            P.wmask[w] |= bit;
+        }
+    for (int w = P.nwin; w < 8; ++w) { P.woff[w] = 0; P.wmask[w] = 0; }
+    // fetch groups: one 32-position fetch serves every window whose centre 9-mer (start woff + 1) lies inside it
+    int g0 = 0;
+    for (int w = 0; w < 8; ++w) { P.wnew[w] = 0; P.wbase[w] = 0; P.wgrp[w] = 0; P.wsh[w] = 0; }
+    for (int w = 0; w < P.nwin; ++w) {
+        const int cs = P.woff[w] + 1;
+        if (w == 0 || cs - (P.woff[g0] + 1) > 23) { g0 = w; P.wnew[w] = 1; }
+        P.wbase[w] = P.woff[g0] + 1;
+        P.wsh[w] = cs - P.wbase[w];
+        P.wgrp[g0] |= 1u << w;
+    }
+    // rows per strip: as long as every warp still gets several strips (tail balance), longer strips
+    const unsigned long long rows_total = h->n_tiles * (unsigned long long)(IGD_TILE_CHUNKS / 32);
+    const unsigned long long warps = (unsigned long long)h->sm_count * V5_WARPS;
+    P.rows = 4;
+    while (P.rows > 1 && rows_total / P.rows < 6 * warps) P.rows >>= 1;
+    P.n_strips = rows_total / P.rows;
+    P.hits = h->d_hits; P.cap = h->hit_cap; P.count = h->d_count;
+    auto kernel = h->consensus_prefilter ? rss_scan5_kernel<true> : rss_scan5_kernel<false>;
+    IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScan5Smem));
+    unsigned long long blocks = (unsigned long long)h->sm_count;
+    const unsigned long long wanted = (P.n_strips + V5_WARPS - 1) / V5_WARPS;
+    if (blocks > wanted) blocks = wanted;
+    if (blocks < 1) blocks = 1;
+    kernel<<<(unsigned)blocks, V5_THREADS, kScan5Smem, h->stream>>>(P);
     h->timing.total_launches++;
     IGD_CUDA(cudaGetLastError());
     return IGD_OK;

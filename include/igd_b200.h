@@ -107,6 +107,14 @@ int         igd_get_timing(igd_handle *h, igd_timing *out);
  * motifs[t][k] (t = IGD_SIG_*).  Reverse-strand tables are derived inside. */
 int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9);
 
+/* Host-only helper of the scan (no GPU needed), exposed for tests: the 262144-bit "centre" bitmap
+ * igd_set_motifs derives from flags9.  Bit c is set iff the 9-mer c, or a 9-mer overlapping it
+ * shifted by one base to either side, is in some nonamer set on either strand; the scan looks up
+ * the 9-mer in the middle of the three candidate nonamer starts (spacer s-1, s, s+1 of
+ * find_valid_rss, py/IGDetective.py:162-168) to discard a heptamer's window with one probe.
+ * Bit order: index = (high bits of the 2-bit codes << 9) | low bits, first base = bit 0. */
+int igd_center_bitmap(const uint8_t *flags9, uint32_t *bitmap /* 8192 words */);
+
 /* parent_seq of get_contigwise_rss (py/IGDetective.py:180): contigs as raw ASCII
  * (any case, IUPAC allowed), concatenated; offsets[n_contigs+1].  Copies to the
  * device and packs to 2-bit planes + validity plane there. */

@@ -170,3 +170,44 @@ def test_native_fasta_reader_multithreaded(tmp_path):
     for k in want:
         assert len(nf[k]) == len(want[k]), k
         assert str(nf[k]) == want[k], k
+
+
+def test_center_bitmap_is_conservative(motifs):
+    """igd_center_bitmap (no GPU): a clear bit for the 9-mer at x+1 proves that none of the three candidate
+    nonamer starts x, x+1, x+2 of a spacer window (py/IGDetective.py:162-168) holds a motif on either strand;
+    and the filter stays selective (a few per cent of all 9-mers)."""
+    from igdetective_b200 import _lib
+    from igdetective_b200.engine import motif_flag_tables
+    lib = _lib.load()
+    _, f9 = motif_flag_tables(motifs)
+    f9 = np.ascontiguousarray(f9)
+    bm = np.zeros(8192, np.uint32)
+    assert lib.igd_center_bitmap(f9.ctypes.data, bm.ctypes.data) == 0
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")
+
+    def kidx(s):          # kernel index: (high bits of the codes << 9) | low bits, first base = bit 0
+        lo = hi = 0
+        for i, c in enumerate(s):
+            v = "ACGT".index(c)
+            lo |= (v & 1) << i
+            hi |= (v >> 1) << i
+        return (hi << 9) | lo
+    comp = str.maketrans("ACGT", "TGCA")
+    members = set()
+    for t in motifs:
+        for m in motifs[t]["9"]:
+            members.add(m)
+            members.add(m.translate(comp)[::-1])
+    for m in members:
+        assert bits[kidx(m)]
+        for a in "ACGT":
+            assert bits[kidx(m[1:] + a)] and bits[kidx(a + m[:-1])]
+    # exhaustive the other way round on a random sample: bit set => one of the three windows can be a member
+    rng = np.random.default_rng(5)
+    pre = {m[:8] for m in members}
+    suf = {m[1:] for m in members}
+    for _ in range(20000):
+        c = "".join("ACGT"[i] for i in rng.integers(0, 4, 9))
+        want = c in members or c[:8] in suf or c[1:] in pre
+        assert bool(bits[kidx(c)]) == want
+    assert 0.01 < bits.mean() < 0.08
