@@ -75,7 +75,7 @@ igd_handle *igd_create(int device)
            && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess
            && cudaMalloc(&h->d_count, 64 * sizeof(unsigned long long)) == cudaSuccess
            && cudaMalloc(&h->d_lut7, 16384) == cudaSuccess && cudaMalloc(&h->d_lut9, 262144) == cudaSuccess
-           && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any9c, 32768) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
+           && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any9c, 32768) == cudaSuccess && cudaMalloc(&h->d_need7, 16384) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
     if (!ok) { igd_cuda_fail(cudaGetLastError(), "igd_create allocations"); igd_destroy(h); return nullptr; }
     if (igd_probe_fp_increment(h, &h->fp_increment_ok) != IGD_OK) { igd_destroy(h); return nullptr; }
     return h;
@@ -86,7 +86,7 @@ void igd_destroy(igd_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any9c); cudaFree(h->d_any7);
+    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any9c); cudaFree(h->d_need7); cudaFree(h->d_any7);
     cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
@@ -188,6 +188,8 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
     igd_center_bitmap(flags9, a9c.data());
     IGD_CUDA(cudaMemcpyAsync(h->d_any9c, a9c.data(), 32768, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
+    h->h_lut7 = l7;
+    h->need7_valid = false;
     h->motifs_set = true;
     return IGD_OK;
 }

@@ -3,14 +3,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <string>
 #include <vector>
 #include "../../include/igd_b200.h"
 
 // ---- packed contig layout in HBM ---------------------------------------------------------------
-// One "chunk" = 64 consecutive bases = one 16-byte record {lo0, lo1, hi0, hi1}:
+// One "chunk" = 64 consecutive bases = one 16-byte record {lo0, hi0, lo1, hi1}:
 //   bit b of lo0 / hi0 = low / high bit of the 2-bit code of base b       (bases  0..31)
 //   bit b of lo1 / hi1 = the same for base 32 + b                          (bases 32..63)
+// so the array is also a sequence of aligned 8-byte (lo, hi) pairs, one per 32 bases: any 32
+// consecutive positions of both planes are two adjacent pairs and two funnel shifts.
 // codes A=0 C=1 G=2 T=3 (complement = both bits flipped); anything else packs as 0 and sets the
 // base's bit in the validity plane inv[chunk] (one uint64 per chunk) and the chunk's bit in the
 // summary bitmap invsum[chunk / 32].  The scan reads the 16-byte records (0.25 B/base) for every
@@ -42,6 +45,10 @@ struct igd_handle {
     uint32_t *d_any9 = nullptr;   // 262144-bit bitmap: lut9 != 0
     uint32_t *d_any9c = nullptr;  // 262144-bit bitmap: the 9-mer or a neighbour shifted by one base is in lut9 (igd_center_bitmap)
     uint32_t *d_any7 = nullptr;   // 16384-bit bitmap: lut7 != 0
+    uint8_t *d_need7 = nullptr;   // 16384: windows of the last igd_scan's spacers that serve a 7-mer's flags (rss_scan.cu)
+    std::vector<uint8_t> h_lut7;  // host copy of d_lut7
+    bool need7_valid = false;
+    int32_t need7_spacer[4] = {0, 0, 0, 0};
     bool motifs_set = false;
     bool consensus_prefilter = false;   // every heptamer flag entry matches CAC.GTG in >= 4 of 6 positions
 

@@ -58,7 +58,7 @@ pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restric
                 w[half][2] = __ballot_sync(0xffffffffu, bad);
             }
             if (lane == 0) {
-                planes[chunk] = make_uint4(w[0][0], w[1][0], w[0][1], w[1][1]);
+                planes[chunk] = make_uint4(w[0][0], w[0][1], w[1][0], w[1][1]);
                 inv[chunk] = (unsigned long long)w[0][2] | ((unsigned long long)w[1][2] << 32);
             }
             if (w[0][2] | w[1][2]) summary |= 1u << i;
