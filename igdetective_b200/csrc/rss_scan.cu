@@ -95,11 +95,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
     return ok != 0;
 }
 
+// Shared-memory reads of the hot loops take 32-bit shared-window addresses, so that a table or stage base
+// is one register and the access one instruction.  The stage is written by the async proxy: its loads are
+// volatile asm, ordered after the volatile mbarrier wait; the tables are constant after the prologue.
+__device__ __forceinline__ uint2 lds_stage64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_tab8(uint32_t addr)
+{
+    unsigned v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_tab32(uint32_t addr)
+{
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // 32 consecutive positions of both bit-planes starting at stage position p: the (lo, hi) words of 32
 // bases are one aligned 8-byte pair, so a fetch is two LDS.64 off one address and two funnel shifts
-__device__ __forceinline__ void swin32x2(const uint2 *sp, int p, unsigned &lo, unsigned &hi)
+__device__ __forceinline__ void swin32x2(uint32_t sp, int p, unsigned &lo, unsigned &hi)
 {
-    const uint2 a = sp[p >> 5], b = sp[(p >> 5) + 1];
+    const uint32_t at = sp + ((unsigned)(p >> 5) << 3);
+    const uint2 a = lds_stage64(at), b = lds_stage64(at + 8);
     lo = __funnelshift_r(a.x, b.x, p);
     hi = __funnelshift_r(a.y, b.y, p);
 }
@@ -220,9 +243,8 @@ constexpr size_t kScanSmem = (size_t)V5_WARPS * WR_SIZE + 16384 + 32768;
 
 struct Warp {                      // per-warp state of the cascade (queue fills are warp-uniform)
     unsigned char *wb;             // the warp's shared-memory region
-    const uint2 *sp;               // current stage buffer as (lo, hi) word pairs
-    const uint8_t *need7;
-    const uint32_t *any9c;
+    uint32_t sp;                   // current stage buffer ((lo, hi) word pairs), shared-window address
+    uint32_t need7, any9c;         // the SM's tables, shared-window addresses
     unsigned strip, strip_bases;   // global base index of stage position 0 = strip * strip_bases
     int n1, n2, nsq;
     unsigned lane, lt;             // lane id, mask of lower lanes
@@ -231,22 +253,38 @@ struct Warp {                      // per-warp state of the cascade (queue fills
     __device__ __forceinline__ unsigned long long *sq() const { return (unsigned long long *)(wb + WR_SQ); }
 };
 
-// Step 3: up to 32 heptamer hits (entry = stage position | need << 16, 0 for idle lanes)
+// one probe of the centre bitmap: 9-mer at bit `sh` of the fetched planes
+__device__ __forceinline__ unsigned centre_probe(const Warp &W, unsigned lo, unsigned hi, int sh)
+{
+    const unsigned tl = lo >> sh, th = (hi >> sh) & 511u;
+    const unsigned word = lds_tab32(W.any9c + ((th << 6) | ((tl >> 3) & 60u)));
+    return (word >> (tl & 31u)) & 1u;
+}
+
+// Step 3: up to 32 heptamer hits (entry = stage position | need << 16; idle lanes pass a valid position
+// with need 0).  STD4: four windows in two fetch groups {0, 1} and {2, 3} (any set of spacers with one
+// value for V/J and one for D_left/D_right, like the reference's 23/12/12/23).
+template <bool STD4>
 __device__ __forceinline__ void hits_round(const ScanParams &P, Warp &W, unsigned entry)
 {
     const int q = (int)(entry & 0xffffu);
     const unsigned need = entry >> 16;
     unsigned lo = 0, hi = 0, pm = 0;
+    if (STD4) {
+        swin32x2(W.sp, q + P.wbase[0], lo, hi);
+        pm = centre_probe(W, lo, hi, 0) | (centre_probe(W, lo, hi, P.wsh[1]) << 1);
+        swin32x2(W.sp, q + P.wbase[2], lo, hi);
+        pm |= (centre_probe(W, lo, hi, 0) << 2) | (centre_probe(W, lo, hi, P.wsh[3]) << 3);
+        pm &= need;
+    } else {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        if (w < P.nwin) {
-            if (P.wnew[w] && (need & P.wgrp[w])) swin32x2(W.sp, q + P.wbase[w], lo, hi);
-            if ((need >> w) & 1u) {
-                const unsigned tl = lo >> P.wsh[w], th = (hi >> P.wsh[w]) & 511u;
-                const unsigned word = W.any9c[(th << 4) | ((tl >> 5) & 15u)];
-                pm |= ((word >> (tl & 31u)) & 1u) << w;
+        for (int w = 0; w < 8; ++w) {
+            if (w < P.nwin) {
+                if (P.wnew[w]) swin32x2(W.sp, q + P.wbase[w], lo, hi);
+                pm |= centre_probe(W, lo, hi, P.wsh[w]) << w;
             }
         }
+        pm &= need;
     }
     const unsigned m = __ballot_sync(0xffffffffu, pm != 0);
     if (pm) W.sq()[W.nsq + __popc(m & W.lt)] = (((unsigned long long)W.strip * W.strip_bases + (unsigned)q) << 8) | pm;
@@ -262,13 +300,13 @@ __device__ __forceinline__ void survivors_round(Warp &W, int take)
         unsigned lo, hi;
         q0 = W.q1()[W.n1 + W.lane];
         swin32x2(W.sp, (int)q0, lo, hi);
-        need0 = W.need7[((hi & 127u) << 7) | (lo & 127u)];
+        need0 = lds_tab8(W.need7 + (((hi & 127u) << 7) | (lo & 127u)));
     }
     if (a1) {
         unsigned lo, hi;
         q1 = W.q1()[W.n1 + 32 + W.lane];
         swin32x2(W.sp, (int)q1, lo, hi);
-        need1 = W.need7[((hi & 127u) << 7) | (lo & 127u)];
+        need1 = lds_tab8(W.need7 + (((hi & 127u) << 7) | (lo & 127u)));
     }
     const unsigned m0 = __ballot_sync(0xffffffffu, need0 != 0);
     const unsigned m1 = __ballot_sync(0xffffffffu, need1 != 0);
@@ -282,6 +320,7 @@ __device__ __forceinline__ void survivors_round(Warp &W, int take)
 // Runs full rounds while a queue holds enough for one, later stages first (so the hit queue never holds more
 // than 95 entries and the exact queue never more than 63); with `flush` the queues of stage positions are
 // emptied (end of a strip), with `final` the exact queue too (the warp's last strip).
+template <bool STD4>
 __device__ __forceinline__ void drain(const ScanParams &P, Warp &W, bool flush, bool final)
 {
     for (;;) {
@@ -294,7 +333,7 @@ __device__ __forceinline__ void drain(const ScanParams &P, Warp &W, bool flush, 
         } else if (W.n2 >= 32 || (flush && W.n1 == 0 && W.n2 > 0)) {
             const int take = min(W.n2, 32);
             W.n2 -= take;
-            hits_round(P, W, (int)W.lane < take ? W.q2()[W.n2 + W.lane] : 0u);
+            hits_round<STD4>(P, W, (int)W.lane < take ? W.q2()[W.n2 + W.lane] : 64u);      // 64: any position inside the stage
             __syncwarp();
         } else if (W.n1 >= 64 || (flush && W.n1 > 0)) {
             const int take = min(W.n1, 64);
@@ -331,7 +370,7 @@ __device__ __forceinline__ int top_bit(unsigned m)
     return b;
 }
 
-template <bool PREFILTER>
+template <bool PREFILTER, bool STD4>
 __global__ void __launch_bounds__(V5_THREADS, 1)
 rss_scan_kernel(const __grid_constant__ ScanParams P)
 {
@@ -372,7 +411,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     }
     __syncthreads();
 
-    W.need7 = s_need7; W.any9c = s_any9c;
+    W.need7 = smem_u32(s_need7); W.any9c = smem_u32(s_any9c);
     W.n1 = 0; W.n2 = 0; W.nsq = 0;
     W.lane = (unsigned)lane; W.lt = (1u << lane) - 1u;
     W.strip_bases = strip_chunks * IGD_CHUNK_BASES;
@@ -390,7 +429,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         while (!mbar_try_wait(&full[it & 1u], (it >> 1) & 1u)) { }
 
         const uint4 *rec = (const uint4 *)(W.wb + WR_BUF + (it & 1u) * V5_BUF_STRIDE);
-        W.sp = (const uint2 *)rec;
+        W.sp = smem_u32(rec);
         W.strip = s_cur;                                                       // record 0 = chunk s_cur * strip_chunks
         const bool last_strip = __shfl_sync(0xffffffffu, s_nxt, 0) >= P.n_strips;
         for (unsigned r0 = 0; r0 < rows; r0 += 2) {
@@ -404,7 +443,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
                     if (PREFILTER) {
                         const int c = (int)(r0 + k) * 32 + lane + 1;         // stage record of the chunk
                         const uint4 r = rec[c];
-                        const uint2 n = W.sp[2 * c + 2];
+                        const uint2 n = *(const uint2 *)&rec[c + 1];
                         const Ind i0 = indicators(r.x, r.y), i1 = indicators(r.z, r.w), i2 = indicators(n.x, n.y);
                         cm[2 * k] = consensus_ge4(i0, i1);
                         cm[2 * k + 1] = consensus_ge4(i1, i2);
@@ -452,7 +491,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
                 __syncwarp();
                 // the queues hold stage positions: they are emptied before the buffer is handed back
                 const bool flush = !more && r0 + 2 >= rows;
-                drain(P, W, flush, flush && last_strip);
+                drain<STD4>(P, W, flush, flush && last_strip);
             }
         }
         __syncwarp();
@@ -565,7 +604,9 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
     if (rows_total / P.rows > 0xffffff00ull) { igd_set_error("too many chunks for one scan"); return IGD_ERR_CAPACITY; }
     P.n_strips = (unsigned)(rows_total / P.rows);
     P.hits = h->d_hits; P.cap = h->hit_cap; P.count = h->d_count;
-    auto kernel = h->consensus_prefilter ? rss_scan_kernel<true> : rss_scan_kernel<false>;
+    const bool std4 = P.nwin == 4 && P.wnew[0] && !P.wnew[1] && P.wnew[2] && !P.wnew[3];
+    auto kernel = h->consensus_prefilter ? (std4 ? rss_scan_kernel<true, true> : rss_scan_kernel<true, false>)
+                                         : (std4 ? rss_scan_kernel<false, true> : rss_scan_kernel<false, false>);
     IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
     unsigned long long blocks = (unsigned long long)h->sm_count;
     const unsigned long long wanted = (P.n_strips + V5_WARPS - 1) / V5_WARPS;
