@@ -47,6 +47,7 @@ constexpr int V5_MAXROWS = 4;
 constexpr int V5_BUF_STRIDE = 2176;                             // (32 * 4 + 2) * 16 = 2080, 128-byte aligned
 constexpr int V5_Q1CAP = 256;                                   // survivors (16-bit stage positions)
 constexpr int V5_Q2CAP = 128;                                   // heptamer hits (position | need << 16)
+constexpr int V5_EBCAP = 64;                                    // found RSS keys waiting for one global atomic
 constexpr int V5_SQCAP = 64;                                    // (global position << 8 | windows) for the exact path
 
 struct ScanParams {
@@ -165,16 +166,51 @@ __device__ __forceinline__ unsigned hept_flags(const ScanParams &P, unsigned lon
     return window_valid(P, g, 7) ? f : 0;
 }
 
-__device__ __forceinline__ void emit(const ScanParams &P, unsigned long long gq, int t, int strand, int d)
+// Shared memory: one private region per warp (two stage buffers, the three queues, found RSS keys, two mbarriers), so that
+// everything a warp touches sits at a constant offset from one base; then the tables shared by the SM.
+constexpr int WR_BUF = 0;                                       // 2 x V5_BUF_STRIDE
+constexpr int WR_Q1 = 2 * V5_BUF_STRIDE;                        // V5_Q1CAP x u16
+constexpr int WR_Q2 = WR_Q1 + V5_Q1CAP * 2;                     // V5_Q2CAP x u32
+constexpr int WR_SQ = WR_Q2 + V5_Q2CAP * 4;                     // V5_SQCAP x u64
+constexpr int WR_EB = WR_SQ + V5_SQCAP * 8;                     // V5_EBCAP x u64: RSS keys waiting for one global atomic
+constexpr int WR_BAR = WR_EB + V5_EBCAP * 8;                    // 2 x u64 mbarriers, then the u32 fill of the key buffer
+constexpr int WR_EBN = WR_BAR + 16;
+constexpr int WR_SIZE = (WR_EBN + 4 + 127) / 128 * 128;
+constexpr size_t kScanSmem = (size_t)V5_WARPS * WR_SIZE + 16384 + 32768;
+
+// An RSS is found ~6e-5 times per base: keys collect in the warp's buffer (shared-memory atomic) and leave with
+// one global atomic per flush instead of one round trip to L2 per key.
+__device__ __forceinline__ void emit(const ScanParams &P, unsigned char *wb, unsigned long long gq, int t, int strand, int d)
 {
-    const unsigned long long i = atomicAdd(P.count, 1ull);
-    if (i < P.cap) P.hits[i] = (gq << 8) | ((unsigned long long)t << 4) | ((unsigned long long)strand << 3) | (unsigned long long)d;
+    const unsigned long long key = (gq << 8) | ((unsigned long long)t << 4) | ((unsigned long long)strand << 3) | (unsigned long long)d;
+    const unsigned i = atomicAdd((unsigned *)(wb + WR_EBN), 1u);
+    if (i < (unsigned)V5_EBCAP) ((unsigned long long *)(wb + WR_EB))[i] = key;
+    else {                                                       // buffer full inside one round: straight to global memory
+        const unsigned long long j = atomicAdd(P.count, 1ull);
+        if (j < P.cap) P.hits[j] = key;
+    }
+}
+
+// all lanes of the warp; empties the key buffer
+__device__ __forceinline__ void flush_keys(const ScanParams &P, unsigned char *wb, unsigned lane)
+{
+    __syncwarp();
+    const unsigned n = min(*(volatile unsigned *)(wb + WR_EBN), (unsigned)V5_EBCAP);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(P.count, (unsigned long long)n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const unsigned long long *eb = (const unsigned long long *)(wb + WR_EB);
+    for (unsigned i = lane; i < n; i += 32)
+        if (base + i < P.cap) P.hits[base + i] = eb[i];
+    __syncwarp();
+    if (lane == 0) *(volatile unsigned *)(wb + WR_EBN) = 0;
+    __syncwarp();
 }
 
 // Step 4, exact: item = heptamer position << 8 | windows whose centre probe passed.  Nonamer flags of the
 // three candidate starts of each window, validity, and the reference's ranking (py/IGDetective.py:162-175,
 // inverted for the nonamer-first types as in the header of this file).
-__device__ __forceinline__ void exact_round(const ScanParams &P, unsigned long long item, bool active)
+__device__ __forceinline__ void exact_round(const ScanParams &P, unsigned char *wb, unsigned long long item, bool active)
 {
     if (!active) return;
     const unsigned long long gq = item >> 8;
@@ -211,35 +247,25 @@ __device__ __forceinline__ void exact_round(const ScanParams &P, unsigned long l
             // window positions ascend; on the right they are spacers s-1, s, s+1, on the left s+1, s, s-1
             const unsigned bm = right ? 1u : 4u, bp = right ? 4u : 1u;
             if (hept_first) {                                      // the heptamer picks: s, then s-1, then s+1
-                emit(P, gq, t, strand, (n & 2u) ? 0 : ((n & bm) ? 1 : 2));
+                emit(P, wb, gq, t, strand, (n & 2u) ? 0 : ((n & bm) ? 1 : 2));
             } else {                                               // each nonamer picks its best-ranked heptamer
                 if (!have_nb && (n & 5u)) {
                     hm2 = hept_flags(P, gq - 2); hm1 = hept_flags(P, gq - 1);
                     hp1 = hept_flags(P, gq + 1); hp2 = hept_flags(P, gq + 2);
                     have_nb = true;
                 }
-                if (n & 2u) emit(P, gq, t, strand, 0);
+                if (n & 2u) emit(P, wb, gq, t, strand, 0);
                 if (strand == 0) {      // nonamer p = q-9-s' ranks heptamers p+9+s, +s-1, +s+1
-                    if ((n & bm) && !(hp1 & bit)) emit(P, gq, t, 0, 1);
-                    if ((n & bp) && !(hm1 & bit) && !(hm2 & bit)) emit(P, gq, t, 0, 2);
+                    if ((n & bm) && !(hp1 & bit)) emit(P, wb, gq, t, 0, 1);
+                    if ((n & bp) && !(hm1 & bit) && !(hm2 & bit)) emit(P, wb, gq, t, 0, 2);
                 } else {                // reverse strand: nonamer n = q+7+s' ranks heptamers n-s-7, +1, -1
-                    if ((n & bm) && !(hm1 & bit)) emit(P, gq, t, 1, 1);
-                    if ((n & bp) && !(hp1 & bit) && !(hp2 & bit)) emit(P, gq, t, 1, 2);
+                    if ((n & bm) && !(hm1 & bit)) emit(P, wb, gq, t, 1, 1);
+                    if ((n & bp) && !(hp1 & bit) && !(hp2 & bit)) emit(P, wb, gq, t, 1, 2);
                 }
             }
         }
     }
 }
-
-// Shared memory: one private region per warp (two stage buffers, the three queues, two mbarriers), so that
-// everything a warp touches sits at a constant offset from one base; then the tables shared by the SM.
-constexpr int WR_BUF = 0;                                       // 2 x V5_BUF_STRIDE
-constexpr int WR_Q1 = 2 * V5_BUF_STRIDE;                        // V5_Q1CAP x u16
-constexpr int WR_Q2 = WR_Q1 + V5_Q1CAP * 2;                     // V5_Q2CAP x u32
-constexpr int WR_SQ = WR_Q2 + V5_Q2CAP * 4;                     // V5_SQCAP x u64
-constexpr int WR_BAR = WR_SQ + V5_SQCAP * 8;                    // 2 x u64
-constexpr int WR_SIZE = (WR_BAR + 16 + 127) / 128 * 128;
-constexpr size_t kScanSmem = (size_t)V5_WARPS * WR_SIZE + 16384 + 32768;
 
 struct Warp {                      // per-warp state of the cascade (queue fills are warp-uniform)
     unsigned char *wb;             // the warp's shared-memory region
@@ -328,8 +354,9 @@ __device__ __forceinline__ void drain(const ScanParams &P, Warp &W, bool flush, 
             const int take = min(W.nsq, 32);
             W.nsq -= take;
             const bool active = (int)W.lane < take;
-            exact_round(P, W.sq()[W.nsq + (active ? W.lane : 0u)], active);
+            exact_round(P, W.wb, W.sq()[W.nsq + (active ? W.lane : 0u)], active);
             __syncwarp();
+            if (*(volatile unsigned *)(W.wb + WR_EBN) >= 32u) flush_keys(P, W.wb, W.lane);
         } else if (W.n2 >= 32 || (flush && W.n1 == 0 && W.n2 > 0)) {
             const int take = min(W.n2, 32);
             W.n2 -= take;
@@ -384,6 +411,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     uint64_t *full = (uint64_t *)(W.wb + WR_BAR);
     if (lane == 0) {
         mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        *(volatile unsigned *)(W.wb + WR_EBN) = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -402,7 +430,6 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
             bulk_g2s(W.wb + WR_BUF, P.planes + (size_t)s_cur * strip_chunks, buf_bytes, &full[0]);
         }
     }
-    s_cur = __shfl_sync(0xffffffffu, s_cur, 0);
     {   // motif tables -> shared memory (L2-resident after the first CTA)
         const uint4 *src7 = (const uint4 *)P.need7; uint4 *dst7 = (uint4 *)s_need7;
         for (int i = tid; i < 16384 / 16; i += V5_THREADS) dst7[i] = __ldg(&src7[i]);
@@ -410,6 +437,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         for (int i = tid; i < 32768 / 16; i += V5_THREADS) dst9[i] = __ldg(&src9[i]);
     }
     __syncthreads();
+    s_cur = __shfl_sync(0xffffffffu, s_cur, 0);            // the counter's answer arrived behind the table copy
 
     W.need7 = smem_u32(s_need7); W.any9c = smem_u32(s_any9c);
     W.n1 = 0; W.n2 = 0; W.nsq = 0;
@@ -498,6 +526,7 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         s_cur = __shfl_sync(0xffffffffu, s_nxt, 0);
         s_nxt = s_nn;
     }
+    flush_keys(P, W.wb, W.lane);
 }
 
 // ---- K1a: plain k-mer membership (find_valid_motif_idx for all sets of one k at once) ----------
