@@ -224,7 +224,7 @@ def gpu_arm(a):
         dist.destroy_process_group()
 
 
-ALU_OPS_PER_CELL = 8.4      # ALU-pipe instructions per cell in the SASS of gotoh_packed_kernel<32,11,false,false,true>: 92 per 11-cell step (15.4 incl. FMA pipe)
+ALU_OPS_PER_CELL = 7.3      # ALU-pipe instructions per cell in the SASS of gotoh_packed_kernel<32,11,0,false,true>: 80 per 11-cell column step (14.4 incl. the FMA pipe: 38 IMAD + 34 FFMA/FADD)
 
 
 def kernel_stats(eng, seqs, canon, igdetective):
