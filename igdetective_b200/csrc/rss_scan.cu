@@ -43,8 +43,11 @@ namespace {
 #endif
 constexpr int V5_WARPS = SCAN_WARPS_N;
 constexpr int V5_THREADS = V5_WARPS * 32;
-constexpr int V5_MAXROWS = 4;
-constexpr int V5_BUF_STRIDE = 2176;                             // (32 * 4 + 2) * 16 = 2080, 128-byte aligned
+#ifndef SCAN_MAXROWS
+#define SCAN_MAXROWS 4
+#endif
+constexpr int V5_MAXROWS = SCAN_MAXROWS;
+constexpr int V5_BUF_STRIDE = ((32 * V5_MAXROWS + 2) * 16 + 127) / 128 * 128;   // 2080 -> 2176 for 4 rows
 constexpr int V5_Q1CAP = 256;                                   // survivors (16-bit stage positions)
 constexpr int V5_Q2CAP = 128;                                   // heptamer hits (position | need << 16)
 constexpr int V5_EBCAP = 64;                                    // found RSS keys waiting for one global atomic
@@ -60,7 +63,8 @@ struct ScanParams {
     const uint32_t *any9c;
     unsigned long long n_chunks;
     unsigned n_strips;
-    int rows;                      // rows (32 chunks each) per strip: 1, 2 or 4
+    unsigned batch;                // consecutive strips handed out together: 1, 2 or 4
+    unsigned n_long;               // strips [0, n_long) hold V5_MAXROWS rows (32 chunks each), the rest one row (fine-grained tail)
     int nwin;                      // distinct (side, spacer) nonamer windows, <= 8, ascending offset
     int woff[8];                   // first candidate nonamer start relative to the heptamer start
     unsigned wmask[8];             // heptamer flag bits whose nonamers live in that window
@@ -271,7 +275,7 @@ struct Warp {                      // per-warp state of the cascade (queue fills
     unsigned char *wb;             // the warp's shared-memory region
     uint32_t sp;                   // current stage buffer ((lo, hi) word pairs), shared-window address
     uint32_t need7, any9c;         // the SM's tables, shared-window addresses
-    unsigned strip, strip_bases;   // global base index of stage position 0 = strip * strip_bases
+    unsigned row0;                 // first row of the strip: global base index of stage position 0 = row0 * 2048
     int n1, n2, nsq;
     unsigned lane, lt;             // lane id, mask of lower lanes
     __device__ __forceinline__ uint16_t *q1() const { return (uint16_t *)(wb + WR_Q1); }
@@ -313,7 +317,7 @@ __device__ __forceinline__ void hits_round(const ScanParams &P, Warp &W, unsigne
         pm &= need;
     }
     const unsigned m = __ballot_sync(0xffffffffu, pm != 0);
-    if (pm) W.sq()[W.nsq + __popc(m & W.lt)] = (((unsigned long long)W.strip * W.strip_bases + (unsigned)q) << 8) | pm;
+    if (pm) W.sq()[W.nsq + __popc(m & W.lt)] = (((unsigned long long)W.row0 * (32u * IGD_CHUNK_BASES) + (unsigned)q) << 8) | pm;
     W.nsq += __popc(m);
 }
 
@@ -416,18 +420,24 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    // strips are handed out by a global counter; the warp's first copy is in flight during the prologue
-    const unsigned rows = (unsigned)P.rows;
-    const unsigned strip_chunks = rows * 32u;
-    const unsigned buf_bytes = (strip_chunks + 2u) * 16u;
-    unsigned *const strip_counter = (unsigned *)(P.count + 1);
-    unsigned s_cur = 0, s_nxt = 0;
+    // strip s: V5_MAXROWS rows from row s * V5_MAXROWS while s < n_long, then single rows
+    const auto strip_row0 = [&](unsigned s) { return s < P.n_long ? s * V5_MAXROWS : P.n_long * V5_MAXROWS + (s - P.n_long); };
+    const auto strip_rows = [&](unsigned s) { return s < P.n_long ? (unsigned)V5_MAXROWS : 1u; };
+    // Strips are handed out in batches of P.batch consecutive strips: every warp owns two batches from the start
+    // (no rush on the counter when the kernel starts), later ones come from a global atomic counter whose answer
+    // is needed a whole batch after it was asked for.  All of this is warp-uniform except `nn` (lane 0).
+    unsigned *const batch_counter = (unsigned *)(P.count + 1);
+    const unsigned nwarps = gridDim.x * V5_WARPS, gw = blockIdx.x * V5_WARPS + warp;
+    unsigned s_cur = gw * P.batch;                                       // current strip
+    unsigned s_end = min(s_cur + P.batch, P.n_strips);                   // end of its batch
+    unsigned nb = gw + nwarps;                                           // next batch
+    unsigned nn = 0;                                                     // the batch after that (lane 0; atomic in flight)
     if (lane == 0) {
-        s_cur = atomicAdd(strip_counter, 1u);
-        s_nxt = atomicAdd(strip_counter, 1u);
+        nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
         if (s_cur < P.n_strips) {
-            mbar_expect_tx(&full[0], buf_bytes);
-            bulk_g2s(W.wb + WR_BUF, P.planes + (size_t)s_cur * strip_chunks, buf_bytes, &full[0]);
+            const unsigned bytes = (strip_rows(s_cur) * 32u + 2u) * 16u;
+            mbar_expect_tx(&full[0], bytes);
+            bulk_g2s(W.wb + WR_BUF, P.planes + (size_t)strip_row0(s_cur) * 32u, bytes, &full[0]);
         }
     }
     {   // motif tables -> shared memory (L2-resident after the first CTA)
@@ -437,29 +447,27 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         for (int i = tid; i < 32768 / 16; i += V5_THREADS) dst9[i] = __ldg(&src9[i]);
     }
     __syncthreads();
-    s_cur = __shfl_sync(0xffffffffu, s_cur, 0);            // the counter's answer arrived behind the table copy
 
     W.need7 = smem_u32(s_need7); W.any9c = smem_u32(s_any9c);
     W.n1 = 0; W.n2 = 0; W.nsq = 0;
     W.lane = (unsigned)lane; W.lt = (1u << lane) - 1u;
-    W.strip_bases = strip_chunks * IGD_CHUNK_BASES;
     for (unsigned it = 0; s_cur < P.n_strips; ++it) {
-        unsigned s_nn = 0;
-        if (lane == 0) {
+        const bool switch_batch = s_cur + 1 >= s_end;
+        const unsigned s_nxt = switch_batch ? (nb < 0x40000000u ? nb * P.batch : 0xffffffffu) : s_cur + 1;
+        if (lane == 0 && s_nxt < P.n_strips) {
             // the other buffer was read during iteration it-1 (all lanes passed the __syncwarp at its end)
-            if (s_nxt < P.n_strips) {
-                mbar_expect_tx(&full[(it + 1) & 1u], buf_bytes);
-                bulk_g2s(W.wb + WR_BUF + ((it + 1) & 1u) * V5_BUF_STRIDE, P.planes + (size_t)s_nxt * strip_chunks, buf_bytes, &full[(it + 1) & 1u]);
-            }
-            s_nn = atomicAdd(strip_counter, 1u);
+            const unsigned bytes = (strip_rows(s_nxt) * 32u + 2u) * 16u;
+            mbar_expect_tx(&full[(it + 1) & 1u], bytes);
+            bulk_g2s(W.wb + WR_BUF + ((it + 1) & 1u) * V5_BUF_STRIDE, P.planes + (size_t)strip_row0(s_nxt) * 32u, bytes, &full[(it + 1) & 1u]);
         }
         __syncwarp();
         while (!mbar_try_wait(&full[it & 1u], (it >> 1) & 1u)) { }
 
         const uint4 *rec = (const uint4 *)(W.wb + WR_BUF + (it & 1u) * V5_BUF_STRIDE);
         W.sp = smem_u32(rec);
-        W.strip = s_cur;                                                       // record 0 = chunk s_cur * strip_chunks
-        const bool last_strip = __shfl_sync(0xffffffffu, s_nxt, 0) >= P.n_strips;
+        W.row0 = strip_row0(s_cur);                                            // record 0 = chunk row0 * 32
+        const unsigned rows = strip_rows(s_cur);
+        const bool last_strip = s_nxt >= P.n_strips;
         for (unsigned r0 = 0; r0 < rows; r0 += 2) {
             // ---- step 1: candidate masks of the 2 x 64 windows starting in this lane's chunk of two rows
             uint32_t cm[4];
@@ -523,10 +531,37 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
             }
         }
         __syncwarp();
-        s_cur = __shfl_sync(0xffffffffu, s_nxt, 0);
-        s_nxt = s_nn;
+        if (switch_batch) {
+            s_end = s_nxt < P.n_strips ? min(s_nxt + P.batch, P.n_strips) : 0u;
+            nb = __shfl_sync(0xffffffffu, nn, 0);
+            if (lane == 0) nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
+        }
+        s_cur = s_nxt;
     }
-    flush_keys(P, W.wb, W.lane);
+    // what is left of the found keys leaves with ONE global atomic per CTA
+    __syncthreads();
+    unsigned *s_base = (unsigned *)s_any9c;                                  // the tables are no longer needed
+    unsigned long long *s_gbase = (unsigned long long *)(s_base + 32);
+    if (warp == 0) {
+        unsigned n = lane < V5_WARPS ? min(*(volatile unsigned *)(smem + lane * WR_SIZE + WR_EBN), (unsigned)V5_EBCAP) : 0u;
+        unsigned incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        s_base[lane] = incl - n;
+        const unsigned tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) *s_gbase = tot ? atomicAdd(P.count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    {
+        const unsigned n = min(*(volatile unsigned *)(W.wb + WR_EBN), (unsigned)V5_EBCAP);
+        const unsigned long long base = *s_gbase + s_base[warp];
+        const unsigned long long *eb = (const unsigned long long *)(W.wb + WR_EB);
+        for (unsigned i = lane; i < n; i += 32)
+            if (base + i < P.cap) P.hits[base + i] = eb[i];
+    }
 }
 
 // ---- K1a: plain k-mer membership (find_valid_motif_idx for all sets of one k at once) ----------
@@ -574,6 +609,10 @@ kmer_scan_kernel(const KmerParams P)
         }
     }
 }
+
+#ifndef SCAN_TAIL_ROWS_PER_WARP
+#define SCAN_TAIL_ROWS_PER_WARP 4
+#endif
 
 } // namespace
 
@@ -625,18 +664,26 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
         memcpy(h->need7_spacer, spacer, sizeof h->need7_spacer);
         h->need7_valid = true;
     }
-    // rows per strip: longer strips as long as every warp still gets several of them (tail balance)
+    // long strips first, then a tail of single rows (about four per warp) so that the SMs finish together
     const unsigned long long rows_total = h->n_tiles * (unsigned long long)(IGD_TILE_CHUNKS / 32);
     const unsigned long long warps = (unsigned long long)h->sm_count * V5_WARPS;
-    P.rows = V5_MAXROWS;
-    while (P.rows > 1 && rows_total / P.rows < 6 * warps) P.rows >>= 1;
-    if (rows_total / P.rows > 0xffffff00ull) { igd_set_error("too many chunks for one scan"); return IGD_ERR_CAPACITY; }
-    P.n_strips = (unsigned)(rows_total / P.rows);
+    const unsigned long long tail_rows = std::min<unsigned long long>(rows_total, SCAN_TAIL_ROWS_PER_WARP * warps);
+    const unsigned long long n_long = (rows_total - tail_rows) / V5_MAXROWS;
+    const unsigned long long n_strips = n_long + (rows_total - n_long * V5_MAXROWS);
+    if (n_strips > 0xffffff00ull || rows_total > 0xffffff00ull) { igd_set_error("too many chunks for one scan"); return IGD_ERR_CAPACITY; }
+    P.n_long = (unsigned)n_long;
+    P.n_strips = (unsigned)n_strips;
+    P.batch = n_strips >= 32 * warps ? 4u : (n_strips >= 16 * warps ? 2u : 1u);
     P.hits = h->d_hits; P.cap = h->hit_cap; P.count = h->d_count;
     const bool std4 = P.nwin == 4 && P.wnew[0] && !P.wnew[1] && P.wnew[2] && !P.wnew[3];
     auto kernel = h->consensus_prefilter ? (std4 ? rss_scan_kernel<true, true> : rss_scan_kernel<true, false>)
                                          : (std4 ? rss_scan_kernel<false, true> : rss_scan_kernel<false, false>);
-    IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+    static bool attr_set[4] = {false, false, false, false};           // once per kernel instance (same for every device of the process)
+    const int inst = (h->consensus_prefilter ? 2 : 0) + (std4 ? 1 : 0);
+    if (!attr_set[inst]) {
+        IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
+        attr_set[inst] = true;
+    }
     unsigned long long blocks = (unsigned long long)h->sm_count;
     const unsigned long long wanted = (P.n_strips + V5_WARPS - 1) / V5_WARPS;
     if (blocks > wanted) blocks = wanted;
