@@ -165,6 +165,22 @@ def gpu_arm(a):
     kstat = kernel_stats(eng, seqs, canon, igdetective)
     t_e2e, h2d, d2h, _ = timed(True, a.steps)
     clk = clocks.stop() if clocks else None
+    # scan kernel alone at assembly scale (rank 0): the workload contig repeated, so that the fixed cost of a launch
+    # (~15 us of the ~45 us a 100 Mb scan takes) does not hide the kernel's streaming rate
+    scan_large = None
+    if rank == 0 and a.scan_mbases > a.mbases:
+        reps = int(round(a.scan_mbases / a.mbases))
+        big = np.tile(contig, reps)
+        eng.load_contigs((big, np.array([0, len(big)], np.uint64)), ["large"])
+        samples = []
+        for _ in range(max(3, a.steps) + 1):
+            flush.zero_(); torch.cuda.synchronize(); eng.sync()
+            n_large = eng.scan_rss_count(SPACER_LENGTH)
+            samples.append(eng.timing()["scan_ms"])
+        ms = float(np.mean(samples[1:]))
+        scan_large = {"bases": int(len(big)), "kernel_ms": ms, "hits": int(n_large),
+                      "achieved": (len(big) + 3) // 4 / (ms * 1e-3) / 1e9}
+        del big
 
     if rank != 0:
         if world > 1:
@@ -216,6 +232,13 @@ def gpu_arm(a):
                           "traffic": 25355264 if a.mbases == 100.0 else None,
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
     }
+    if scan_large:
+        line["roofline_scan_large"] = {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": scan_large["achieved"],
+                                       "peak": hbm_peak, "unit": "GB/s", "frac": scan_large["achieved"] / hbm_peak,
+                                       "workload": "the %.0f Mb contig repeated to %.0f Mb, scan kernel only, L2 flushed"
+                                                   % (a.mbases, scan_large["bases"] / 1e6),
+                                       "kernel_ms": scan_large["kernel_ms"], "hits": scan_large["hits"],
+                                       "gb_per_s_both_strands": scan_large["bases"] / (scan_large["kernel_ms"] * 1e-3) / 1e9}
     if not a.no_cpu:
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
         line["cpu_baseline"] = cpu_sample(contig, seqs, motifs, canon, kstat["fragments"], a)
@@ -344,6 +367,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mbases", type=float, default=100.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scan-mbases", type=float, default=1000.0,
+                    help="size of the extra scan-only measurement (the workload contig repeated; 0 = skip)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":

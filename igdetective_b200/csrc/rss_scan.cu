@@ -180,7 +180,7 @@ constexpr int WR_EB = WR_SQ + V5_SQCAP * 8;                     // V5_EBCAP x u6
 constexpr int WR_BAR = WR_EB + V5_EBCAP * 8;                    // 2 x u64 mbarriers, then the u32 fill of the key buffer
 constexpr int WR_EBN = WR_BAR + 16;
 constexpr int WR_SIZE = (WR_EBN + 4 + 127) / 128 * 128;
-constexpr size_t kScanSmem = (size_t)V5_WARPS * WR_SIZE + 16384 + 32768;
+constexpr size_t kScanSmem = (size_t)V5_WARPS * WR_SIZE + 16384 + 32768 + 16;   // + the tables' mbarrier
 
 // An RSS is found ~6e-5 times per base: keys collect in the warp's buffer (shared-memory atomic) and leave with
 // one global atomic per flush instead of one round trip to L2 per key.
@@ -440,13 +440,18 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
             bulk_g2s(W.wb + WR_BUF, P.planes + (size_t)strip_row0(s_cur) * 32u, bytes, &full[0]);
         }
     }
-    {   // motif tables -> shared memory (L2-resident after the first CTA)
-        const uint4 *src7 = (const uint4 *)P.need7; uint4 *dst7 = (uint4 *)s_need7;
-        for (int i = tid; i < 16384 / 16; i += V5_THREADS) dst7[i] = __ldg(&src7[i]);
-        const uint4 *src9 = (const uint4 *)P.any9c; uint4 *dst9 = (uint4 *)s_any9c;
-        for (int i = tid; i < 32768 / 16; i += V5_THREADS) dst9[i] = __ldg(&src9[i]);
+    // motif tables -> shared memory: two bulk copies on a CTA-wide mbarrier (L2-resident after the first CTA)
+    uint64_t *tbar = (uint64_t *)(s_any9c + 8192);
+    if (tid == 0) {
+        mbar_init(tbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(tbar, 16384 + 32768);
+        bulk_g2s(s_need7, P.need7, 16384, tbar);
+        bulk_g2s(s_any9c, P.any9c, 32768, tbar);
     }
     __syncthreads();
+    while (!mbar_try_wait(tbar, 0)) { }
 
     W.need7 = smem_u32(s_need7); W.any9c = smem_u32(s_any9c);
     W.n1 = 0; W.n2 = 0; W.nsq = 0;

@@ -285,3 +285,44 @@ def test_scan_pathological_density_and_buffer_regrow(engine, motifs):
     assert np.all(ph == n_units - 2000)
     kh = engine.scan_kmers(7)
     assert len(kh) >= n_units
+
+
+@pytest.mark.parametrize("spacers", [{"V": 22, "D_left": 11, "D_right": 12, "J": 23},
+                                     {"V": 23, "D_left": 12, "D_right": 9, "J": 23},
+                                     {"V": 12, "D_left": 12, "D_right": 12, "J": 12},
+                                     {"V": 2, "D_left": 23, "D_right": 3, "J": 17}])
+def test_scan_shipped_motifs_other_spacers(engine, motifs, spacers):
+    """the shipped motif tables (consensus prefilter on) with spacers other than 23/12/12/23: five to eight
+    nonamer windows, other fetch groups (the generic window loop instead of the two-group instance), one
+    window only; bit-exact against the oracle's loops with the same spacers"""
+    rng = np.random.default_rng(sum(spacers.values()))
+    contigs, _ = synth.assembly(11, [120_000, 4_100, 63, 30_001], motifs, n_runs=2, soft_mask=0.3)
+    for c in contigs:
+        for _ in range(len(c) // 300):
+            t = SIG[rng.integers(4)]
+            h = sorted(motifs[t]["7"])[rng.integers(len(motifs[t]["7"]))]
+            n = sorted(motifs[t]["9"])[rng.integers(len(motifs[t]["9"]))]
+            sp = "".join("ACGT"[i] for i in rng.integers(0, 4, max(0, spacers[t] + int(rng.integers(-1, 2)))))
+            u = np.frombuffer((h + sp + n if synth.HEPT_FIRST[t] else n + sp + h).encode(), np.uint8)
+            if rng.integers(2):
+                u = synth.revcomp_bytes(u)
+            if len(c) > len(u):
+                p = int(rng.integers(0, len(c) - len(u)))
+                c[p:p + len(u)] = u
+    seqs = {"c%d" % i: c.tobytes().decode() for i, c in enumerate(contigs)}
+    engine.load_contigs(seqs)
+    h = engine.scan_rss(spacers)
+    got = {}
+    for r in h:
+        got.setdefault((int(r["contig"]), SIG[r["sig_type"]], "+-"[r["strand"]]), []).append((int(r["hept"]), int(r["nona"])))
+    total = 0
+    for t in SIG:
+        for sd in "+-":
+            want = O.get_contigwise_rss(t, sd, seqs, motifs, order="canonical", spacers=spacers)
+            for ci, c in enumerate(seqs):
+                assert sorted(got.get((ci, t, sd), [])) == sorted(want[c]), (ci, t, sd)
+                total += len(want[c])
+    assert total > 100
+    # and back to the reference's spacers on the same handle (the window-need table follows the spacers)
+    engine.load_contigs(seqs)
+    check(engine, seqs, motifs)
