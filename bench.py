@@ -229,7 +229,7 @@ def gpu_arm(a):
         "roofline_scan": {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes": alg_bytes,
                           # dram__bytes_read+write of one launch, ncu --set full capture in profiles/: equals the algorithmic bytes
-                          "traffic": 25355264 if a.mbases == 100.0 else None,
+                          "traffic": 25554688 if a.mbases == 100.0 else None,
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
     }
     if scan_large:
