@@ -78,6 +78,8 @@ struct igd_handle {
     size_t scratch_cap[14] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
+    void *h_ring = nullptr;       // ring of pinned pieces for the upload of pageable genomes (capi.cu, upload_letters)
+    cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
     igd_timing timing = {};
 };

@@ -81,8 +81,9 @@ def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
     glist = list(canonical.values())
     flat = []
     for strand in (FWD, REV):
-        for contig in fragments[strand]:
-            flat.extend(fragments[strand][contig])
+        for frs in fragments[strand].values():
+            if frs:
+                flat.extend(frs)
     # the reference runs the same computation twice ('AFFINE' and 'MAXK', :467-468); once is enough
     pi_mat, len_mat = align_fragment_to_genes(flat, glist, "AFFINE", gene, engine=engine)
     winners, k = [], 0
@@ -90,8 +91,10 @@ def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
     rows_idx = np.arange(len(best_all))
     pi_best, len_best = pi_mat[rows_idx, best_all], len_mat[rows_idx, best_all]
     for strand in (FWD, REV):
-        for contig in fragments[strand]:
-            for i, frag in enumerate(fragments[strand][contig]):
+        for contig, frs in fragments[strand].items():
+            if not frs:
+                continue
+            for i, frag in enumerate(frs):
                 best, pi, maxk = best_all[k], pi_best[k], len_best[k]
                 k += 1
                 if pi >= PI_CUTOFF["strict"][gene] or (pi >= PI_CUTOFF["relax"][gene] and maxk >= MAXK_CUTOFF[gene]):
@@ -128,10 +131,12 @@ def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=
     Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only."""
     scan = RssScan(engine, input_seq_dict, order=order, load=load)
     info = {st: {sd: scan.contigwise(st, sd) for sd in (FWD, REV)} for st in SIGNAL_TYPES}
-    info[D] = {sd: combine_D_RSS(info[DL][sd], info[DR][sd], input_seq_dict, sd) for sd in (FWD, REV)}
+    sparse = scan.sparse
+    info[D] = {sd: combine_D_RSS(info[DL][sd], info[DR][sd], input_seq_dict, sd, sparse=sparse) for sd in (FWD, REV)}
     if rss_only:
         return info, None
-    frags = {g: {sd: get_s_fragment_from_RSS(g, sd, info, input_seq_dict) for sd in (FWD, REV)} for g in (V, J)}
+    frags = {g: {sd: get_s_fragment_from_RSS(g, sd, info, input_seq_dict, sparse=sparse) for sd in (FWD, REV)}
+             for g in (V, J)}
     rows = {D: d_gene_rows(input_seq_dict, info[D])}
     for gene in (V, J):
         rows[gene] = vj_gene_rows(engine, input_seq_dict, gene, info[gene], frags[gene], canonical_genes[gene])

@@ -19,6 +19,14 @@ SIGNAL_TYPES = [V, J, DL, DR]                        # :119-125 with the default
 SPACER_LENGTH = {V: 23, DL: 12, DR: 12, J: 23}
 GENE_LENGTH = {V: 350, J: 70, D: 150}
 HEPT_FIRST = {V: True, DR: True, J: False, DL: False}
+# Whole-genome runs (order="canonical": hundreds of thousands of contigs, most without any RSS of a given type)
+# share ONE immutable empty value between the contigs that have nothing instead of building a list per contig and
+# call; the reference-order mode keeps the reference's own shape, a fresh list per contig.
+_NOTHING = ()
+
+
+def _empty_map(keys, sparse):
+    return dict.fromkeys(keys, _NOTHING) if sparse else {c: [] for c in keys}
 
 
 class RssScan:
@@ -33,6 +41,7 @@ class RssScan:
         self.lens = [len(parent_seq[c]) for c in self.ids]
         self.spacers = dict(spacers or SPACER_LENGTH)
         self.order = order
+        self.sparse = order == "canonical"
         if load:                       # load=False: the caller already put these contigs on the engine
             if hasattr(parent_seq, "_f"):                  # fasta.NativeFasta: no Python copy of the letters
                 engine.load_fasta(parent_seq)
@@ -64,7 +73,7 @@ class RssScan:
         t, s = SIGNAL_INDEX[sig_type], (0 if strand == FWD else 1)
         h = self.hits[(self.hits["sig_type"] == t) & (self.hits["strand"] == s)]
         # hits arrive sorted by (contig, type, strand, scan-order index): one split per contig that has any
-        res = {cid: [] for cid in self.ids}
+        res = _empty_map(self.ids, self.sparse)
         if len(h):
             cs, first = np.unique(h["contig"], return_index=True)
             bounds = np.append(first, len(h)).tolist()
@@ -95,14 +104,16 @@ def get_contigwise_rss(sig_type, strand, parent_seq, scan=None, engine=None, ord
     return scan.contigwise(sig_type, strand)
 
 
-def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GENE_LENGTH[D]):
+def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GENE_LENGTH[D], sparse=False):
     """py/IGDetective.py:210-224: every (dr, dl) with left < right and right-(left+7) <= Dgene_len,
     dr-outer / dl-inner in the given list orders.  The reference's double loop is replaced by one
     sorted search per contig; the output (content and order) is the same."""
-    res = {c: [] for c in input_seq_dict.keys()}
+    res = _empty_map(input_seq_dict.keys(), sparse)
     for c, drs in D_right_idx.items():
-        dls = D_left_idx[c] if drs else None
-        if not dls or not drs:
+        if not drs:
+            continue
+        dls = D_left_idx[c]
+        if not dls:
             continue
         dl0 = np.fromiter((x[0] for x in dls), np.int64, len(dls))
         dr0 = np.fromiter((x[0] for x in drs), np.int64, len(drs))
@@ -114,12 +125,14 @@ def combine_D_RSS(D_left_idx, D_right_idx, input_seq_dict, strand, Dgene_len=GEN
         else:                    # left = dr, right = dl:  dr+1 <= dl <= dr+157
             lo = np.searchsorted(sdl, dr0 + 1, "left")
             hi = np.searchsorted(sdl, dr0 + (Dgene_len + 7), "right")
-        out = res[c]
+        out = []
         for k in np.nonzero(hi > lo)[0]:
             dr = drs[k]
             for i in np.sort(order[lo[k]:hi[k]]):      # dl-inner order = position in the dl list
                 dl = dls[i]
                 out.append((dl[0], dl[1], dr[0], dr[1]))
+        if out or not sparse:
+            res[c] = out
     return res
 
 
@@ -130,9 +143,9 @@ def extract_s_fragment(index, extract_dir, length, parent_seq):
     return parent_seq[index - length:index]
 
 
-def get_s_fragment_from_RSS(gene, strand, input_rss_info, input_seq_dict):
+def get_s_fragment_from_RSS(gene, strand, input_rss_info, input_seq_dict, sparse=False):
     """py/IGDetective.py:268-300 (the globals it reads are parameters here)."""
-    out = {c: [] for c in input_rss_info[gene][strand]}
+    out = _empty_map(input_rss_info[gene][strand], sparse)
     for c, rss in input_rss_info[gene][strand].items():
         if not rss:
             continue

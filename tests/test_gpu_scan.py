@@ -326,3 +326,23 @@ def test_scan_shipped_motifs_other_spacers(engine, motifs, spacers):
     # and back to the reference's spacers on the same handle (the window-need table follows the spacers)
     engine.load_contigs(seqs)
     check(engine, seqs, motifs)
+
+
+def test_upload_pageable_ring_equals_pinned(engine, motifs):
+    """igd_load_contigs moves a large pageable genome through a ring of pinned pieces (several memcpy threads, one
+    DMA per piece); the same bytes from pinned memory go in one DMA: identical hits, on one contig that spans
+    several pieces and on many contigs whose boundaries fall inside pieces"""
+    import torch
+    contigs, _ = synth.assembly(21, [1_000_003], motifs, plant_every=5_000, n_runs=3, soft_mask=0.3)
+    big = np.tile(contigs[0], 150)                         # 150 Mb > 4 pieces of 32 MiB
+    n = len(big)
+    pinned = torch.empty(n, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = big
+    for off in (np.array([0, n], np.uint64),
+                np.array(sorted({0, n} | set(np.random.default_rng(3).integers(1, n, 300).tolist())), np.uint64)):
+        engine.load_contigs((big, off), list(range(len(off) - 1)))
+        a = engine.scan_rss(O.SPACER_LENGTH)
+        engine.load_contigs((pinned.data_ptr(), off), list(range(len(off) - 1)))
+        b = engine.scan_rss(O.SPACER_LENGTH)
+        assert len(a) == len(b) > 10_000
+        assert a.tobytes() == b.tobytes()
