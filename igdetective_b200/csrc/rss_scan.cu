@@ -616,7 +616,7 @@ kmer_scan_kernel(const KmerParams P)
 }
 
 #ifndef SCAN_TAIL_ROWS_PER_WARP
-#define SCAN_TAIL_ROWS_PER_WARP 4
+#define SCAN_TAIL_ROWS_PER_WARP 2
 #endif
 
 } // namespace
@@ -669,7 +669,7 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
         memcpy(h->need7_spacer, spacer, sizeof h->need7_spacer);
         h->need7_valid = true;
     }
-    // long strips first, then a tail of single rows (about four per warp) so that the SMs finish together
+    // long strips first, then a tail of single rows (two per warp) so that the SMs finish together
     const unsigned long long rows_total = h->n_tiles * (unsigned long long)(IGD_TILE_CHUNKS / 32);
     const unsigned long long warps = (unsigned long long)h->sm_count * V5_WARPS;
     const unsigned long long tail_rows = std::min<unsigned long long>(rows_total, SCAN_TAIL_ROWS_PER_WARP * warps);

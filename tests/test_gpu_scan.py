@@ -346,3 +346,16 @@ def test_upload_pageable_ring_equals_pinned(engine, motifs):
         b = engine.scan_rss(O.SPACER_LENGTH)
         assert len(a) == len(b) > 10_000
         assert a.tobytes() == b.tobytes()
+
+
+def test_scan_is_deterministic_across_launches(engine, motifs):
+    """warps pick strips from a global counter and queue candidates in arrival order: whichever way a launch
+    interleaves, the sorted hit list is the same -- twelve launches on one input, byte for byte (a race in the
+    queues or in the key buffers would show up here as a lost or doubled hit)"""
+    contigs, _ = synth.assembly(31, [3_000_000, 40_000, 700_001], motifs, plant_every=900, n_runs=4, soft_mask=0.4)
+    seqs = {"c%d" % i: c.tobytes().decode() for i, c in enumerate(contigs)}
+    engine.load_contigs(seqs)
+    first = engine.scan_rss(O.SPACER_LENGTH).tobytes()
+    assert len(first) > 4000 * 24
+    for _ in range(11):
+        assert engine.scan_rss(O.SPACER_LENGTH).tobytes() == first
