@@ -57,6 +57,101 @@ def scan_model(seq, motifs, spacers):
     return out
 
 
+def scan_windows(spacers):
+    """igd_launch_rss_scan's window table: one window per distinct (side, spacer), ascending offset.
+    Returns [(woff, {(type, strand), ...})]: the three candidate nonamer starts of a window are
+    q + woff, q + woff + 1, q + woff + 2 for a heptamer at q."""
+    wins = {}
+    for t in SIG:
+        sp = spacers[t]
+        right, left = 7 + sp - 1, -9 - sp - 1
+        if HEPT_FIRST[t]:
+            wins.setdefault(right, set()).add((t, "+"))
+            wins.setdefault(left, set()).add((t, "-"))
+        else:
+            wins.setdefault(left, set()).add((t, "+"))
+            wins.setdefault(right, set()).add((t, "-"))
+    return sorted(wins.items())
+
+
+def centre_set(motifs):
+    """igd_center_bitmap as a set of strings: a nonamer of any set on either strand, or a 9-mer that
+    overlaps one shifted by one base to either side."""
+    out = set()
+    for t in SIG:
+        for m in motifs[t]["9"]:
+            for x in (m, _rc(m)):
+                out.add(x)
+                for a in "ACGT":
+                    out.add(x[1:] + a)
+                    out.add(a + x[:-1])
+    return out
+
+
+def scan_cascade_model(seq, motifs, spacers):
+    """rss_scan.cu's cascade after the prefilter: heptamer test -> window-need bits -> ONE centre probe per
+    needed window -> exact resolution of the windows that pass (three nonamer starts, the reference's ranking).
+    Letters outside ACGT must already be '#'.  Returns {(type, strand): set of (hept, nona)}."""
+    s = seq.upper()
+    L = len(s)
+    H = {(t, "+"): motifs[t]["7"] for t in SIG}
+    H.update({(t, "-"): {_rc(m) for m in motifs[t]["7"]} for t in SIG})
+    N = {(t, "+"): motifs[t]["9"] for t in SIG}
+    N.update({(t, "-"): {_rc(m) for m in motifs[t]["9"]} for t in SIG})
+    wins = scan_windows(spacers)
+    centres = centre_set(motifs)
+    # the packed planes hold code 0 ('A') for invalid letters: the probe sees them as 'A' (conservative)
+    probe_view = s.replace("#", "A")
+
+    def flags7(x):
+        return {k for k in H if 0 <= x <= L - 7 and s[x:x + 7] in H[k]}
+
+    def flags9(x):
+        return {k for k in N if 0 <= x <= L - 9 and s[x:x + 9] in N[k]}
+    out = {(t, sd): set() for t in SIG for sd in "+-"}
+    for q in range(L - 6):
+        f = flags7(q)
+        if not f:
+            continue
+        for woff, served in wins:
+            fm = f & served                                   # need bit of this window
+            if not fm:
+                continue
+            c = q + woff + 1
+            centre = probe_view[max(c, 0):c + 9] if c >= 0 else ""
+            if len(centre) == 9 and centre not in centres:    # windows hanging over an end go to the exact path
+                continue
+            x = q + woff
+            nf = [flags9(x), flags9(x + 1), flags9(x + 2)]
+            right = woff > 0
+            for key in fm:
+                t, sd = key
+                n = [key in nf[0], key in nf[1], key in nf[2]]
+                if not any(n):
+                    continue
+                # window positions ascend: on the right spacers s-1, s, s+1, on the left s+1, s, s-1
+                minus, plus = (n[0], n[2]) if right else (n[2], n[0])
+                pos = {"mid": x + 1, "minus": x if right else x + 2, "plus": x + 2 if right else x}
+                if HEPT_FIRST[t]:
+                    pick = "mid" if n[1] else ("minus" if minus else "plus")
+                    out[key].add((q, pos[pick]))
+                else:
+                    h = lambda d: key in flags7(q + d)
+                    if n[1]:
+                        out[key].add((q, pos["mid"]))
+                    if sd == "+":
+                        if minus and not h(1):
+                            out[key].add((q, pos["minus"]))
+                        if plus and not h(-1) and not h(-2):
+                            out[key].add((q, pos["plus"]))
+                    else:
+                        if minus and not h(-1):
+                            out[key].add((q, pos["minus"]))
+                        if plus and not h(1) and not h(2):
+                            out[key].add((q, pos["plus"]))
+    return out
+
+
 NEG = -(1 << 26)
 
 

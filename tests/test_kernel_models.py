@@ -45,6 +45,42 @@ def test_scan_model_equals_oracle(motifs, seed):
             assert set(want) == model[(t, sd)], (t, sd)
 
 
+@pytest.mark.parametrize("spacers,n_windows", [(None, 4), ({"V": 22, "D_left": 11, "D_right": 12, "J": 23}, 8),
+                                               ({"V": 12, "D_left": 12, "D_right": 12, "J": 12}, 2),
+                                               ({"V": 2, "D_left": 23, "D_right": 3, "J": 17}, 8)])
+def test_scan_cascade_model_equals_oracle(motifs, spacers, n_windows):
+    """the kernel's cascade (window table with merged windows, need bits, one centre probe per window, per-window
+    exact resolution) against the reference's loops, for the reference's spacers and for sets that merge or
+    split the windows differently"""
+    sp = dict(O.SPACER_LENGTH) if spacers is None else spacers
+    wins = KM.scan_windows(sp)
+    assert len(wins) == n_windows and [w for w, _ in wins] == sorted(w for w, _ in wins)
+    total = 0
+    for seed in range(3):
+        rng = np.random.default_rng(100 + seed)
+        s = list(rng.choice(list("ACGT"), 4000, p=[0.295, 0.205, 0.205, 0.295]))
+        for _ in range(60):
+            t = KM.SIG[rng.integers(4)]
+            h = sorted(motifs[t]["7"])[rng.integers(len(motifs[t]["7"]))]
+            n = sorted(motifs[t]["9"])[rng.integers(len(motifs[t]["9"]))]
+            spacer = "".join(rng.choice(list("ACGT"), max(0, sp[t] + int(rng.integers(-1, 2)))))
+            unit = h + spacer + n if KM.HEPT_FIRST[t] else n + spacer + h
+            if rng.integers(2):
+                unit = O.revcomp(unit)
+            p = int(rng.integers(0, len(s) - len(unit)))
+            s[p:p + len(unit)] = list(unit)
+        seq = "".join(s)
+        b = int(rng.integers(0, len(seq) - 30))
+        seq = seq[:b] + "N" * 11 + seq[b + 11:]
+        model = KM.scan_cascade_model("".join(ch if ch in "ACGT" else "#" for ch in seq), motifs, sp)
+        for t in KM.SIG:
+            for sd in "+-":
+                want = O.get_contigwise_rss(t, sd, {"c": seq}, motifs, order="canonical", spacers=sp)["c"]
+                assert set(want) == model[(t, sd)], (t, sd, seed)
+                total += len(want)
+    assert total > 60
+
+
 def _pairs(rng, n):
     out = []
     for _ in range(n):
