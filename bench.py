@@ -242,7 +242,7 @@ def gpu_arm(a):
     if not a.no_cpu:
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
         line["cpu_baseline"] = cpu_sample(contig, seqs, motifs, canon, kstat["fragments"], a)
-    print(json.dumps(line))
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -349,17 +349,39 @@ def reference_arm(a):
     s_len = int(n_bases * frac)
     val = s_len * a.steps / t_all / 1e9
     res["value"] = val
-    print(json.dumps({
+    emit_line({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", a.gpus)),
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_all / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
         "config": {"workload": "configs[1]: synthetic %.0f Mb single contig, bounded proportional sample (%.2f%% "
                                "of the contig and of the V/J candidates per step)" % (a.mbases, 100 * frac)},
         "cpu_baseline": res,
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else a library prints there during the run (NCCL's version
+    banner under NCCL_DEBUG=VERSION, for one) is sent to stderr, and the line goes out on the real stdout at the end."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_line(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == "__main__":
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
