@@ -14,18 +14,20 @@
 //   strand -, nonamer first              :  nonamer n=q+7+s' selects q iff (q-1 | q+1,q+2) miss
 // with s' tried in the order s, s-1, s+1 (:162-168).
 //
-// Execution: one persistent CTA of 24 warps per SM.  Every warp streams its own strips of R rows
-// (R x 32 chunks, R x 2048 bases) through a private double buffer: its own TMA bulk copies
-// (cp.async.bulk + mbarrier), one halo chunk per side (64 bases >= the 40-base RSS span), strips
-// handed out by a global atomic counter -- no CTA-wide coupling after the prologue, every base is
-// read from HBM once (0.25 B/base).  The motif tables are shared by the SM's 24 warps.
+// Execution: one persistent CTA of 24 warps per SM.  Every warp streams its own strips (4 rows of 32
+// chunks = 8192 bases; single rows for the last ~2 rows per warp so that the SMs finish together)
+// through a private double buffer: its own TMA bulk copies (cp.async.bulk + mbarrier), one halo chunk
+// per side (64 bases >= the 40-base RSS span).  Strips are handed out in batches: two static batches
+// per warp, then a global atomic counter asked one batch ahead -- no CTA-wide coupling between the
+// prologue and the final key flush, every base is read from HBM once (0.25 B/base).  The motif
+// tables (two more bulk copies) are shared by the SM's 24 warps.
 // A cascade of ever rarer, ever more expensive steps, each one run with full lanes on a queue:
 //   1. bit-parallel prefilter, one 64-base chunk per lane: every heptamer of the shipped motif file
 //      (both strands) agrees with the consensus CAC.GTG in at least 4 of its 6 fixed positions; a
 //      bit-sliced population count thresholded at 4 passes every possible hit and ~3.8 % of random
 //      positions (igd_set_motifs verifies the property for the tables it is given; otherwise the
 //      exhaustive instance, where every position is a candidate, runs).  Survivors are queued.
-//   2. 32 survivors at a time: the window-need byte of the 7-mer (need7, 16 KB, zero = not a
+//   2. 64 survivors at a time (two per lane): the window-need byte of the 7-mer (need7, 16 KB, zero = not a
 //      heptamer of any set) -- real heptamer hits (~1 %) are queued with their need bits.
 //   3. 32 hits at a time: for every nonamer window the hit's types need, ONE probe of the "centre"
 //      bitmap any9c (32 KB): the three candidate nonamers (spacer s-1, s, s+1) start at x, x+1,
