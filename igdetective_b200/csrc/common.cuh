@@ -48,6 +48,7 @@ struct igd_handle {
     uint8_t *d_need7 = nullptr;   // 16384: windows of the last igd_scan's spacers that serve a 7-mer's flags (rss_scan.cu)
     std::vector<uint8_t> h_lut7;  // host copy of d_lut7
     bool need7_valid = false;
+    bool scan_attr_set[4] = {false, false, false, false};   // dynamic shared memory size set for the scan kernel instances
     int32_t need7_spacer[4] = {0, 0, 0, 0};
     bool motifs_set = false;
     bool consensus_prefilter = false;   // every heptamer flag entry matches CAC.GTG in >= 4 of 6 positions

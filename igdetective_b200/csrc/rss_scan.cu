@@ -685,11 +685,10 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
     const bool std4 = P.nwin == 4 && P.wnew[0] && !P.wnew[1] && P.wnew[2] && !P.wnew[3];
     auto kernel = h->consensus_prefilter ? (std4 ? rss_scan_kernel<true, true> : rss_scan_kernel<true, false>)
                                          : (std4 ? rss_scan_kernel<false, true> : rss_scan_kernel<false, false>);
-    static bool attr_set[4] = {false, false, false, false};           // once per kernel instance (same for every device of the process)
     const int inst = (h->consensus_prefilter ? 2 : 0) + (std4 ? 1 : 0);
-    if (!attr_set[inst]) {
+    if (!h->scan_attr_set[inst]) {                     // once per handle and kernel instance (the attribute is per device)
         IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
-        attr_set[inst] = true;
+        h->scan_attr_set[inst] = true;
     }
     unsigned long long blocks = (unsigned long long)h->sm_count;
     const unsigned long long wanted = (P.n_strips + V5_WARPS - 1) / V5_WARPS;
