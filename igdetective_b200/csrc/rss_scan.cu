@@ -495,6 +495,21 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
             }
             // ---- survivors into the warp queue, rounds as they form
             const unsigned pos00 = (r0 * 32 + lane + 1) * 64;                  // stage position of bit 0 of cm[0]
+            if (!PREFILTER) {
+                // exhaustive instance: every position is a candidate, so no enumeration -- two positions per lane
+                // and step go straight into the survivor queue (64 entries: one round of the heptamer test)
+                const unsigned nrow = min(rows - r0, 2u);
+                for (unsigned cur = 0; cur < nrow * 64u; cur += 2) {
+                    const unsigned pos = pos00 + (cur >> 6) * 2048u + (cur & 63u);
+                    W.q1()[W.n1 + lane] = (uint16_t)pos;
+                    W.q1()[W.n1 + 32 + lane] = (uint16_t)(pos + 1);
+                    W.n1 += 64;
+                    __syncwarp();
+                    const bool flush = cur + 2 >= nrow * 64u && r0 + 2 >= rows;
+                    drain<STD4>(P, W, flush, flush && last_strip);
+                }
+                continue;
+            }
             for (bool more = true; more;) {
                 const int cnt = __popc(cm[0]) + __popc(cm[1]) + __popc(cm[2]) + __popc(cm[3]);
                 int incl = cnt;
