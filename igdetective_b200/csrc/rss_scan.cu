@@ -356,23 +356,31 @@ template <bool STD4>
 __device__ __forceinline__ void drain(const ScanParams &P, Warp &W, bool flush, bool final)
 {
     for (;;) {
-        if (W.nsq >= 32 || (final && W.n1 == 0 && W.n2 == 0 && W.nsq > 0)) {
+        // full rounds first (three plain comparisons on the hot path); the partial rounds of a flush only
+        // when no queue holds a full one
+        int stage = W.nsq >= 32 ? 3 : (W.n2 >= 32 ? 2 : (W.n1 >= 64 ? 1 : 0));
+        if (stage == 0) {
+            if (!flush) break;
+            stage = W.n1 > 0 ? 1 : (W.n2 > 0 ? 2 : (final && W.nsq > 0 ? 3 : 0));
+            if (stage == 0) break;
+        }
+        if (stage == 3) {
             const int take = min(W.nsq, 32);
             W.nsq -= take;
             const bool active = (int)W.lane < take;
             exact_round(P, W.wb, W.sq()[W.nsq + (active ? W.lane : 0u)], active);
             __syncwarp();
             if (*(volatile unsigned *)(W.wb + WR_EBN) >= 32u) flush_keys(P, W.wb, W.lane);
-        } else if (W.n2 >= 32 || (flush && W.n1 == 0 && W.n2 > 0)) {
+        } else if (stage == 2) {
             const int take = min(W.n2, 32);
             W.n2 -= take;
             hits_round<STD4>(P, W, (int)W.lane < take ? W.q2()[W.n2 + W.lane] : 64u);      // 64: any position inside the stage
             __syncwarp();
-        } else if (W.n1 >= 64 || (flush && W.n1 > 0)) {
+        } else {
             const int take = min(W.n1, 64);
             W.n1 -= take;
             survivors_round(W, take);
-        } else break;
+        }
     }
 }
 
