@@ -420,6 +420,10 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     uint32_t *s_any9c = (uint32_t *)(s_need7 + 16384);                       // 32768
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef SCAN_TIMELINE
+    unsigned long long tl0, tl1 = 0, tl2 = 0; unsigned tl_strips = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
     Warp W;
     W.wb = smem + warp * WR_SIZE;
     uint64_t *full = (uint64_t *)(W.wb + WR_BAR);
@@ -434,16 +438,19 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     const auto strip_row0 = [&](unsigned s) { return s < P.n_long ? s * V5_MAXROWS : P.n_long * V5_MAXROWS + (s - P.n_long); };
     const auto strip_rows = [&](unsigned s) { return s < P.n_long ? (unsigned)V5_MAXROWS : 1u; };
     // Strips are handed out in batches of P.batch consecutive strips: every warp owns two batches from the start
-    // (no rush on the counter when the kernel starts), later ones come from a global atomic counter whose answer
-    // is needed a whole batch after it was asked for.  All of this is warp-uniform except `nn` (lane 0).
+    // (no rush on the counter when the kernel starts), later ones come from a global atomic counter.  With batches
+    // of several strips (large inputs) the answer is asked for two batches ahead; with single strips (small inputs)
+    // one strip ahead only, because every reserved strip is one a warp may still have to work through alone when
+    // the others have run out (seen as a tail of 8 us on 100 Mb).  All of this is warp-uniform except `nn` (lane 0).
     unsigned *const batch_counter = (unsigned *)(P.count + 1);
     const unsigned nwarps = gridDim.x * V5_WARPS, gw = blockIdx.x * V5_WARPS + warp;
     unsigned s_cur = gw * P.batch;                                       // current strip
     unsigned s_end = min(s_cur + P.batch, P.n_strips);                   // end of its batch
-    unsigned nb = gw + nwarps;                                           // next batch
-    unsigned nn = 0;                                                     // the batch after that (lane 0; atomic in flight)
+    const bool deep = P.batch > 1;
+    unsigned nb = gw + nwarps;                                           // next batch (deep hand-out)
+    unsigned nn = gw + nwarps;                                           // lane 0: the batch after that / the next one, may be in flight
     if (lane == 0) {
-        nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
+        if (deep) nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
         if (s_cur < P.n_strips) {
             const unsigned bytes = (strip_rows(s_cur) * 32u + 2u) * 16u;
             mbar_expect_tx(&full[0], bytes);
@@ -468,7 +475,12 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
     W.lane = (unsigned)lane; W.lt = (1u << lane) - 1u;
     for (unsigned it = 0; s_cur < P.n_strips; ++it) {
         const bool switch_batch = s_cur + 1 >= s_end;
-        const unsigned s_nxt = switch_batch ? (nb < 0x40000000u ? nb * P.batch : 0xffffffffu) : s_cur + 1;
+        unsigned s_nxt = s_cur + 1;
+        if (switch_batch) {
+            const unsigned b = deep ? nb : __shfl_sync(0xffffffffu, nn, 0);
+            s_nxt = b < 0x40000000u ? b * P.batch : 0xffffffffu;
+            if (!deep && lane == 0) nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
+        }
         if (lane == 0 && s_nxt < P.n_strips) {
             // the other buffer was read during iteration it-1 (all lanes passed the __syncwarp at its end)
             const unsigned bytes = (strip_rows(s_nxt) * 32u + 2u) * 16u;
@@ -477,6 +489,10 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         }
         __syncwarp();
         while (!mbar_try_wait(&full[it & 1u], (it >> 1) & 1u)) { }
+#ifdef SCAN_TIMELINE
+        if (it == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+        ++tl_strips;
+#endif
 
         const uint4 *rec = (const uint4 *)(W.wb + WR_BUF + (it & 1u) * V5_BUF_STRIDE);
         W.sp = smem_u32(rec);
@@ -563,11 +579,17 @@ rss_scan_kernel(const __grid_constant__ ScanParams P)
         __syncwarp();
         if (switch_batch) {
             s_end = s_nxt < P.n_strips ? min(s_nxt + P.batch, P.n_strips) : 0u;
-            nb = __shfl_sync(0xffffffffu, nn, 0);
-            if (lane == 0) nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
+            if (deep) {
+                nb = __shfl_sync(0xffffffffu, nn, 0);
+                if (lane == 0) nn = 2u * nwarps + atomicAdd(batch_counter, 1u);
+            }
         }
         s_cur = s_nxt;
     }
+#ifdef SCAN_TIMELINE
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl2));
+    if (lane == 0) printf("TL %u %d %llu %llu %llu %u\n", blockIdx.x, warp, tl0, tl1, tl2, tl_strips);
+#endif
     // what is left of the found keys leaves with ONE global atomic per CTA
     __syncthreads();
     unsigned *s_base = (unsigned *)s_any9c;                                  // the tables are no longer needed
