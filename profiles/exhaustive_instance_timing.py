@@ -1,5 +1,11 @@
-import sys, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+"""Scan kernel time on the 100 Mb bench contig with the shipped motif tables (consensus prefilter) and with one
+extra heptamer that breaks the consensus property (exhaustive instance of the same kernel)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, bench
 from igdetective_b200.engine import Engine
 from igdetective_b200.rss import SPACER_LENGTH

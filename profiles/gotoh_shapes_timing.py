@@ -1,5 +1,10 @@
+"""Packed Gotoh kernel throughput by target length (= kernel shape): 300 targets x the 490 IGHV genes."""
+import os
 import sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, bench, synth
 from igdetective_b200.engine import Engine
 motifs, canon = bench.load_data()

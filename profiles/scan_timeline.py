@@ -1,5 +1,12 @@
+"""Per-warp timeline of a 100 Mb scan: run with a library built with -DSCAN_TIMELINE
+(python profiles/build_variant.py tl -DSCAN_TIMELINE; IGD_B200_LIB=variants/libigd_tl.so python profiles/scan_timeline.py > log;
+python profiles/scan_timeline_summary.py log).  Every warp prints: CTA, warp, start, first data, end (globaltimer ns), strips."""
+import os
 import sys
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, bench
 from igdetective_b200.engine import Engine
 from igdetective_b200.rss import SPACER_LENGTH

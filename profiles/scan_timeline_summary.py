@@ -1,3 +1,4 @@
+"""Summary of the TL lines a -DSCAN_TIMELINE build prints (see scan_timeline.py).  usage: python profiles/scan_timeline_summary.py <log>"""
 import numpy as np, collections, sys
 runs=[];cur=None
 for l in open(sys.argv[1]):
