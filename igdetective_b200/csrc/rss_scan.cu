@@ -668,7 +668,7 @@ kmer_scan_kernel(const KmerParams P)
 
 } // namespace
 
-int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
+int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4], bool prepare_only)
 {
     ScanParams P;
     P.planes = h->d_planes; P.inv = h->d_inv; P.invsum = h->d_invsum;
@@ -735,6 +735,7 @@ int igd_launch_rss_scan(igd_handle *h, const int32_t spacer[4])
         IGD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScanSmem));
         h->scan_attr_set[inst] = true;
     }
+    if (prepare_only) return IGD_OK;                 // tables uploaded, kernel instance loaded and configured
     unsigned long long blocks = (unsigned long long)h->sm_count;
     const unsigned long long wanted = (P.n_strips + V5_WARPS - 1) / V5_WARPS;
     if (blocks > wanted) blocks = wanted;
