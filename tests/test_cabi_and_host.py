@@ -211,3 +211,33 @@ def test_center_bitmap_is_conservative(motifs):
         want = c in members or c[:8] in suf or c[1:] in pre
         assert bool(bits[kidx(c)]) == want
     assert 0.01 < bits.mean() < 0.08
+
+
+def test_sparse_host_glue_equals_reference_shapes():
+    """whole-genome mode (order="canonical") shares one empty value between the contigs that have nothing; the
+    contents are those of the reference-shaped dicts: same keys in the same order, same lists where there is
+    anything, an empty sequence elsewhere"""
+    from igdetective_b200.rss import combine_D_RSS, get_s_fragment_from_RSS
+    rng = np.random.default_rng(7)
+    ids = ["c%d" % i for i in range(40)]
+    s = "".join("ACGT"[i] for i in rng.integers(0, 4, 3000))
+    seqs = {c: s for c in ids}
+    for strand in "+-":
+        dl = {c: ([(int(p), int(p) - 21) for p in rng.integers(0, 3000, 30)] if i % 3 == 0 else []) for i, c in enumerate(ids)}
+        dr = {c: ([(int(p), int(p) + 19) for p in rng.integers(0, 3000, 30)] if i % 2 == 0 else []) for i, c in enumerate(ids)}
+        dense = combine_D_RSS(dl, dr, seqs, strand)
+        sparse = combine_D_RSS(dl, dr, seqs, strand, sparse=True)
+        assert dense == O.combine_D_RSS(dl, dr, seqs, strand)
+        assert list(sparse) == list(dense)
+        assert sum(len(v) for v in dense.values()) > 0
+        for c in ids:
+            assert list(sparse[c]) == dense[c]
+            assert dense[c] or sparse[c] == ()
+        info = {"V": {strand: {c: [(int(p), int(p) + 30) for p in rng.integers(400, 2500, 3)] if i % 4 == 0 else []
+                               for i, c in enumerate(ids)}},
+                "D": {strand: dense}}
+        for g in ("V", "D"):
+            fd = get_s_fragment_from_RSS(g, strand, info, seqs)
+            fs = get_s_fragment_from_RSS(g, strand, info, seqs, sparse=True)
+            assert fd == O.s_fragments(g, strand, info, seqs)
+            assert list(fs) == list(fd) and all(list(fs[c]) == fd[c] for c in ids)
