@@ -117,12 +117,14 @@ def gpu_arm(a):
 
     stats = {}
 
-    def step(e2e):
+    def step(e2e, record=False):
+        """One pass of the hot path: contigs -> the rows of genes_{V,D,J}.tsv (strings included)."""
         if e2e:
             eng.load_contigs((pinned.data_ptr(), off), list(seqs))
         info, rows = igdetective.detect(eng, seqs, canon, order="canonical", load=False)
-        stats["rows"] = {g: len(r) for g, r in rows.items()}
-        stats["rss"] = {st: sum(len(v) for sd in info[st] for v in info[st][sd].values()) for st in info}
+        if record:                          # workload description for the JSON line, outside the timed steps
+            stats["rows"] = {g: len(r) for g, r in rows.items()}
+            stats["rss"] = {st: sum(len(v) for sd in info[st] for v in info[st][sd].values()) for st in info}
         return rows
 
     def timed(e2e, k):
@@ -148,6 +150,7 @@ def gpu_arm(a):
     eng.load_contigs((pinned.data_ptr(), off), list(seqs))
     for _ in range(a.warmup):
         step(False)
+    step(False, record=True)
     clocks = Clocks(local) if rank == 0 else None
     t_dev, _, _, launches = timed(False, a.steps)
     # per-kernel device times of the last resident step: CUDA events on the library's stream

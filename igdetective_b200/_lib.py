@@ -12,13 +12,20 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IGD_B200_LIB") or os.path.join(_HERE, "libigd_b200.so")
 
 IGD_OK, IGD_ERR_CUDA, IGD_ERR_ARG, IGD_ERR_STATE = 0, -1, -2, -3
-IGD_ERR_TOO_LONG, IGD_ERR_UNSUPPORTED, IGD_ERR_CAPACITY = -4, -5, -6
+IGD_ERR_TOO_LONG, IGD_ERR_UNSUPPORTED, IGD_ERR_CAPACITY, IGD_ERR_INTERNAL = -4, -5, -6, -7
 MAX_TARGET_LEN, MAX_QUERY_LEN = 1023, 1023
 SIG_V, SIG_D_LEFT, SIG_D_RIGHT, SIG_J = 0, 1, 2, 3
 
 HIT_DTYPE = np.dtype([("hept", "<i8"), ("nona", "<i8"), ("contig", "<u4"), ("sig_type", "u1"),
                       ("strand", "u1"), ("spacer", "u1"), ("reserved", "u1")])
 KMER_HIT_DTYPE = np.dtype([("pos", "<i8"), ("contig", "<u4"), ("flags", "u1"), ("reserved", "u1", (3,))])
+# igd_vj_row / igd_d_row (include/igd_b200.h): rows of genes_V/J.tsv and genes_D.tsv in integer form
+VJ_ROW_DTYPE = np.dtype([("hept", "<i8"), ("nona", "<i8"), ("frag_start", "<i8"), ("contig", "<u4"), ("frag_len", "<i4"),
+                         ("best_gene", "<i4"), ("matches", "<i4"), ("alen", "<i4"), ("start", "<i4"), ("ient", "<i4"),
+                         ("gene_type", "u1"), ("strand", "u1"), ("direction", "u1"), ("reserved", "u1")])
+D_ROW_DTYPE = np.dtype([("dl_hept", "<i8"), ("dl_nona", "<i8"), ("dr_hept", "<i8"), ("dr_nona", "<i8"), ("contig", "<u4"),
+                        ("strand", "u1"), ("reserved", "u1", (3,))])
+assert VJ_ROW_DTYPE.itemsize == 56 and D_ROW_DTYPE.itemsize == 40
 
 
 class Scoring(ctypes.Structure):
@@ -27,6 +34,12 @@ class Scoring(ctypes.Structure):
         "match", "mismatch", "target_internal_open", "target_internal_extend",
         "target_end_open", "target_end_extend", "query_internal_open", "query_internal_extend",
         "query_end_open", "query_end_extend")]
+
+
+class DetectParams(ctypes.Structure):
+    """igd_detect_params == GENE_LENGTH, PI_CUTOFF, MAXK_CUTOFF of py/IGDetective.py:29-32 (index 0 = V, 1 = J)."""
+    _fields_ = [("gene_length", ctypes.c_int32 * 2), ("d_gene_length", ctypes.c_int32),
+                ("pi_strict", ctypes.c_double * 2), ("pi_relax", ctypes.c_double * 2), ("maxk_cutoff", ctypes.c_int32 * 2)]
 
 
 class Timing(ctypes.Structure):
@@ -45,7 +58,8 @@ class IgdError(RuntimeError):
 EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "igd_sync", "igd_get_timing",
            "igd_set_motifs", "igd_center_bitmap", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
-           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows")
+           "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows",
+           "igd_detect", "igd_fetch_vj_rows", "igd_fetch_d_rows")
 
 _lib = None
 
@@ -83,6 +97,13 @@ def load():
     lib.igd_score_fragments.restype = ctypes.c_int
     lib.igd_score_windows.argtypes = [vp, vp, vp, i32, vp, vp, i32, ctypes.POINTER(Scoring), vp, vp, vp, vp, vp]
     lib.igd_score_windows.restype = ctypes.c_int
+    lib.igd_detect.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, ctypes.POINTER(Scoring), ctypes.POINTER(DetectParams),
+                               u64p, u64p, u64p]
+    lib.igd_detect.restype = ctypes.c_int
+    lib.igd_fetch_vj_rows.argtypes = [vp, vp, ctypes.c_uint64]
+    lib.igd_fetch_vj_rows.restype = ctypes.c_int
+    lib.igd_fetch_d_rows.argtypes = [vp, vp, ctypes.c_uint64]
+    lib.igd_fetch_d_rows.restype = ctypes.c_int
     lib.igd_fasta_open.restype = vp
     lib.igd_fasta_open.argtypes = [ctypes.c_char_p]
     lib.igd_fasta_close.restype = None

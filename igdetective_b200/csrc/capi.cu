@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fcntl.h>
+#include <mutex>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -38,7 +39,6 @@ int igd_reserve(igd_handle *h, int slot, size_t bytes)
     return IGD_OK;
 }
 
-enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK, S_COUNT };
 
 extern "C" {
 
@@ -86,7 +86,7 @@ void igd_destroy(igd_handle *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any9c); cudaFree(h->d_need7); cudaFree(h->d_any7);
+    cudaFree(h->d_comp); cudaFree(h->d_lut7); cudaFree(h->d_lut9); cudaFree(h->d_any9); cudaFree(h->d_any9c); cudaFree(h->d_need7); cudaFree(h->d_any7);
     cudaFree(h->d_planes); cudaFree(h->d_inv); cudaFree(h->d_invsum);
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
@@ -277,6 +277,7 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     if ((rc = igd_reserve(h, S_CHUNK0, (size_t)(n_contigs + 1) * 8))) return rc;
     std::vector<uint64_t> rel(n_contigs + 1);
     for (int c = 0; c <= n_contigs; ++c) rel[c] = offsets[c] - offsets[0];
+    h->contig_seq_off = rel;
     if (nbytes) {
         int rc2 = upload_letters(h, (uint8_t *)h->d_scratch[S_SEQ], seq + offsets[0], nbytes);
         if (rc2) return rc2;
@@ -299,6 +300,7 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     }
     h->contigs_loaded = true;
     h->last_scan_kind = 0;
+    h->sorted_hits_valid = false;
     return IGD_OK;
 }
 
@@ -469,6 +471,7 @@ static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint6
         if (count <= h->hit_cap) {
             *n_hits = count;
             h->host_hits.clear();
+            h->sorted_hits_valid = false;
             h->last_scan_kind = kind; h->last_k = k;
             if (spacer) memcpy(h->last_spacer, spacer, sizeof h->last_spacer);
             return IGD_OK;
@@ -483,7 +486,9 @@ static int run_scan(igd_handle *h, int kind, int k, const int32_t *spacer, uint6
     return IGD_ERR_CAPACITY;
 }
 
-int igd_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits)
+} // extern "C"
+
+int igd_run_rss_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits)
 {
     if (!spacer) { igd_set_error("null spacer"); return IGD_ERR_ARG; }
     for (int t = 0; t < 4; ++t)
@@ -493,6 +498,10 @@ int igd_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits)
         }
     return run_scan(h, 1, 0, spacer, n_hits);
 }
+
+extern "C" {
+
+int igd_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits) { return igd_run_rss_scan(h, spacer, n_hits); }
 
 int igd_scan_kmers(igd_handle *h, int32_t k, uint64_t *n_hits)
 {
@@ -526,14 +535,17 @@ static int current_count(igd_handle *h, uint64_t *n)
     return IGD_OK;
 }
 
-int igd_fetch_hits(igd_handle *h, igd_hit *out, uint64_t capacity)
+} // extern "C"
+
+// Decodes the raw keys of the last RSS scan into igd_hit records sorted by (contig, sig_type, strand, index of the 5'
+// k-mer in scanned-strand coordinates); cached in the handle until the next scan.
+int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
 {
-    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
     if (h->last_scan_kind != 1) { igd_set_error("no RSS scan result to fetch"); return IGD_ERR_STATE; }
+    if (h->sorted_hits_valid) { *n_out = h->sorted_hits.size(); return IGD_OK; }
     IGD_CUDA(cudaSetDevice(h->device));
     uint64_t n = 0; int rc;
     if ((rc = current_count(h, &n))) return rc;
-    if (n > capacity) { igd_set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)n); return IGD_ERR_CAPACITY; }
     if ((rc = pull_hits(h, n))) return rc;
     struct Rec { uint64_t k0, k1; igd_hit hit; };
     std::vector<Rec> recs(n);
@@ -559,7 +571,22 @@ int igd_fetch_hits(igd_handle *h, igd_hit *out, uint64_t capacity)
         r.hit.sig_type = (uint8_t)t; r.hit.strand = (uint8_t)strand; r.hit.spacer = (uint8_t)s1; r.hit.reserved = 0;
     }
     std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.k0 != b.k0 ? a.k0 < b.k0 : a.k1 < b.k1; });
-    for (uint64_t i = 0; i < n; ++i) out[i] = recs[i].hit;
+    h->sorted_hits.resize(n);
+    for (uint64_t i = 0; i < n; ++i) h->sorted_hits[i] = recs[i].hit;
+    h->sorted_hits_valid = true;
+    *n_out = n;
+    return IGD_OK;
+}
+
+extern "C" {
+
+int igd_fetch_hits(igd_handle *h, igd_hit *out, uint64_t capacity)
+{
+    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    uint64_t n = 0; int rc;
+    if ((rc = igd_sorted_hits(h, &n))) return rc;
+    if (n > capacity) { igd_set_error("capacity %llu < %llu hits", (unsigned long long)capacity, (unsigned long long)n); return IGD_ERR_CAPACITY; }
+    if (n) memcpy(out, h->sorted_hits.data(), n * sizeof(igd_hit));
     return IGD_OK;
 }
 
@@ -590,12 +617,14 @@ int igd_fetch_kmer_hits(igd_handle *h, igd_kmer_hit *out, uint64_t capacity)
 // Can every intermediate DP value of an nA x nB pair be held in the packed kernel's 12-bit score
 // field, with the sentinel (-2000) below everything reachable and one extension short of wrapping?
 // 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
-static int case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t qbytes)
+} // extern "C"
+int igd_case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t qbytes)
 {
     for (size_t i = 0; i < qbytes; ++i) if ((unsigned)(qry[i] - 'a') < 26u) return 2;
     for (size_t i = 0; i < tbytes; ++i) if ((unsigned)(tgt[i] - 'a') < 26u) return 1;
     return 0;
 }
+extern "C" {
 
 static bool packed_scheme_ok(const igd_scoring *sc)
 {
@@ -649,7 +678,7 @@ int igd_align_batch(igd_handle *h,
 
     // validate, bucket by target length and kernel, detect lower-case letters
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
-    const int mixed = case_mix(tgt, tbytes, qry, qbytes);
+    const int mixed = igd_case_mix(tgt, tbytes, qry, qbytes);
     const bool detail = start || ient;
     const bool packed_ok = !detail && packed_scheme_ok(sc);
     constexpr int NB = 6;
@@ -790,10 +819,10 @@ int igd_align_batch(igd_handle *h,
 // Every target against every query through the packed run-mode kernels, results left on the device
 // (S_SCORE, S_PAY: [n_tgt][n_qry]); *launched = false (and nothing done) when some pair does not fit
 // the packed kernels, the caller then takes the pair-table path.
-static int dense_launch(igd_handle *h,
-                        const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
-                        const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
-                        const igd_scoring *sc, bool *launched)
+int igd_dense_launch(igd_handle *h,
+                     const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                     const igd_scoring *sc, bool *launched, bool tgt_resident)
 {
     *launched = false;
     const int64_t n_pairs = (int64_t)n_tgt * (int64_t)n_qry;
@@ -823,16 +852,19 @@ static int dense_launch(igd_handle *h,
     IGD_CUDA(cudaSetDevice(h->device));
     h->timing.align_ms = 0.f; h->timing.align_launches = 0; h->timing.align_cells = 0;
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
-    const int mixed = case_mix(tgt, tbytes, qry, qbytes);
+    // resident targets (igd_detect: gathered and upper-cased on the device) hold no lower-case letter
+    const int mixed = igd_case_mix(tgt, tgt_resident ? 0 : tbytes, qry, qbytes);
     int rc;
-    if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
-    if ((rc = igd_reserve(h, S_TGTOFF, (size_t)(n_tgt + 1) * 4))) return rc;
+    if (!tgt_resident) {
+        if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
+        if ((rc = igd_reserve(h, S_TGTOFF, (size_t)(n_tgt + 1) * 4))) return rc;
+    }
     if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
     if ((rc = igd_reserve(h, S_QRYOFF, (size_t)(n_qry + 1) * 4))) return rc;
     if ((rc = igd_reserve(h, S_SCORE, (size_t)n_pairs * 4))) return rc;
     if ((rc = igd_reserve(h, S_PAY, (size_t)n_pairs * 4))) return rc;
-    if (tbytes) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGT], tgt, tbytes, cudaMemcpyHostToDevice, h->stream));
-    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], tgt_off, (size_t)(n_tgt + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    if (tbytes && !tgt_resident) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGT], tgt, tbytes, cudaMemcpyHostToDevice, h->stream));
+    if (!tgt_resident) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], tgt_off, (size_t)(n_tgt + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRY], qry, qbytes, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, (size_t)(n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     // runs: each target's query list cut into chunks small enough to balance the persistent warps
@@ -886,7 +918,7 @@ int igd_align_dense(igd_handle *h,
     if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
     bool launched = false;
     int rc;
-    if ((rc = dense_launch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, sc, &launched))) return rc;
+    if ((rc = igd_dense_launch(h, tgt, tgt_off, n_tgt, qry, qry_off, n_qry, sc, &launched, false))) return rc;
     if (!launched) {                                   // generic path: explicit pair tables
         std::vector<int32_t> pt((size_t)n_pairs), pq((size_t)n_pairs);
         for (int t = 0; t < n_tgt; ++t)
@@ -923,17 +955,17 @@ int igd_align_dense(igd_handle *h,
 // str(Seq(s).reverse_complement()): Bio.Seq's IUPAC table, case preserving (as fasta.py:_COMP);
 // bytes outside the table stay as they are.
 static uint8_t g_comp[256];
-static bool g_comp_ready = false;
-static void init_comp()
+static std::once_flag g_comp_once;
+static void init_comp()                                 // reachable from two handles on two threads
 {
-    if (g_comp_ready) return;
-    for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
-    const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxnUu", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxnAa";
-    for (int i = 0; from[i]; ++i) g_comp[(uint8_t)from[i]] = (uint8_t)to[i];
-    g_comp_ready = true;
+    std::call_once(g_comp_once, [] {
+        for (int i = 0; i < 256; ++i) g_comp[i] = (uint8_t)i;
+        const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxnUu", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxnAa";
+        for (int i = 0; from[i]; ++i) g_comp[(uint8_t)from[i]] = (uint8_t)to[i];
+    });
 }
 
-static int stage_reserve(igd_handle *h, size_t bytes)
+int igd_stage_reserve(igd_handle *h, size_t bytes)
 {
     if (h->h_stage_cap >= bytes) return IGD_OK;
     if (h->h_stage) { IGD_CUDA(cudaFreeHost(h->h_stage)); h->h_stage = nullptr; h->h_stage_cap = 0; }
@@ -986,10 +1018,10 @@ int igd_score_fragments(igd_handle *h,
     int rc;
     if (U > 0) {
         bool launched = false;
-        if ((rc = dense_launch(h, tgt.data(), toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched))) return rc;
+        if ((rc = igd_dense_launch(h, tgt.data(), toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, false))) return rc;
         if (launched) {
             if ((rc = igd_reserve(h, S_PICK, UG * 4))) return rc;
-            if ((rc = stage_reserve(h, UG * 4))) return rc;
+            if ((rc = igd_stage_reserve(h, UG * 4))) return rc;
             if ((rc = igd_launch_pick(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_QRYOFF],
                                       U, n_gene, (uint32_t *)h->d_scratch[S_PICK]))) return rc;
             IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -1087,7 +1119,7 @@ int igd_score_windows(igd_handle *h,
     float ms_total = 0.f; int launches = 0; uint64_t cells = 0;
     bool launched = false;
     int rc;
-    if ((rc = dense_launch(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, sc, &launched))) return rc;
+    if ((rc = igd_dense_launch(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, sc, &launched, false))) return rc;
     if (launched) {
         if ((rc = igd_reserve(h, S_PICK, (size_t)n_win * sizeof(int4)))) return rc;
         if ((rc = igd_launch_select_windows(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_TGTOFF],

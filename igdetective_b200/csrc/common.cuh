@@ -61,6 +61,7 @@ struct igd_handle {
     uint64_t n_tiles = 0;
     std::vector<uint64_t> contig_chunk0;   // first chunk of each contig
     std::vector<uint64_t> contig_len;
+    std::vector<uint64_t> contig_seq_off;  // first letter of each contig in the resident letter buffer (S_SEQ)
     uint64_t total_bases = 0;
     bool contigs_loaded = false;
     size_t planes_cap = 0;        // chunks of capacity currently allocated
@@ -70,13 +71,18 @@ struct igd_handle {
     uint64_t hit_cap = 0;
     unsigned long long *d_count = nullptr;
     std::vector<unsigned long long> host_hits;   // last scan's raw keys
+    std::vector<igd_hit> sorted_hits;            // the same decoded and sorted (igd_fetch_hits order)
+    bool sorted_hits_valid = false;
+    std::vector<igd_vj_row> vj_rows;             // last igd_detect
+    std::vector<igd_d_row> d_rows;
+    uint8_t *d_comp = nullptr;                   // 256-byte complement table (Bio.Seq's IUPAC table), detect.cu
     int last_scan_kind = 0;                      // 0 none, 1 rss, 2 kmers
     int last_k = 0;
     int32_t last_spacer[4] = {0, 0, 0, 0};
 
     // generic growable device scratch for the aligner
-    void *d_scratch[14] = {nullptr};
-    size_t scratch_cap[14] = {0};
+    void *d_scratch[16] = {nullptr};
+    size_t scratch_cap[16] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
     void *h_ring = nullptr;       // ring of pinned pieces for the upload of pageable genomes (capi.cu, upload_letters)
@@ -93,7 +99,22 @@ int igd_cuda_fail(cudaError_t e, const char *what);
         if (_e != cudaSuccess) return igd_cuda_fail(_e, #call);            \
     } while (0)
 
+// growable device scratch slots (capi.cu, detect.cu)
+enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK,
+       S_FRAG, S_BEST, S_COUNT };
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
+int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
+// 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
+int igd_case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t qbytes);
+// Every target against every query through the packed run-mode kernels, results left on the device
+// (S_SCORE, S_PAY: [n_tgt][n_qry]); *launched = false (and nothing done) when some pair does not fit the
+// packed kernels.  tgt_resident: the targets and their offsets already sit in S_TGT / S_TGTOFF.
+int igd_dense_launch(igd_handle *h, const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
+                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                     const igd_scoring *sc, bool *launched, bool tgt_resident);
+// scan + hit decoding shared by igd_scan / igd_fetch_hits / igd_detect
+int igd_run_rss_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits);
+int igd_sorted_hits(igd_handle *h, uint64_t *n);          // fills h->sorted_hits from the last RSS scan
 
 // pack.cu
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,

@@ -1,0 +1,406 @@
+// igd_detect: the module body of py/IGDetective.py:439-487 in one call on the contigs resident in the handle.
+//
+//   RSS scan (rss_scan.cu)  ->  hit list (host: decode + sort, a few 10^3..10^5 records)
+//   combine_D_RSS (:210-224) -> sorted search over the D_left / D_right hits, host
+//   get_s_fragment_from_RSS (:268-300) -> gather_fragments_kernel over the resident ASCII letters: Python slice
+//       semantics incl. the negative-start quirk of parent_seq[index-length:index] (:265), upper-cased (:308),
+//       reverse-complemented for strand '-' with Bio.Seq's IUPAC table; each fragment and its reverse complement
+//       become targets 2u / 2u+1
+//   align_fragment_to_genes (:319-360) -> packed Gotoh kernels over [2U targets] x [all genes], the orientation
+//       choice of ComputeAlignment (:314-317) and np.argmax's first maximum (:473) on the device
+//   threshold (:387) on the host in float64, the winners' ComputeAlignment (:388) through the two-register
+//       Gotoh kernel for AlignmentRange()[0] and the end of QuerySeq()
+// Only integers cross the bus: 8 bytes per RSS hit in, 16 bytes per candidate and 8 per winner out.
+#include "common.cuh"
+#include <algorithm>
+#include <unordered_map>
+
+namespace {
+
+struct FragDesc { unsigned long long g0; int32_t len; int32_t rc; };   // letters [g0, g0+len) of the letter buffer
+
+// target 2u = upper(fragment u) (reverse-complemented when rc), target 2u+1 = its reverse complement
+__global__ void __launch_bounds__(128)
+gather_fragments_kernel(const uint8_t *__restrict__ seq, const FragDesc *__restrict__ fr, const int32_t *__restrict__ toff,
+                        const uint8_t *__restrict__ comp, int n, uint8_t *__restrict__ tgt)
+{
+    __shared__ uint8_t s_comp[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_comp[i] = comp[i];
+    __syncthreads();
+    for (int u = blockIdx.x; u < n; u += gridDim.x) {
+        const FragDesc f = fr[u];
+        uint8_t *F = tgt + toff[2 * u], *R = tgt + toff[2 * u + 1];
+        for (int k = threadIdx.x; k < f.len; k += blockDim.x) {
+            unsigned c = seq[f.g0 + (unsigned long long)(f.rc ? f.len - 1 - k : k)];
+            if (c - 'a' < 26u) c -= 32u;
+            if (f.rc) c = s_comp[c];
+            F[k] = (uint8_t)c;
+            R[f.len - 1 - k] = s_comp[c];
+        }
+    }
+}
+
+// np.argmax(pi_mat[k]) (py/IGDetective.py:473): FIRST maximum of PI = (matches-1)/len*100 over the genes, compared
+// exactly by cross-multiplication (equal rationals give equal float64 PI, different ones differ by far more than
+// an ulp).  pick[u][g] = matches | len << 10 | forward << 31 (pick_orientation_kernel).  One warp per fragment.
+__global__ void __launch_bounds__(256)
+argmax_pick_kernel(const uint32_t *__restrict__ pick, int n_unique, int n_qry, int4 *__restrict__ out)
+{
+    const int u = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (u >= n_unique) return;
+    long long bn = 0, bd = 1; int bi = -1; uint32_t bw = 0;
+    for (int g = lane; g < n_qry; g += 32) {
+        const uint32_t w = pick[(size_t)u * n_qry + g];
+        const long long num = (long long)(int)(w & 1023u) - 1, den = (long long)((w >> 10) & 0x1fffffu);
+        if (bi < 0 || num * bd > bn * den) { bn = num; bd = den; bi = g; bw = w; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long on = __shfl_xor_sync(0xffffffffu, bn, o), od = __shfl_xor_sync(0xffffffffu, bd, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const uint32_t ow = __shfl_xor_sync(0xffffffffu, bw, o);
+        if (oi >= 0) {
+            const long long l = on * bd, r = bn * od;
+            if (bi < 0 || l > r || (l == r && oi < bi)) { bn = on; bd = od; bi = oi; bw = ow; }
+        }
+    }
+    if (lane == 0) out[u] = make_int4(bi, (int)(bw & 1023u), (int)((bw >> 10) & 0x1fffffu), (int)(bw >> 31));
+}
+
+// parent_seq[a:b] with Python's slice semantics on a sequence of length L -> (start, length)
+inline void py_slice(int64_t a, int64_t b, int64_t L, int64_t &s, int64_t &n)
+{
+    if (a < 0) { a += L; if (a < 0) a = 0; } else if (a > L) a = L;
+    if (b < 0) { b += L; if (b < 0) b = 0; } else if (b > L) b = L;
+    s = a; n = b > a ? b - a : 0;
+}
+
+struct Best { int32_t gene, matches, alen, fwd; };
+
+struct SliceKey {
+    unsigned long long g0; int32_t len, rc;
+    bool operator==(const SliceKey &o) const { return g0 == o.g0 && len == o.len && rc == o.rc; }
+};
+struct SliceHash {
+    size_t operator()(const SliceKey &k) const { return (size_t)(k.g0 * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.len << 1) ^ (size_t)k.rc; }
+};
+struct Acc { float ms = 0.f; uint64_t cells = 0; unsigned launches = 0; };
+
+// the 'A' * len(gene) stand-in of an empty fragment (py/IGDetective.py:339-340), per gene: pick word as in
+// pick_orientation_kernel (host pair-table path: a few hundred short pairs, and only when an empty fragment exists)
+int empty_fragment_best(igd_handle *h, const uint8_t *gene, const int32_t *gene_off, int32_t n_gene, const igd_scoring *sc, Best *best)
+{
+    std::unordered_map<int, int32_t> by_len;
+    std::vector<uint8_t> et; std::vector<int32_t> eoff(1, 0), pt, pq;
+    for (int32_t g = 0; g < n_gene; ++g) {
+        const int n = gene_off[g + 1] - gene_off[g];
+        auto it = by_len.find(n);
+        if (it == by_len.end()) {
+            it = by_len.emplace(n, (int32_t)by_len.size()).first;
+            et.insert(et.end(), (size_t)n, (uint8_t)'A'); eoff.push_back((int32_t)et.size());
+            et.insert(et.end(), (size_t)n, (uint8_t)'T'); eoff.push_back((int32_t)et.size());
+        }
+        pt.push_back(2 * it->second); pq.push_back(g);
+        pt.push_back(2 * it->second + 1); pq.push_back(g);
+    }
+    std::vector<int32_t> s_(pt.size()), m_(pt.size()), l_(pt.size());
+    int rc = igd_align_batch(h, et.data(), eoff.data(), (int32_t)eoff.size() - 1, gene, gene_off, n_gene,
+                             pt.data(), pq.data(), (int64_t)pt.size(), sc, s_.data(), m_.data(), l_.data(), nullptr, nullptr);
+    if (rc) return rc;
+    long long bn = 0, bd = 1; best->gene = -1;
+    for (int32_t g = 0; g < n_gene; ++g) {
+        const bool fwd = m_[2 * (size_t)g] > m_[2 * (size_t)g + 1];
+        const size_t w = 2 * (size_t)g + (fwd ? 0 : 1);
+        const long long num = m_[w] - 1, den = l_[w];
+        if (best->gene < 0 || num * bd > bn * den) { bn = num; bd = den; best->gene = g; best->matches = m_[w]; best->alen = l_[w]; best->fwd = fwd; }
+    }
+    return IGD_OK;
+}
+
+struct Cand { uint32_t hit; int64_t start; int32_t len; int32_t rc; };
+
+// One gene type (V or J): score the candidates cand[] against the gene table, append the winners' rows.
+int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
+                    const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                    const igd_scoring *sc, const igd_detect_params *prm, Acc &acc)
+{
+    if (cand.empty() || n_gene <= 0) return IGD_OK;
+    int rc;
+    bool any_empty = false;
+    for (const Cand &c : cand) any_empty |= c.len == 0;
+    Best empty_best = {-1, 0, 0, 0};
+    if (any_empty) {
+        if ((rc = empty_fragment_best(h, gene, gene_off, n_gene, sc, &empty_best))) return rc;
+        acc.ms += h->timing.align_ms; acc.cells += h->timing.align_cells; acc.launches += h->timing.align_launches;
+    }
+    const int mixed = igd_case_mix(nullptr, 0, gene, (size_t)gene_off[n_gene]);      // targets are upper-cased
+    constexpr int NB = 6;
+    const size_t max_pairs = (size_t)1 << 28;                                       // per batch: 2 x 1 GiB of result words
+    const size_t batch_frag = std::max<size_t>(1, max_pairs / (2 * (size_t)n_gene));
+    for (size_t c0 = 0; c0 < cand.size();) {
+        // ---- batch: candidates [c0, c1) with at most batch_frag distinct non-empty fragments ---------------
+        std::unordered_map<SliceKey, int32_t, SliceHash> seen;                      // identical slices are scored once
+        std::vector<FragDesc> frags;
+        std::vector<int32_t> uid;
+        size_t c1 = c0;
+        for (; c1 < cand.size(); ++c1) {
+            const Cand &c = cand[c1];
+            if (c.len == 0) { uid.push_back(-1); continue; }
+            const SliceKey key = {h->contig_seq_off[h->sorted_hits[c.hit].contig] + (unsigned long long)c.start, c.len, c.rc};
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                if (frags.size() >= batch_frag) break;
+                it = seen.emplace(key, (int32_t)frags.size()).first;
+                frags.push_back({key.g0, c.len, c.rc});
+            }
+            uid.push_back(it->second);
+        }
+        const int32_t U = (int32_t)frags.size();
+        std::vector<int4> best((size_t)std::max(U, 1));
+        std::vector<int32_t> toff((size_t)2 * U + 1, 0);
+        if (U > 0) {
+            for (int32_t u = 0; u < U; ++u) { toff[2 * u + 1] = toff[2 * u] + frags[u].len; toff[2 * u + 2] = toff[2 * u + 1] + frags[u].len; }
+            const size_t tbytes = (size_t)toff[2 * U];
+            if (tbytes > 0x7fffff00u) { igd_set_error("fragment batch exceeds 2 GiB"); return IGD_ERR_CAPACITY; }
+            if ((rc = igd_reserve(h, S_FRAG, (size_t)U * sizeof(FragDesc)))) return rc;
+            if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
+            if ((rc = igd_reserve(h, S_TGTOFF, ((size_t)2 * U + 1) * 4))) return rc;
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_FRAG], frags.data(), (size_t)U * sizeof(FragDesc), cudaMemcpyHostToDevice, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], toff.data(), ((size_t)2 * U + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+            gather_fragments_kernel<<<std::min(U, h->sm_count * 16), 128, 0, h->stream>>>(
+                (const uint8_t *)h->d_scratch[S_SEQ], (const FragDesc *)h->d_scratch[S_FRAG], (const int32_t *)h->d_scratch[S_TGTOFF],
+                h->d_comp, U, (uint8_t *)h->d_scratch[S_TGT]);
+            h->timing.total_launches++;
+            IGD_CUDA(cudaGetLastError());
+            bool launched = false;
+            if ((rc = igd_dense_launch(h, nullptr, toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, true))) return rc;
+            if (!launched) {
+                igd_set_error("a (fragment, gene) pair does not fit the packed alignment kernels (gene longer than 511 or scores out of range)");
+                return IGD_ERR_UNSUPPORTED;
+            }
+            if ((rc = igd_reserve(h, S_PICK, (size_t)U * n_gene * 4))) return rc;
+            if ((rc = igd_reserve(h, S_BEST, (size_t)U * sizeof(int4)))) return rc;
+            if ((rc = igd_launch_pick(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_QRYOFF],
+                                      U, n_gene, (uint32_t *)h->d_scratch[S_PICK]))) return rc;
+            argmax_pick_kernel<<<(unsigned)(((size_t)U * 32 + 255) / 256), 256, 0, h->stream>>>(
+                (const uint32_t *)h->d_scratch[S_PICK], U, n_gene, (int4 *)h->d_scratch[S_BEST]);
+            h->timing.total_launches++; h->timing.align_launches++;
+            IGD_CUDA(cudaGetLastError());
+            IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(best.data(), h->d_scratch[S_BEST], (size_t)U * sizeof(int4), cudaMemcpyDeviceToHost, h->stream));
+            IGD_CUDA(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            acc.ms += ms; acc.cells += h->timing.align_cells; acc.launches += h->timing.align_launches;
+        }
+        // ---- threshold (:387) in float64, exactly as the reference evaluates it ------------------------------
+        struct Win { size_t cand; Best b; };
+        std::vector<Win> wins;
+        for (size_t c = c0; c < c1; ++c) {
+            const int32_t u = uid[c - c0];
+            Best b;
+            if (u >= 0) { const int4 v = best[(size_t)u]; b = {v.x, v.y, v.z, v.w}; } else b = empty_best;
+            if (b.gene < 0) continue;
+            const double pi = (double)(b.matches - 1) / (double)b.alen * 100.0;
+            const double maxk = (double)b.alen;
+            if (pi >= prm->pi_strict[gt] || (pi >= prm->pi_relax[gt] && maxk >= (double)prm->maxk_cutoff[gt])) wins.push_back({c, b});
+        }
+        // ---- the winners' alignment once more for its range (:388): two passes of the two-register kernel -----
+        std::vector<int32_t> w_start(wins.size(), 0), w_ient(wins.size(), 0);
+        std::vector<int32_t> pt, pq, who;
+        for (size_t i = 0; i < wins.size(); ++i) {
+            const int32_t u = uid[wins[i].cand - c0];
+            if (u < 0) continue;                                    // empty fragment: the reference aligns '' here
+            pt.push_back(2 * u + (wins[i].b.fwd ? 0 : 1)); pq.push_back(wins[i].b.gene); who.push_back((int32_t)i);
+        }
+        if (!pt.empty()) {
+            const size_t n = pt.size();
+            std::vector<int32_t> work[NB], flat;
+            for (size_t i = 0; i < n; ++i) work[igd_align_bucket_of(toff[pt[i] + 1] - toff[pt[i]])].push_back((int32_t)i);
+            size_t woff[NB];
+            for (int b = 0; b < NB; ++b) { woff[b] = flat.size(); flat.insert(flat.end(), work[b].begin(), work[b].end()); }
+            if ((rc = igd_reserve(h, S_SCORE, n * 4))) return rc;          // the dense results are consumed: reuse their slots
+            if ((rc = igd_reserve(h, S_PAY, 2 * n * 4))) return rc;
+            if ((rc = igd_reserve(h, S_PT, n * 4))) return rc;
+            if ((rc = igd_reserve(h, S_PQ, n * 4))) return rc;
+            if ((rc = igd_reserve(h, S_WORK, n * 4))) return rc;
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PT], pt.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_PQ], pq.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_WORK], flat.data(), n * 4, cudaMemcpyHostToDevice, h->stream));
+            std::vector<uint32_t> pay(2 * n);
+            h->timing.align_launches = 0;
+            IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+            for (int pass = 0; pass < 2; ++pass) {
+                IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
+                for (int b = 0; b < NB; ++b) {
+                    if (work[b].empty()) continue;
+                    igd_align_job job;
+                    job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
+                    job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
+                    job.d_pair_t = (const int32_t *)h->d_scratch[S_PT]; job.d_pair_q = (const int32_t *)h->d_scratch[S_PQ];
+                    job.d_work = (const int32_t *)h->d_scratch[S_WORK] + woff[b]; job.d_runs = nullptr;
+                    job.n_work = (int32_t)work[b].size();
+                    job.bucket = b; job.mixed_case = mixed; job.packed = 0; job.pay_mode = pass; job.sc = *sc;
+                    job.d_score = (int32_t *)h->d_scratch[S_SCORE];
+                    job.d_pay = (uint32_t *)h->d_scratch[S_PAY] + (size_t)pass * n;
+                    job.d_counter = (unsigned int *)(h->d_count + 8 + b);
+                    if ((rc = igd_launch_gotoh(h, job))) return rc;
+                }
+            }
+            IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+            IGD_CUDA(cudaMemcpyAsync(pay.data(), h->d_scratch[S_PAY], 2 * n * 4, cudaMemcpyDeviceToHost, h->stream));
+            IGD_CUDA(cudaStreamSynchronize(h->stream));
+            float ms = 0.f;
+            IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            acc.ms += ms; acc.launches += h->timing.align_launches;
+            for (size_t i = 0; i < n; ++i) {
+                const int nA = toff[pt[i] + 1] - toff[pt[i]], nB = gene_off[pq[i] + 1] - gene_off[pq[i]];
+                const Best &b = wins[(size_t)who[i]].b;
+                const int m = (int)(pay[i] & 1023u), alen = nB + (int)((pay[i] >> 10) & 1023u);
+                if (m != b.matches || alen != b.alen) { igd_set_error("internal: packed and two-register kernels disagree"); return IGD_ERR_INTERNAL; }
+                acc.cells += 2ull * (uint64_t)nA * (uint64_t)nB;
+                w_start[(size_t)who[i]] = (int)((pay[i] >> 20) & 1023u);
+                w_ient[(size_t)who[i]] = nA - (int)((pay[n + i] >> 20) & 1023u);
+            }
+        }
+        for (size_t i = 0; i < wins.size(); ++i) {
+            const Cand &c = cand[wins[i].cand];
+            const igd_hit &hit = h->sorted_hits[c.hit];
+            igd_vj_row r;
+            r.hept = hit.hept; r.nona = hit.nona; r.frag_start = c.start; r.contig = hit.contig; r.frag_len = c.len;
+            r.best_gene = wins[i].b.gene; r.matches = wins[i].b.matches; r.alen = wins[i].b.alen;
+            r.start = w_start[i]; r.ient = w_ient[i];
+            r.gene_type = (uint8_t)gt; r.strand = hit.strand;
+            r.direction = (uint8_t)((c.len > 0 && wins[i].b.fwd) ? '+' : '-');
+            r.reserved = 0;
+            h->vj_rows.push_back(r);
+        }
+        c0 = c1;
+    }
+    return IGD_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int igd_detect(igd_handle *h, const int32_t spacer[4],
+               const uint8_t *vgene, const int32_t *vgene_off, int32_t n_vgene,
+               const uint8_t *jgene, const int32_t *jgene_off, int32_t n_jgene,
+               const igd_scoring *sc, const igd_detect_params *prm,
+               uint64_t *n_hits, uint64_t *n_vj_rows, uint64_t *n_d_rows)
+{
+    if (!h || !spacer || !sc || !prm || !n_hits || !n_vj_rows || !n_d_rows || n_vgene < 0 || n_jgene < 0 ||
+        (n_vgene && (!vgene || !vgene_off)) || (n_jgene && (!jgene || !jgene_off))) {
+        igd_set_error("bad arguments to igd_detect"); return IGD_ERR_ARG;
+    }
+    if (prm->gene_length[0] < 1 || prm->gene_length[0] > IGD_MAX_TARGET_LEN || prm->gene_length[1] < 1 || prm->gene_length[1] > IGD_MAX_TARGET_LEN) {
+        igd_set_error("gene_length must lie in 1..%d", IGD_MAX_TARGET_LEN); return IGD_ERR_ARG;
+    }
+    h->vj_rows.clear(); h->d_rows.clear();
+    int rc;
+    if ((rc = igd_run_rss_scan(h, spacer, n_hits))) return rc;
+    uint64_t n = 0;
+    if ((rc = igd_sorted_hits(h, &n))) return rc;
+    if (!h->d_comp) {
+        uint8_t comp[256];
+        for (int i = 0; i < 256; ++i) comp[i] = (uint8_t)i;
+        const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxnUu", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxnAa";
+        for (int i = 0; from[i]; ++i) comp[(uint8_t)from[i]] = (uint8_t)to[i];
+        IGD_CUDA(cudaMalloc(&h->d_comp, 256));
+        IGD_CUDA(cudaMemcpyAsync(h->d_comp, comp, 256, cudaMemcpyHostToDevice, h->stream));
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    const std::vector<igd_hit> &hits = h->sorted_hits;
+    // hits are sorted by (contig, type, strand, list index): one block per contig, eight sub-lists inside
+    std::vector<Cand> cand[2][2];                       // [V, J][strand]
+    std::vector<igd_d_row> drows[2];
+    for (size_t b0 = 0; b0 < hits.size();) {
+        size_t b1 = b0;
+        while (b1 < hits.size() && hits[b1].contig == hits[b0].contig) ++b1;
+        const int64_t L = (int64_t)h->contig_len[hits[b0].contig];
+        size_t lo[4][2], hi[4][2];
+        for (int t = 0; t < 4; ++t) for (int s = 0; s < 2; ++s) lo[t][s] = hi[t][s] = b0;
+        for (size_t i = b0; i < b1;) {
+            size_t j = i;
+            while (j < b1 && hits[j].sig_type == hits[i].sig_type && hits[j].strand == hits[i].strand) ++j;
+            lo[hits[i].sig_type][hits[i].strand] = i; hi[hits[i].sig_type][hits[i].strand] = j;
+            i = j;
+        }
+        // V / J candidates: get_s_fragment_from_RSS (:268-286)
+        for (int gt = 0; gt < 2; ++gt) {
+            const int t = gt == 0 ? IGD_SIG_V : IGD_SIG_J;
+            const int64_t glen = prm->gene_length[gt];
+            for (int s = 0; s < 2; ++s)
+                for (size_t i = lo[t][s]; i < hi[t][s]; ++i) {
+                    const int64_t q = hits[i].hept;
+                    int64_t st, ln;
+                    const bool before = (gt == 0 && s == 0) || (gt == 1 && s == 1);     // the letters in front of the heptamer
+                    if (before) py_slice(q - glen, q, L, st, ln); else py_slice(q + 7, q + 7 + glen, L, st, ln);
+                    cand[gt][s].push_back({(uint32_t)i, st, (int32_t)ln, s});
+                }
+        }
+        // D pairs: combine_D_RSS (:210-224), D_right outer / D_left inner
+        for (int s = 0; s < 2; ++s) {
+            const size_t l0 = lo[IGD_SIG_D_LEFT][s], l1 = hi[IGD_SIG_D_LEFT][s], r0 = lo[IGD_SIG_D_RIGHT][s], r1 = hi[IGD_SIG_D_RIGHT][s];
+            if (l0 == l1 || r0 == r1) continue;
+            std::vector<std::pair<int64_t, uint32_t>> dl;           // (heptamer, list position)
+            for (size_t i = l0; i < l1; ++i) dl.push_back({hits[i].hept, (uint32_t)(i - l0)});
+            std::sort(dl.begin(), dl.end());
+            const int64_t span = prm->d_gene_length + 7;
+            std::vector<uint32_t> sel;
+            for (size_t k = r0; k < r1; ++k) {
+                const int64_t dr = hits[k].hept;
+                // '+': left = dl, right = dr: dr-span <= dl <= dr-1;  '-': left = dr, right = dl: dr+1 <= dl <= dr+span
+                const int64_t a = s == 0 ? dr - span : dr + 1, b = s == 0 ? dr - 1 : dr + span;
+                auto x = std::lower_bound(dl.begin(), dl.end(), std::make_pair(a, (uint32_t)0));
+                auto y = std::upper_bound(dl.begin(), dl.end(), std::make_pair(b, (uint32_t)0xffffffffu));
+                sel.clear();
+                for (auto it = x; it != y; ++it) sel.push_back(it->second);
+                std::sort(sel.begin(), sel.end());
+                for (uint32_t p : sel) {
+                    const igd_hit &l = hits[l0 + p];
+                    igd_d_row r;
+                    r.dl_hept = l.hept; r.dl_nona = l.nona; r.dr_hept = hits[k].hept; r.dr_nona = hits[k].nona;
+                    r.contig = hits[k].contig; r.strand = (uint8_t)s; r.reserved[0] = r.reserved[1] = r.reserved[2] = 0;
+                    drows[s].push_back(r);
+                }
+            }
+        }
+        b0 = b1;
+    }
+    h->d_rows = drows[0];
+    h->d_rows.insert(h->d_rows.end(), drows[1].begin(), drows[1].end());
+    const float scan_ms = h->timing.scan_ms;
+    Acc acc;
+    for (int gt = 0; gt < 2; ++gt) {
+        std::vector<Cand> all = cand[gt][0];
+        all.insert(all.end(), cand[gt][1].begin(), cand[gt][1].end());
+        if ((rc = score_gene_type(h, gt, all, gt == 0 ? vgene : jgene, gt == 0 ? vgene_off : jgene_off, gt == 0 ? n_vgene : n_jgene,
+                                  sc, prm, acc))) return rc;
+    }
+    h->timing.scan_ms = scan_ms;
+    h->timing.align_ms = acc.ms; h->timing.align_cells = acc.cells; h->timing.align_launches = acc.launches;
+    *n_vj_rows = h->vj_rows.size();
+    *n_d_rows = h->d_rows.size();
+    return IGD_OK;
+}
+
+int igd_fetch_vj_rows(igd_handle *h, igd_vj_row *out, uint64_t capacity)
+{
+    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (h->vj_rows.size() > capacity) { igd_set_error("capacity %llu < %llu rows", (unsigned long long)capacity, (unsigned long long)h->vj_rows.size()); return IGD_ERR_CAPACITY; }
+    if (!h->vj_rows.empty()) memcpy(out, h->vj_rows.data(), h->vj_rows.size() * sizeof(igd_vj_row));
+    return IGD_OK;
+}
+
+int igd_fetch_d_rows(igd_handle *h, igd_d_row *out, uint64_t capacity)
+{
+    if (!h || (!out && capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (h->d_rows.size() > capacity) { igd_set_error("capacity %llu < %llu rows", (unsigned long long)capacity, (unsigned long long)h->d_rows.size()); return IGD_ERR_CAPACITY; }
+    if (!h->d_rows.empty()) memcpy(out, h->d_rows.data(), h->d_rows.size() * sizeof(igd_d_row));
+    return IGD_OK;
+}
+
+} // extern "C"

@@ -4,64 +4,109 @@
 // (py/IGDetective.py:140-143) and the str(seq.reverse_complement()) copies of
 // get_contigwise_rss (:187-190): case is folded and non-ACGT letters are marked once here;
 // the reverse strand is never materialised.
+//
+// HBM-bound: 1 B read + 0.375 B written per base.  A warp packs 32 consecutive chunks (one word of the
+// summary bitmap) in four steps of 8 chunks; in a step every lane owns 16 consecutive letters, fetched
+// by two aligned 16-byte loads (the contigs sit back to back in the letter buffer, so a chunk's letters
+// start at any byte: the 16 wanted bytes are cut out of the 32 loaded ones by funnel shifts), classified
+// through a 256-entry table in shared memory whose entries hold the low / high code bit and the
+// "not ACGT" bit in three byte-wide fields, and accumulated with one shift-add per letter; four lanes'
+// results are joined into the chunk's record by shuffles.
 #include "common.cuh"
 
 namespace {
 
-__device__ __forceinline__ void classify(unsigned char ch, bool in_range, unsigned &code, bool &bad)
-{
-    const unsigned c = ch & 0xDFu;                       // fold case
-    const bool ok = in_range && (c == 'A' || c == 'C' || c == 'G' || c == 'T');
-    const unsigned x = (c >> 1) & 3u;                    // A0 C1 G3 T2
-    code = ok ? (x ^ (x >> 1)) : 0u;                     // A0 C1 G2 T3
-    bad = !ok;
-}
+constexpr int PACK_THREADS = 256;
 
-// One warp packs 32 consecutive chunks (so it owns one word of the summary bitmap).
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint4 ldg_nc_128(const uint8_t *p) { return __ldg((const uint4 *)p); }
+
+__global__ void __launch_bounds__(PACK_THREADS)
 pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restrict__ seq_off,
             const unsigned long long *__restrict__ chunk0, int n_contigs,
             unsigned long long n_chunks, uint4 *__restrict__ planes,
             unsigned long long *__restrict__ inv, uint32_t *__restrict__ invsum)
 {
-    const unsigned lane = threadIdx.x & 31u;
+    // entry: bit 0 = low code bit, bit 8 = high code bit, bit 16 = letter is not A/C/G/T in either case
+    // (codes A0 C1 G2 T3)
+    __shared__ uint32_t lut[256];
+    for (int i = threadIdx.x; i < 256; i += PACK_THREADS) {
+        const int c = i & 0xDF;
+        uint32_t e = 1u << 16;
+        if (c == 'A') e = 0u;
+        else if (c == 'C') e = 1u;
+        else if (c == 'G') e = 1u << 8;
+        else if (c == 'T') e = 1u | (1u << 8);
+        lut[i] = e;
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31u, sub = lane & 3u;
     const unsigned long long warp = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
     const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     const unsigned long long ngroups = (n_chunks + 31) / 32;
 
     for (unsigned long long g = warp; g < ngroups; g += nwarps) {
-        unsigned summary = 0;
-        // contig holding the first chunk of the group: last c with chunk0[c] <= chunk
-        unsigned long long chunk = g * 32;
-        int lo = 0, hi = n_contigs;                      // first c with chunk0[c] > chunk
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (chunk0[mid] <= chunk) lo = mid + 1; else hi = mid; }
+        // contig holding the first chunk of the group: last c with chunk0[c] <= chunk (warp-uniform search)
+        int lo = 0, hi = n_contigs;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&chunk0[mid]) <= g * 32) lo = mid + 1; else hi = mid; }
         int c = lo - 1;
-        for (int i = 0; i < 32; ++i, ++chunk) {
-            if (chunk >= n_chunks) break;
-            while (c + 1 < n_contigs && chunk0[c + 1] <= chunk) ++c;
-            unsigned long long base_in_contig = 0, len = 0, src = 0;
-            if (c >= 0) {
-                base_in_contig = (chunk - chunk0[c]) * 64ull;
-                len = seq_off[c + 1] - seq_off[c];
-                src = seq_off[c] + base_in_contig;
-            }
-            unsigned w[2][3];
+        unsigned summary = 0;
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const unsigned long long p = base_in_contig + half * 32 + lane;
-                const bool in_range = (c >= 0) && p < len;
-                const unsigned char ch = in_range ? seq[src + half * 32 + lane] : 0;
-                unsigned code; bool bad;
-                classify(ch, in_range, code, bad);
-                w[half][0] = __ballot_sync(0xffffffffu, code & 1u);
-                w[half][1] = __ballot_sync(0xffffffffu, code & 2u);
-                w[half][2] = __ballot_sync(0xffffffffu, bad);
+        for (int it = 0; it < 4; ++it) {
+            const unsigned long long chunk = g * 32 + (unsigned)it * 8u + (lane >> 2);
+            while (c + 1 < n_contigs && __ldg(&chunk0[c + 1]) <= chunk) ++c;
+            int nvalid = 0;
+            const uint8_t *src = seq;
+            if (c >= 0 && chunk < n_chunks) {
+                const unsigned long long base = (chunk - __ldg(&chunk0[c])) * 64ull + 16u * sub;
+                const unsigned long long o0 = __ldg(&seq_off[c]), len = __ldg(&seq_off[c + 1]) - o0;
+                if (base < len) { nvalid = (int)min(16ull, len - base); src = seq + o0 + base; }
             }
-            if (lane == 0) {
-                planes[chunk] = make_uint4(w[0][0], w[0][1], w[1][0], w[1][1]);
-                inv[chunk] = (unsigned long long)w[0][2] | ((unsigned long long)w[1][2] << 32);
+            unsigned acc0 = 0, acc1 = 0;                       // letters 0..7 and 8..15: three 8-bit fields each
+            if (nvalid > 0) {
+                const uint8_t *a0 = (const uint8_t *)((unsigned long long)src & ~15ull);
+                const unsigned k = (unsigned)((unsigned long long)src & 15ull);
+                const uint4 A = ldg_nc_128(a0);
+                // the second half is wanted only when the letters start inside the first one (and the last
+                // contig may end in the buffer's last 16 bytes)
+                const uint4 B = k ? ldg_nc_128(a0 + 16) : make_uint4(0, 0, 0, 0);
+                unsigned w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z, w7 = B.w;
+                if (k & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
+                if (k & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+                const unsigned sh = (k & 3u) * 8u;
+                const unsigned v[4] = {__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh),
+                                       __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh)};
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    acc0 += lut[(v[b >> 2] >> (8 * (b & 3))) & 255u] << b;
+                    acc1 += lut[(v[2 + (b >> 2)] >> (8 * (b & 3))) & 255u] << b;
+                }
             }
-            if (w[0][2] | w[1][2]) summary |= 1u << i;
+            // positions past the contig's end: code 0, marked invalid
+            const unsigned keep = (1u << nvalid) - 1u;              // nvalid <= 16
+            const unsigned lo16 = ((acc0 & 0xffu) | ((acc1 & 0xffu) << 8)) & keep;
+            const unsigned hi16 = (((acc0 >> 8) & 0xffu) | (acc1 & 0xff00u)) & keep;
+            const unsigned bad16 = ((((acc0 >> 16) & 0xffu) | ((acc1 >> 8) & 0xff00u)) & keep) | (~keep & 0xffffu);
+            // four lanes -> one record {lo0, hi0, lo1, hi1} and one validity word
+            const unsigned lh = lo16 | (hi16 << 16);
+            const unsigned lh1 = __shfl_down_sync(0xffffffffu, lh, 1);
+            const unsigned bd1 = __shfl_down_sync(0xffffffffu, bad16, 1);
+            const unsigned lo32 = (lh & 0xffffu) | (lh1 << 16);
+            const unsigned hi32 = (lh >> 16) | (lh1 & 0xffff0000u);
+            const unsigned bad32 = bad16 | (bd1 << 16);
+            const unsigned lo32b = __shfl_down_sync(0xffffffffu, lo32, 2);
+            const unsigned hi32b = __shfl_down_sync(0xffffffffu, hi32, 2);
+            const unsigned bad32b = __shfl_down_sync(0xffffffffu, bad32, 2);
+            const bool any_bad = (bad32 | bad32b) != 0u;
+            if (sub == 0 && chunk < n_chunks) {
+                planes[chunk] = make_uint4(lo32, hi32, lo32b, hi32b);
+                inv[chunk] = (unsigned long long)bad32 | ((unsigned long long)bad32b << 32);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, sub == 0 && any_bad && chunk < n_chunks);   // bits 0, 4, .., 28
+            // one bit per chunk: gather every fourth bit
+            unsigned byte = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) byte |= ((m >> (4 * q)) & 1u) << q;
+            summary |= byte << (8 * it);
         }
         if (lane == 0) invsum[g] = summary;
     }
@@ -72,14 +117,13 @@ pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restric
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,
                     const unsigned long long *d_chunk0, int n_contigs)
 {
-    const int threads = 256;
     const unsigned long long groups = (h->n_chunks + 31) / 32;
-    unsigned long long blocks = (groups * 32 + threads - 1) / threads;
-    const unsigned long long cap = (unsigned long long)h->sm_count * 16;
+    unsigned long long blocks = (groups * 32 + PACK_THREADS - 1) / PACK_THREADS;
+    const unsigned long long cap = (unsigned long long)h->sm_count * 8;          // 8 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    pack_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(d_seq, d_seq_off, d_chunk0, n_contigs,
-                                                            h->n_chunks, h->d_planes, h->d_inv, h->d_invsum);
+    pack_kernel<<<(unsigned)blocks, PACK_THREADS, 0, h->stream>>>(d_seq, d_seq_off, d_chunk0, n_contigs,
+                                                                  h->n_chunks, h->d_planes, h->d_inv, h->d_invsum);
     h->timing.total_launches++;
     IGD_CUDA(cudaGetLastError());
     return IGD_OK;

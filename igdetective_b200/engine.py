@@ -256,6 +256,41 @@ class Engine:
         self.d2h_bytes += 16 * W + 16 * W
         return res
 
+    def detect(self, spacers, v_genes, j_genes, scoring=None, gene_length=(350, 70), d_gene_length=150,
+               pi_strict=(70, 70), pi_relax=(60, 65), maxk_cutoff=(15, 11)):
+        """The whole de-novo stage on the loaded contigs in one call (igd_detect): scan, D pairing, fragment gather on
+        the device, scoring of every V / J candidate against every gene in both orientations, argmax, threshold and the
+        winners' detail pass.  v_genes / j_genes: list[str] (or (buffer, offsets)).  Returns {"hits": HIT_DTYPE array,
+        "vj": VJ_ROW_DTYPE array (V rows, then J rows), "d": D_ROW_DTYPE array}, rows in the reference's order for
+        ascending RSS lists."""
+        sp = np.asarray([spacers[n] for n in SIGNAL_NAMES] if isinstance(spacers, dict) else spacers, np.int32)
+        vb, vo = v_genes if isinstance(v_genes, tuple) else concat(v_genes)
+        jb, jo = j_genes if isinstance(j_genes, tuple) else concat(j_genes)
+        vb, jb = np.ascontiguousarray(vb, np.uint8), np.ascontiguousarray(jb, np.uint8)
+        vo, jo = np.ascontiguousarray(vo, np.int32), np.ascontiguousarray(jo, np.int32)
+        sc = _lib.Scoring(**(scoring or REFERENCE_SCORING))
+        prm = _lib.DetectParams((ctypes.c_int32 * 2)(*gene_length), int(d_gene_length), (ctypes.c_double * 2)(*pi_strict),
+                                (ctypes.c_double * 2)(*pi_relax), (ctypes.c_int32 * 2)(*maxk_cutoff))
+        nh, nvj, nd = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        _lib.check(self._lib.igd_detect(self._h, sp.ctypes.data, vb.ctypes.data if vb.size else None, vo.ctypes.data, len(vo) - 1,
+                                        jb.ctypes.data if jb.size else None, jo.ctypes.data, len(jo) - 1,
+                                        ctypes.byref(sc), ctypes.byref(prm), ctypes.byref(nh), ctypes.byref(nvj), ctypes.byref(nd)))
+        hits = np.zeros(nh.value, _lib.HIT_DTYPE)
+        _lib.check(self._lib.igd_fetch_hits(self._h, hits.ctypes.data, nh.value))
+        vj = np.zeros(nvj.value, _lib.VJ_ROW_DTYPE)
+        _lib.check(self._lib.igd_fetch_vj_rows(self._h, vj.ctypes.data, nvj.value))
+        d = np.zeros(nd.value, _lib.D_ROW_DTYPE)
+        _lib.check(self._lib.igd_fetch_d_rows(self._h, d.ctypes.data, nd.value))
+        t = self.timing()
+        self.align_ms_total += t["align_ms"]
+        self.align_cells_total += t["align_cells"]
+        # over the bus: gene tables in; one 64-bit key per hit, 16 bytes per scored fragment (<= hits) and the
+        # winners' words out -- the device never sends letters back
+        n_cand = int(np.count_nonzero((hits["sig_type"] == _lib.SIG_V) | (hits["sig_type"] == _lib.SIG_J)))
+        self.h2d_bytes += vb.nbytes + vo.nbytes + jb.nbytes + jo.nbytes + 24 * n_cand + 12 * int(nvj.value)
+        self.d2h_bytes += 8 + 8 * int(nh.value) + 16 * n_cand + 8 * int(nvj.value)
+        return {"hits": hits, "vj": vj, "d": d}
+
     def sync(self):
         _lib.check(self._lib.igd_sync(self._h))
 

@@ -126,9 +126,159 @@ def vj_gene_rows(engine, parent_seq, gene, rss_idx, fragments, canonical):
     return rows
 
 
-def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False, load=True):
+class RssInfo(dict):
+    """input_rss_info of the reference ({signal type or 'D': {strand: {contig: [tuples]}}}), built from the scan's hit
+    list the first time an entry is asked for: a whole-genome run that only writes the gene tables never pays for
+    Python lists of every RSS."""
+
+    def __init__(self, scan, input_seq_dict):
+        super().__init__()
+        self._scan, self._seqs = scan, input_seq_dict
+
+    def __missing__(self, st):
+        if st == D:
+            v = {sd: combine_D_RSS(self[DL][sd], self[DR][sd], self._seqs, sd, sparse=self._scan.sparse) for sd in (FWD, REV)}
+        elif st in SIGNAL_TYPES:
+            v = {sd: self._scan.contigwise(st, sd) for sd in (FWD, REV)}
+        else:
+            raise KeyError(st)
+        self[st] = v
+        return v
+
+    def __iter__(self):
+        return iter(SIGNAL_TYPES + [D])
+
+    def keys(self):
+        return SIGNAL_TYPES + [D]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
+
+
+def _rows_from_device(res, ids, parent_seq, canonical_genes, scan, order):
+    """Strings of genes_{V,D,J}.tsv for the integer rows of igd_detect (py/IGDetective.py:364-420); with
+    order="reference" the rows of every (strand, contig) are put into the reference's RSS list order."""
+    vj, dr = res["vj"], res["d"]
+    gene_ids = {0: list(canonical_genes[V].keys()), 1: list(canonical_genes[J].keys())}
+    gene_len = {0: [len(s) for s in canonical_genes[V].values()], 1: [len(s) for s in canonical_genes[J].values()]}
+    rows = {V: [], J: [], D: []}
+    keys = {V: [], J: [], D: []}
+    ranks = {}
+
+    def rank(sig_type, strand, ci):
+        k = (sig_type, strand, ci)
+        if k not in ranks:
+            from .order import rank_map
+            ranks[k] = rank_map(scan._first_set(sig_type, strand, ci))
+        return ranks[k]
+
+    def scan_index(sig_type, strand, ci, first_pos):
+        k = 7 if sig_type in (V, DR) else 9
+        return first_pos if strand == FWD else scan.lens[ci] - first_pos - k
+
+    # group sizes, to ask for a rank map only where the order is not trivial
+    want_order = order == "reference"
+    for r in vj.tolist():
+        hept, nona, fstart, ci, flen, best, matches, alen, start, ient, gt, sd, direction, _ = r
+        gene, strand, contig = (V, J)[gt], (FWD, REV)[sd], ids[ci]
+        s = parent_seq[contig]
+        if flen > 0:
+            frag = s[fstart:fstart + flen]
+            if strand == REV:
+                frag = reverse_complement(frag)
+            frag = frag.upper()
+            if chr(direction) == "-":
+                frag = reverse_complement(frag)
+            end = start + alen
+            query = frag[start:ient]
+        else:                                   # the reference's empty slice: ComputeAlignment('', gene) at :388
+            end, query = gene_len[gt][best], ""
+        if strand == FWD:
+            if gene == V:
+                ge = hept - 1
+                gs = hept - GENE_LENGTH[gene] + start
+            else:
+                gs = hept + 7
+                ge = gs + end
+        else:
+            if gene == V:
+                gs = hept + 7
+                ge = gs + GENE_LENGTH[gene] - start - 1
+            else:
+                ge = hept - 1
+                gs = hept - end
+        pi = (matches - 1) / alen * 100
+        rows[gene].append([contig, strand, hept, nona, _kmer(s, hept, 7, strand), _kmer(s, nona, 9, strand),
+                           gs, ge, gene_ids[gt][best], chr(direction), int(round(pi)), float(alen), query])
+        keys[gene].append((sd, ci, hept if gene == V else nona))
+    for r in dr.tolist():
+        dlh, dln, drh, drn, ci, sd, _ = r
+        strand, contig = (FWD, REV)[sd], ids[ci]
+        s = parent_seq[contig]
+        lh, ln = _kmer(s, dlh, 7, strand), _kmer(s, dln, 9, strand)
+        rh, rn = _kmer(s, drh, 7, strand), _kmer(s, drn, 9, strand)
+        if strand == FWD:
+            gs, ge, seq = dlh + 7, drh - 1, s[dlh + 7:drh].upper()
+        else:
+            gs, ge, seq = drh + 7, dlh - 1, reverse_complement(s[drh + 7:dlh]).upper()
+        rows[D].append([contig, strand, dlh, dln, lh, ln, drh, drn, rh, rn, gs, ge, seq])
+        keys[D].append((sd, ci, drh, dln))
+    if want_order:
+        import collections
+        for gene in (V, J):
+            n = collections.Counter((k[0], k[1]) for k in keys[gene])
+            def key(i, gene=gene):
+                sd, ci, first = keys[gene][i]
+                if n[(sd, ci)] == 1:
+                    return (sd, ci, 0)
+                strand = (FWD, REV)[sd]
+                return (sd, ci, rank(gene, strand, ci)[scan_index(gene, strand, ci, first)])
+            idx = sorted(range(len(rows[gene])), key=key)
+            rows[gene] = [rows[gene][i] for i in idx]
+        n = collections.Counter((k[0], k[1]) for k in keys[D])
+        def dkey(i):
+            sd, ci, drh, dln = keys[D][i]
+            if n[(sd, ci)] == 1:
+                return (sd, ci, 0, 0)
+            strand = (FWD, REV)[sd]
+            return (sd, ci, rank(DR, strand, ci)[scan_index(DR, strand, ci, drh)],
+                    rank(DL, strand, ci)[scan_index(DL, strand, ci, dln)])
+        idx = sorted(range(len(rows[D])), key=dkey)
+        rows[D] = [rows[D][i] for i in idx]
+    return rows
+
+
+def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False, load=True, by_seams=False):
     """The module body of py/IGDetective.py:439-487 as a function.
-    Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only."""
+    Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only.
+    One C call (igd_detect) goes from the resident contigs to the integer fields of the rows; Python only builds the
+    strings of emitted rows.  by_seams=True runs the same stage function by function through the reference's seams
+    (get_contigwise_rss, combine_D_RSS, get_s_fragment_from_RSS, align_fragment_to_genes, ComputeAlignment) -- the
+    path the seam-level parity tests exercise, and the one taken for gene tables the packed kernels cannot hold
+    (a gene longer than 511 letters)."""
+    if not rss_only and not by_seams:
+        from ._lib import IGD_ERR_UNSUPPORTED, IgdError
+        from .rss import SPACER_LENGTH
+        if order not in ("reference", "canonical"):
+            raise ValueError("order must be 'reference' or 'canonical'")
+        ids = list(input_seq_dict.keys())
+        if load:
+            if hasattr(input_seq_dict, "_f"):
+                engine.load_fasta(input_seq_dict)
+            else:
+                engine.load_contigs([str(input_seq_dict[c]) for c in ids], ids)
+        try:
+            res = engine.detect(SPACER_LENGTH, list(canonical_genes[V].values()), list(canonical_genes[J].values()),
+                                gene_length=(GENE_LENGTH[V], GENE_LENGTH[J]), d_gene_length=GENE_LENGTH[D],
+                                pi_strict=(PI_CUTOFF["strict"][V], PI_CUTOFF["strict"][J]),
+                                pi_relax=(PI_CUTOFF["relax"][V], PI_CUTOFF["relax"][J]),
+                                maxk_cutoff=(MAXK_CUTOFF[V], MAXK_CUTOFF[J]))
+        except IgdError as e:
+            if e.code != IGD_ERR_UNSUPPORTED:
+                raise
+            return detect(engine, input_seq_dict, canonical_genes, order, rss_only, load=False, by_seams=True)
+        scan = RssScan(engine, input_seq_dict, order=order, load=False, hits=res["hits"])
+        return RssInfo(scan, input_seq_dict), _rows_from_device(res, ids, input_seq_dict, canonical_genes, scan, order)
     scan = RssScan(engine, input_seq_dict, order=order, load=load)
     info = {st: {sd: scan.contigwise(st, sd) for sd in (FWD, REV)} for st in SIGNAL_TYPES}
     sparse = scan.sparse

@@ -32,7 +32,7 @@ def _empty_map(keys, sparse):
 class RssScan:
     """Result of one scan of `parent_seq` ({contig id: str}) on an Engine."""
 
-    def __init__(self, engine, parent_seq, spacers=None, order="reference", load=True):
+    def __init__(self, engine, parent_seq, spacers=None, order="reference", load=True, hits=None):
         if order not in ("reference", "canonical"):
             raise ValueError("order must be 'reference' or 'canonical'")
         self.engine = engine
@@ -47,7 +47,8 @@ class RssScan:
                 engine.load_fasta(parent_seq)
             else:
                 engine.load_contigs([str(parent_seq[c]) for c in self.ids], self.ids)
-        self.hits = engine.scan_rss(self.spacers)
+        # hits: the hit list of a scan already run on these contigs (Engine.detect), not to scan twice
+        self.hits = engine.scan_rss(self.spacers) if hits is None else hits
         self._kmers = {}
         self._cache = {}
 

@@ -215,6 +215,64 @@ int igd_score_windows(igd_handle *h,
                       const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
                       const igd_scoring *sc, int32_t *best, double *pi, int32_t *start, int32_t *end, int32_t *ient);
 
+/* ---- the whole de-novo stage in one call ------------------------------------------------------ */
+
+/* Module constants of py/IGDetective.py:29-32 that the stage reads (index 0 = V, 1 = J). */
+typedef struct {
+    int32_t gene_length[2];     /* GENE_LENGTH[V], [J]: 350, 70  -- letters cut next to the heptamer (:260-300) */
+    int32_t d_gene_length;      /* GENE_LENGTH[D]: 150           -- combine_D_RSS window (:210-224) */
+    double  pi_strict[2];       /* PI_CUTOFF['strict']: 70, 70   (:31, :387) */
+    double  pi_relax[2];        /* PI_CUTOFF['relax']:  60, 65 */
+    int32_t maxk_cutoff[2];     /* MAXK_CUTOFF: 15, 11           (:32) */
+} igd_detect_params;
+
+/* One row of genes_V.tsv / genes_J.tsv in integer form: an RSS whose best-scoring gene passed the cut-off
+ * (py/IGDetective.py:463-477 argmax, :380-420 extract_genes).  The strings of the row are slices of the
+ * caller's own contig letters. */
+typedef struct {
+    int64_t  hept, nona;        /* the RSS, forward-strand contig coordinates (columns 3, 4) */
+    int64_t  frag_start;        /* first contig letter of the extracted fragment (forward coordinates) */
+    uint32_t contig;
+    int32_t  frag_len;          /* letters extracted; 0 = the reference's empty slice ('A' * len(gene) was scored) */
+    int32_t  best_gene;         /* index of the first maximal PI in the gene table (np.argmax, :473) */
+    int32_t  matches;           /* TRUE match count of the kept orientation; PI = (matches - 1) / alen * 100 */
+    int32_t  alen;              /* len(BioAlign): 'longest common k-mer' column as float */
+    int32_t  start;             /* AlignmentRange()[0] */
+    int32_t  ient;              /* QuerySeq() == upper(kept orientation of the fragment)[start:ient] */
+    uint8_t  gene_type;         /* 0 = V, 1 = J */
+    uint8_t  strand;            /* IGD_STRAND_* of the RSS */
+    uint8_t  direction;         /* '+' : the fragment as extracted aligned better, '-' : its reverse complement (:314-317) */
+    uint8_t  reserved;
+} igd_vj_row;
+
+/* One row of genes_D.tsv: a (D_left, D_right) RSS pair of combine_D_RSS (py/IGDetective.py:210-224). */
+typedef struct {
+    int64_t  dl_hept, dl_nona, dr_hept, dr_nona;
+    uint32_t contig;
+    uint8_t  strand;
+    uint8_t  reserved[3];
+} igd_d_row;
+
+/* The module body of py/IGDetective.py:439-487 on the contigs loaded in the handle, in ONE call:
+ *   get_contigwise_rss x 8 (:443)            -> the RSS scan kernel (as igd_scan; the hits stay fetchable)
+ *   combine_D_RSS (:444-446)                 -> sorted search over the hit list (host, O(n log n))
+ *   get_s_fragment_from_RSS (:455)           -> a gather kernel over the resident contig letters: Python slice
+ *                                               semantics incl. the negative-start quirk (:265), upper-cased,
+ *                                               reverse-complemented for strand '-' (Bio.Seq's IUPAC table)
+ *   align_fragment_to_genes (:467)           -> packed Gotoh kernels, both orientations, orientation choice and
+ *                                               first-maximum argmax (:473) on the device
+ *   threshold (:387), ComputeAlignment (:388) of the winners -> two-register Gotoh kernel for start / ient
+ * Rows come back in the reference's order for ascending RSS lists: V rows then J rows, each strand '+' then
+ * '-', contigs in load order, RSS list order; D rows strand '+' then '-', contigs in order, D_right outer /
+ * D_left inner.  Needs igd_load_contigs / igd_load_fasta (the ASCII letters stay resident) and igd_set_motifs. */
+int igd_detect(igd_handle *h, const int32_t spacer[4],
+               const uint8_t *vgene, const int32_t *vgene_off, int32_t n_vgene,
+               const uint8_t *jgene, const int32_t *jgene_off, int32_t n_jgene,
+               const igd_scoring *sc, const igd_detect_params *prm,
+               uint64_t *n_hits, uint64_t *n_vj_rows, uint64_t *n_d_rows);
+int igd_fetch_vj_rows(igd_handle *h, igd_vj_row *out, uint64_t capacity);
+int igd_fetch_d_rows(igd_handle *h, igd_d_row *out, uint64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

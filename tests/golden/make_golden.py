@@ -29,6 +29,29 @@ STUBS = os.path.join(ROOT, "oracle", "stubs")
 EXAMPLES = {"human": "human.fa", "mouse": "mouse.fa", "cow": "cow.fasta"}
 
 
+def real_biopython():
+    """Version string of a real BioPython >= 1.82 importable WITHOUT the shim on the path, else None."""
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, "-c", "import Bio; from Bio import Align, SeqIO; from Bio.Seq import Seq; print(Bio.__version__)"],
+                       capture_output=True, text=True, env=env)
+    if r.returncode != 0:
+        return None
+    v = r.stdout.strip()
+    try:
+        major, minor = (int(x) for x in v.split(".")[:2])
+    except ValueError:
+        return None
+    return v if (major, minor) >= (1, 82) else None
+
+
+# The moment a real BioPython is importable the reference scripts run on IT, not on oracle/bio_shim: the
+# goldens are then BioPython's own output and every oracle / GPU parity test is pinned to the real library
+# (tests/test_oracle_golden.py fails loudly on any difference).  tests/golden/BIOPYTHON records which it was.
+REAL_BIO = real_biopython()
+if REAL_BIO:
+    SHIM = ""
+
+
 def read_fasta(path):
     recs, title, chunks = [], None, []
     for line in open(path):
@@ -171,7 +194,8 @@ def make_scoring_b_multi():
     """scoring B on the multi-contig input against the short, lower-case IGHJ gene file: positions on
     several contigs (one all lower-case), near contig ends, on contigs shorter than the window"""
     import csv
-    sys.path.insert(0, SHIM)
+    if SHIM:
+        sys.path.insert(0, SHIM)
     sys.path.insert(0, os.path.join(REF, "py"))
     os.environ["PATH"] = STUBS + os.pathsep + os.environ["PATH"]
     import extract_aligned_genes as ref_mod
@@ -198,7 +222,8 @@ def make_scoring_b_multi():
 
 
 def make_scoring_b():
-    sys.path.insert(0, SHIM)
+    if SHIM:
+        sys.path.insert(0, SHIM)
     sys.path.insert(0, os.path.join(REF, "py"))
     os.environ["PATH"] = STUBS + os.pathsep + os.environ["PATH"]
     import extract_aligned_genes as ref_mod
@@ -221,12 +246,127 @@ def make_scoring_b():
                 print("  wrote", os.path.relpath(os.path.join(out, fn), ROOT))
 
 
+
+# ---- table level: the whole pipeline driver ----------------------------------------------------------
+PYLIBS = os.path.join(STUBS, "pylibs")
+DRIVER_KEEP = ("combined_genes_", "denovo_search/predicted_genes_", "iterative_search/")
+
+
+def make_driver_input():
+    """tri_locus: a real IGH locus slice (V, D and J genes of human.fa) plus two synthetic contigs with
+    mutated IGK / IGL V and J genes and their RSSs planted on both strands, partly soft-masked; one id
+    carries a '|' (the driver rewrites it to '_', run_iterative_igdetective.py:203,214)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import synth
+    motifs = pickle.load(open(os.path.join(REF, "datafiles", "motifs"), "rb"))
+    human = read_fasta(os.path.join(REF, "examples", "igh_locus_examples", EXAMPLES["human"]))[0][1]
+    recs = [("chr14_igh_slice", human[850000:1030000])]
+    for seed, locus, cid in ((31, "IGK", "ctgK|synthetic"), (32, "IGL", "ctgL")):
+        gv = dict(read_fasta(os.path.join(REF, "datafiles", "combined_reference_genes", locus + "V.fa")))
+        gj = dict(read_fasta(os.path.join(REF, "datafiles", "combined_reference_genes", locus + "J.fa")))
+        gv = {k.split()[0]: v.upper() for k, v in gv.items()}
+        gj = {k.split()[0]: v.upper() for k, v in gj.items()}
+        contigs, _ = synth.assembly(seed, [60000], motifs, gv, gj, plant_every=0, n_runs=1, soft_mask=0.3,
+                                    clusters=[(0, 5, 0, 2)])
+        recs.append((cid, contigs[0].tobytes().decode()))
+    path = os.path.join(HERE, "inputs", "tri_locus.fa.gz")
+    write_fasta_gz(path, recs)
+    return path
+
+
+def _tree(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for fn in files:
+            p = os.path.join(d, fn)
+            out[os.path.relpath(p, root)] = p
+    return out
+
+
+def make_driver(jobs):
+    """combined_genes_<LOCUS>.txt and every intermediate table written by the UNMODIFIED
+    /root/reference/run_iterative_igdetective.py on tri_locus (Bio shim, stub minimap2, no-op plotting
+    modules), then the restated driver (oracle/ref_driver.py) over the same reference scripts, which
+    must write the same bytes -- that is what pins the restatement the GPU-side test drives."""
+    src = make_driver_input()
+    out = os.path.join(HERE, "driver", "tri_locus")
+    shutil.rmtree(out, ignore_errors=True)
+    os.makedirs(out)
+    env = dict(os.environ, PYTHONPATH=SHIM + os.pathsep + PYLIBS, PYTHONHASHSEED="0",
+               PATH=STUBS + os.pathsep + os.environ["PATH"])
+    env.pop("IGD_STUB_SAM", None)
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("run_iterative_igdetective.py", "py", "datafiles"):
+            os.symlink(os.path.join(REF, name), os.path.join(tmp, name))
+        genome = os.path.join(tmp, "tri_locus.fa")
+        with open(genome, "wb") as f:
+            f.write(gzip.open(src).read())
+        subprocess.run([sys.executable, "run_iterative_igdetective.py", genome, os.path.join(tmp, "out")],
+                       cwd=tmp, env=env, check=True, stdout=open(os.path.join(tmp, "driver.log"), "w"))
+        ref_out = os.path.join(tmp, "out")
+        # the driver deletes ig_contigs/*.fasta at its end (CleanLargeContigs, :195-198): re-run the prefilter's
+        # analysis step on the alignments it left behind to get the directory back as RunIgDetective saw it
+        subprocess.run([sys.executable, "py/analyze_matches.py", os.path.join(ref_out, "initial_alignments"),
+                        os.path.join(tmp, "ig_contigs"), genome], cwd=tmp, env=env, check=True, stdout=subprocess.DEVNULL)
+        assert open(os.path.join(tmp, "ig_contigs", "__summary.txt")).read() == \
+            open(os.path.join(ref_out, "ig_contigs", "__summary.txt")).read()
+        # the restated driver over the same reference scripts
+        subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), genome, os.path.join(tmp, "ig_contigs"),
+                        os.path.join(tmp, "out2"), "datafiles/combined_reference_genes"], cwd=tmp, env=env, check=True,
+                       stdout=subprocess.DEVNULL)
+        a, b = _tree(ref_out), _tree(os.path.join(tmp, "out2"))
+        checked = 0
+        for rel in sorted(a):
+            if not rel.startswith(DRIVER_KEEP) or rel.endswith((".sam", ".out")):
+                continue
+            assert rel in b, "restated driver did not write " + rel
+            assert open(a[rel], "rb").read() == open(b[rel], "rb").read(), "restated driver differs in " + rel
+            checked += 1
+        print("  restated driver == unmodified driver on %d files" % checked)
+        # what the GPU-side test needs: the prefilter's summary + which FASTA files it wrote, and the tables
+        os.makedirs(os.path.join(out, "ig_contigs"))
+        shutil.copyfile(os.path.join(tmp, "ig_contigs", "__summary.txt"), os.path.join(out, "ig_contigs", "__summary.txt"))
+        with open(os.path.join(out, "ig_contigs", "manifest.tsv"), "w") as mf:
+            for fn in sorted(os.listdir(os.path.join(tmp, "ig_contigs"))):
+                if fn.endswith(".fasta"):
+                    recs = read_fasta(os.path.join(tmp, "ig_contigs", fn))
+                    for title, s in recs:
+                        mf.write("%s\t%s\t%d\n" % (fn, title, len(s)))
+        for rel in sorted(a):
+            keep = rel.startswith(DRIVER_KEEP) and rel.endswith((".txt", ".tsv", "_combined.fasta", "genes.fasta"))
+            if rel.startswith("denovo_search/combined_contigs_"):
+                keep = True
+            if "_final/" in rel:
+                keep = False                       # a copy of the best iteration
+            if not keep:
+                continue
+            dst = os.path.join(out, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            if rel.startswith("denovo_search/combined_contigs_"):      # headers only: the letters are slices of the input
+                with open(dst + ".headers", "w") as f:
+                    f.writelines(">%s\t%d\n" % (t, len(s)) for t, s in read_fasta(a[rel]))
+            else:
+                shutil.copyfile(a[rel], dst)
+            print("  wrote", os.path.relpath(dst, ROOT))
+        with open(os.path.join(out, "final_iterations.txt"), "w") as f:
+            for rel in sorted(a):
+                if "_final/genes.tsv" in rel:
+                    gene = rel.split("/")[1][:-len("_final")]
+                    want = open(a[rel], "rb").read()
+                    its = [r for r in sorted(a) if r.startswith("iterative_search/%s_iter" % gene) and r.endswith("genes.tsv")
+                           and open(a[r], "rb").read() == want]
+                    f.write("%s\t%s\n" % (gene, ",".join(i.split("/")[1] for i in its)))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
     ap.add_argument("--jobs", type=int, default=len(os.sched_getaffinity(0)))
     a = ap.parse_args()
     subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True)
+    print("BioPython:", "real " + REAL_BIO if REAL_BIO else "oracle/bio_shim (real BioPython not importable)")
+    with open(os.path.join(HERE, "BIOPYTHON"), "w") as f:
+        f.write(("real %s\n" % REAL_BIO) if REAL_BIO else "shim (oracle/bio_shim over oracle/gotoh_ref.c; BioPython not importable here)\n")
     if a.only in ("", "data"):
         make_data()
     if a.only in ("", "igdetective"):
@@ -234,3 +374,5 @@ if __name__ == "__main__":
     if a.only in ("", "scoring_b"):
         make_scoring_b()
         make_scoring_b_multi()
+    if a.only in ("", "driver"):
+        make_driver(a.jobs)

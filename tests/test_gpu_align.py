@@ -244,3 +244,52 @@ def test_align_lower_case_on_either_side(engine):
         got = engine.align_dense(targets, queries)
         assert np.array_equal(got["matches"].ravel(), want["matches"])
         assert np.array_equal(got["alen"].ravel(), want["end"] - want["start"])
+
+
+def test_compute_alignment_seam_has_the_reference_signature(engine):
+    """extract_aligned_genes.ComputeAlignment(aligner, query_list, strand_list, gene_seqs) -> (Alignment, strand),
+    py/extract_aligned_genes.py:85-105, called the way main() calls it (:153-154,165-166): an aligner object set
+    up by SetupAligner, [window, RC(window)], ['+', '-'], gene records with .seq / .id"""
+    import collections
+
+    from igdetective_b200 import extract_aligned_genes as X
+    Rec = collections.namedtuple("Rec", "id seq")
+    rng = np.random.default_rng(66)
+    gl = list(canonical("combined_reference_genes")["V"].items())[40:60]
+    genes = [(k, v.upper()) for k, v in gl] + [("dup", gl[5][1].upper())]
+    recs = [Rec(k, v) for k, v in genes]
+    aligner = X.GpuAligner(engine)
+    X.SetupAligner(aligner)
+    assert X.scoring_of(aligner) == dict(match=2, mismatch=0, target_internal_open=-2, target_internal_extend=-1,
+                                         target_end_open=-2, target_end_extend=-1, query_internal_open=-2,
+                                         query_internal_extend=-1, query_end_open=0, query_end_extend=0)
+    wins = []
+    for i in range(6):
+        g = genes[int(rng.integers(len(genes)))][1]
+        w = (rand_seq(rng, 200) + synth.mutate(rng, g, 0.08, 0.01) + rand_seq(rng, 400))[:800]
+        if i % 2:
+            w = w[:100] + w[100:500].lower() + w[500:]
+        wins.append(O.revcomp(w) if i % 3 == 0 else w)
+    wins += [rand_seq(rng, 30), "N" * 12]
+    for w in wins:
+        got, strand = X.ComputeAlignment(aligner, [w, O.revcomp(w)], ['+', '-'], recs)
+        want = O.window_best_alignment(w, genes, threads=4)
+        if want is None:
+            assert got.Empty() and strand == ''
+        else:
+            assert (got.gene_seq, got.gene_id, got.pi, strand) == want
+    # another scheme through the same seam: plain attribute assignment like a PairwiseAligner
+    aligner.mismatch_score = -1
+    aligner.query_internal_open_gap_score = -3
+    got, strand = X.ComputeAlignment(aligner, [wins[1]], ['+'], recs[:5])
+    sc = dict(O.REFERENCE_SCORING, mismatch=-1, q_int_open=-3)
+    st = O.align_stats([wins[1]], [g[1] for g in genes[:5]], [0] * 5, list(range(5)), scoring=sc)
+    best_pi, best = 0, None
+    for k in range(5):
+        pi = (int(st[k]["matches"]) - 1) / (int(st[k]["end"]) - int(st[k]["start"])) * 100
+        if pi >= best_pi:
+            best_pi, best = pi, k
+    assert best is not None and strand == '+'
+    assert (got.gene_id, got.pi) == (genes[best][0], best_pi)
+    assert got.gene_seq == wins[1][int(st[best]["lead"]):int(st[best]["ient"])].upper()
+    assert X.ComputeAlignment(aligner, [], [], recs)[1] == ''

@@ -127,3 +127,44 @@ def test_two_rank_window_scoring_equals_single_process(monkeypatch):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert got[0] == single and got[1] == single
+
+
+def test_window_waves_score_exactly_what_the_reference_would_align(monkeypatch):
+    """find_genes scores positions in waves; the rows must equal the reference's sequential loop
+    (py/extract_aligned_genes.py:158-184: a position is aligned iff it lies more than 400 behind the last position
+    that PRODUCED a gene) and the positions within 400 of an accepted one never reach the scorer."""
+    scored = []
+
+    def scorer(engine, windows, genes):
+        scored.extend(windows)
+        return _fake_window_alignments(engine, windows, genes)
+    monkeypatch.setattr(X, "window_alignments", scorer)
+    rng = np.random.default_rng(9)
+    positions = {"a": sorted(set(int(p) for p in rng.integers(1, 29_000, 160))), "b": [10, 450, 880],
+                 "c": sorted(set(int(p) for p in rng.integers(1, 11_900, 60)))}
+    got = X.find_genes(None, CONTIGS, positions, GENES, batch=7)
+    # the reference's loop with the same scorer, one window at a time
+    want = {k: [] for k in X.TSV_COLUMNS}
+    aligned = []
+    for cid in positions:
+        prev = -1
+        for pos in sorted(positions[cid]):
+            if pos - prev <= 400:
+                continue
+            w = CONTIGS[cid][max(0, pos - 400):min(len(CONTIGS[cid]), pos + 400)]
+            aligned.append(w)
+            a, strand = _fake_window_alignments(None, [w], GENES)[0]
+            if a.Empty():
+                continue
+            aa = X.translate(a.gene_seq)
+            for k, v in zip(X.TSV_COLUMNS, (cid, pos, a.gene_seq, aa, a.pi, a.gene_id, '*' not in aa, strand)):
+                want[k].append(v)
+            prev = pos
+    assert got == want and len(got["Pos"]) > 10
+    # every window the reference aligns is scored; beyond those only the few a wave chose on the assumption that an
+    # earlier window would produce a gene when it then came back empty (1 in 7 with this scorer, rare in real data)
+    assert set(aligned) <= set(scored)
+    assert len(scored) <= len(aligned) + 2 * sum(1 for w in aligned if _fake_window_alignments(None, [w], GENES)[0][0].Empty())
+    assert len(scored) < sum(len(p) for p in positions.values()) / 2
+    # the reference's own position dict shape and the (contig, array) list give the same table
+    assert X.find_genes(None, CONTIGS, [(c, np.asarray(sorted(p))) for c, p in positions.items()], GENES, batch=50) == want
