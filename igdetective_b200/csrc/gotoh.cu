@@ -213,7 +213,7 @@ struct PackedParams {
 // once, the factor is a per-row constant (MIXED = 1: queries are all upper case) that a lower-case query
 // letter swaps by one more FFMA per cell (MIXED = 2).
 // resident CTAs per SM the register allocation aims for: 6 for the shapes that fit 80 registers
-constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : 1; }
+constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : (C == 22 ? 4 : 1); }
 // MIXED: 0 = no lower-case letter anywhere; 1 = only targets may hold lower-case letters; 2 = queries may too.
 template <int G, int C, int MIXED, bool LONG, bool FPINC>
 __global__ void __launch_bounds__(GT_THREADS, packed_min_blocks(C))
@@ -395,7 +395,7 @@ int launch(igd_handle *h, const GotohParams &P, int mixed)
 
 // kernel shapes: target rows = G * C
 //   0: 8 x 9   (<= 72,  J flanks of 70)      1: 32 x 6  (<= 192)
-//   2: 32 x 11 (<= 352, V flanks of 350)     3: 32 x 16 (<= 512)
+//   2: 16 x 22 (<= 352, V flanks of 350; packed kernel), 32 x 11 (two-register kernel)     3: 32 x 16 (<= 512)
 //   4: 32 x 25 (<= 800, scoring-B windows)   5: 32 x 32 (<= 1024)
 int igd_align_bucket_of(int target_len)
 {
@@ -431,7 +431,13 @@ static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
         switch (job.bucket) {
         case 0: return launch_packed<8, 9, false>(h, P, job.mixed_case);
         case 1: return launch_packed<32, 6, false>(h, P, job.mixed_case);
-        case 2: return launch_packed<32, 11, false>(h, P, job.mixed_case);
+        case 2: {
+            // 16 lanes x 22 rows: the ~29 per-column instructions (query letter, shuffles, boundary selects) are shared by
+            // 22 cells instead of 11 -- 13.3 instead of 14.6 instructions per cell, 2.04 instead of 1.90 TCUPS at 128
+            // registers / 4 CTAs per SM (8 x 44 at 255 registers / 2 CTAs: 1.96).  IGD_GOTOH_V_SHAPE=32x11 selects the old shape.
+            static const bool narrow = getenv("IGD_GOTOH_V_SHAPE") && !strcmp(getenv("IGD_GOTOH_V_SHAPE"), "32x11");
+            return narrow ? launch_packed<32, 11, false>(h, P, job.mixed_case) : launch_packed<16, 22, false>(h, P, job.mixed_case);
+        }
         case 3: return launch_packed<32, 16, false>(h, P, job.mixed_case);
         }
     } else {

@@ -47,17 +47,86 @@ def all_gather_lists(items, group=None):
     return [x for part in bucket for x in part]
 
 
+def plan_pieces(lengths, world_size, tile=32_000_000, halo=512):
+    """Units of the de-novo stage for `world_size` ranks: contigs longer than 1.5 tiles are cut into pieces of
+    about `tile` bases (the reference's own answer to long contigs is cropping,
+    run_iterative_igdetective.py:41-49), whole contigs otherwise; pieces are assigned by LPT on length.
+    A piece is (contig, own_start, own_end, load_start, load_end): the rank loads [load_start, load_end) -- the
+    owned range plus `halo` bases of context on either side -- and keeps exactly the rows whose heptamer
+    (right heptamer for a D pair) starts inside [own_start, own_end).  halo must cover what a row reads around
+    its heptamer: the 350-nt V flank + 7 (py/IGDetective.py:268-286) and a D pair's 157 + the 40-base RSS span
+    (:210-224); 512 does, so every owned row is computed from the same letters as on one GPU.
+    Returns [pieces of rank r], each list in (contig, own_start) order."""
+    if halo < 400:
+        raise ValueError("halo must be at least 400 bases (V flank 350 + heptamer 7 + RSS span 40)")
+    pieces = []
+    for ci, L in enumerate(lengths):
+        L = int(L)
+        if L <= tile + tile // 2:
+            pieces.append((ci, 0, L, 0, L))
+            continue
+        n = -(-L // tile)
+        step = -(-L // n)
+        for k in range(n):
+            a, b = k * step, min(L, (k + 1) * step)
+            pieces.append((ci, a, b, max(0, a - halo), min(L, b + halo)))
+    bins = [(0, r) for r in range(world_size)]
+    heapq.heapify(bins)
+    out = [[] for _ in range(world_size)]
+    for p in sorted(pieces, key=lambda p: (-(p[4] - p[3]), p[0], p[1])):
+        load, r = heapq.heappop(bins)
+        out[r].append(p)
+        heapq.heappush(bins, (load + p[4] - p[3], r))
+    return [sorted(x) for x in out]
+
+
+def own_rows(rows, piece, contig_id):
+    """Rows computed on a loaded piece (coordinates relative to load_start, contig id = the piece's) -> the rows
+    the piece owns, in contig coordinates.  rows: {gene type: [row]} in the layouts of genes_{V,D,J}.tsv."""
+    _, a, b, p0, _ = piece
+    out = {}
+    for g, rs in rows.items():
+        keep = []
+        if g == "D":            # [contig, strand, lh idx, ln idx, lh, ln, rh idx, rn idx, rh, rn, gs, ge, gene]
+            for r in rs:
+                if a <= r[6] + p0 < b:
+                    keep.append([contig_id, r[1], r[2] + p0, r[3] + p0, r[4], r[5], r[6] + p0, r[7] + p0, r[8], r[9],
+                                 r[10] + p0, r[11] + p0, r[12]])
+        else:                   # [contig, strand, hept idx, nona idx, hept, nona, gs, ge, ...]
+            for r in rs:
+                if a <= r[2] + p0 < b:
+                    keep.append([contig_id, r[1], r[2] + p0, r[3] + p0, r[4], r[5], r[6] + p0, r[7] + p0] + list(r[8:]))
+        out[g] = keep
+    return out
+
+
+def canonical_row_key(gene, rank_of):
+    """Sort key that puts rows of any sharding into the order a single-process canonical run emits them: strand '+'
+    before '-', contigs in input order, then the RSS list order for ascending lists -- ascending position of the list's
+    first element on '+' (heptamer for V, nonamer for J; D: right heptamer, then left nonamer), descending on '-'."""
+    if gene == "D":
+        def key(r):
+            sgn = 1 if r[1] == "+" else -1
+            return (0 if r[1] == "+" else 1, rank_of[r[0]], sgn * r[6], sgn * r[3])
+    else:
+        col = 2 if gene == "V" else 3
+
+        def key(r):
+            return (0 if r[1] == "+" else 1, rank_of[r[0]], r[col] if r[1] == "+" else -r[col])
+    return key
+
+
 def merge_rows(per_rank_rows, contig_order):
     """per_rank_rows: list over ranks of {gene type: rows}; every row starts with (contig id, strand).
-    Returns {gene type: rows} ordered as a single-process run emits them: strand '+' before '-',
-    contigs in input order, list order within a contig (stable)."""
+    Returns {gene type: rows} ordered as a single-process canonical run emits them (canonical_row_key); the
+    result does not depend on how contigs or pieces were distributed."""
     rank_of = {c: i for i, c in enumerate(contig_order)}
     out = {}
     for rows in per_rank_rows:
         for g, rs in rows.items():
             out.setdefault(g, []).extend(rs)
     for g in out:
-        out[g].sort(key=lambda r: (0 if r[1] == "+" else 1, rank_of[r[0]]))
+        out[g].sort(key=canonical_row_key(g, rank_of))
     return out
 
 

@@ -26,9 +26,10 @@ def _rows_for(contigs):
         L = LENGTHS[IDS.index(c)]
         for k in range(L % 5):
             for sd in "+-":
-                rows["V"].append([c, sd, k * 11, k * 11 + 30, "CACAGTG", "ACAAAAACC", L + k])
-        rows["D"].append([c, "+", L % 97, 0])
-        rows["J"].append([c, "-", L % 13, 1])
+                rows["V"].append([c, sd, k * 11, k * 11 + 30, "CACAGTG", "ACAAAAACC", L + k, L + k + 290, "g", "+", 99, 296.0, "ACGT"])
+        rows["D"].append([c, "+", L % 97, L % 97 - 21, "CACAGTG", "ACAAAAACC", L % 97 + 30, L % 97 + 49, "CACTGTG", "GGTTTTTGT",
+                          L % 97 + 7, L % 97 + 29, "ACGTACGT"])
+        rows["J"].append([c, "-", L % 13 + 40, L % 13, "CACAGTG", "ACAAAAACC", L % 13, L % 13 + 39, "j", "-", 98, 52.0, "ACGT"])
     return rows
 
 
@@ -64,6 +65,60 @@ def test_two_rank_gather_equals_single_process():
         assert p.exitcode == 0
     single = shard.merge_rows([_rows_for(IDS)], IDS)
     assert merged == single
+
+
+# ---- pieces: long contigs cut into tiles with context, rows owned by the tile of their heptamer --------
+def test_pieces_cover_every_base_once_and_balance():
+    lengths = [250_000_000, 40_000_000, 33_000_000, 700, 0, 120_000_000, 5_000_000]
+    for world in (1, 2, 8):
+        parts = shard.plan_pieces(lengths, world)
+        assert len(parts) == world
+        pieces = sorted(p for part in parts for p in part)
+        for ci, L in enumerate(lengths):
+            own = [(a, b) for c, a, b, _, _ in pieces if c == ci]
+            assert own[0][0] == 0 and own[-1][1] == L and all(x[1] == y[0] for x, y in zip(own, own[1:]))
+        for c, a, b, p0, p1 in pieces:
+            assert p0 == max(0, a - 512) and p1 == min(lengths[c], b + 512) and b - a <= 48_000_000
+        loads = [sum(p[4] - p[3] for p in part) for part in parts]
+        assert max(loads) <= sum(loads) / world + 48_000_000
+    with pytest.raises(ValueError):
+        shard.plan_pieces(lengths, 2, halo=64)
+
+
+def test_rows_of_pieces_equal_rows_of_the_whole_contig():
+    """ownership + coordinate translation + canonical merge, with a stand-in for the GPU stage whose rows depend
+    on the letters around a marker exactly like the real rows do (350 before / after a heptamer, D pairs within 157)"""
+    import numpy as np
+    rng = np.random.default_rng(12)
+    contig = "".join("ACGT"[i] for i in rng.integers(0, 4, 60_000))
+
+    def fake_detect(text, cid):
+        rows = {"V": [], "J": [], "D": []}
+        hs = [i for i in range(len(text) - 7) if text[i:i + 4] == "CACA"]
+        for h in hs:
+            a = h - 350
+            frag = text[a + len(text):h] if a < 0 and len(text) < 350 else ("" if a < 0 else text[a:h])
+            rows["V"].append([cid, "+", h, h + 30, text[h:h + 7], text[h + 30:h + 39], h - 350, h - 1, "g", "+", len(frag), 296.0, frag[-20:]])
+            rows["J"].append([cid, "-", h, h - 32 + (ord(text[h + 5]) % 3), text[h:h + 7], "", h - 70, h - 1, "j", "-", 0, 52.0, text[max(0, h - 70):h][:9]])
+        for r in hs:
+            for l in hs:
+                if l < r and r - (l + 7) <= 150 and (ord(text[l + 4]) + ord(text[r + 5])) % 3 == 0:
+                    rows["D"].append([cid, "+", l, l - 21 - (ord(text[l + 6]) % 2), "", "", r, r + 19, "", "", l + 7, r - 1, text[l + 7:r]])
+        return rows
+    whole = shard.merge_rows([fake_detect(contig, "c")], ["c"])
+    for tile in (7_000, 20_000):
+        parts = shard.plan_pieces([len(contig)], 3, tile=tile)
+        assert sum(len(p) for p in parts) >= 3
+        per_rank = []
+        for part in parts:
+            rows = {"V": [], "J": [], "D": []}
+            for piece in part:
+                own = shard.own_rows(fake_detect(contig[piece[3]:piece[4]], 0), piece, "c")
+                for g in rows:
+                    rows[g].extend(own[g])
+            per_rank.append(rows)
+        assert shard.merge_rows(per_rank, ["c"]) == whole
+    assert len(whole["V"]) > 100 and len(whole["D"]) > 20
 
 
 # ---- scoring shards: the iterative stage's windows split by DP cells over the ranks --------------
