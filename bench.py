@@ -47,6 +47,115 @@ def make_workload(seed, n_bases, motifs, canon):
     return contigs[0], truth
 
 
+class Assembly3:
+    """BASELINE.json configs[2]: a ~3 Gb mammalian-shaped assembly (40 SUPER_* scaffolds of 20-250 Mb summing to 2.9 Gb
+    + 460 unplaced scaffolds of 10 kb-2 Mb), i.i.d. background with P(A,C,G,T) = (0.295, 0.205, 0.205, 0.295),
+    IGH-like loci (60 V + 6 D + 3 J mutated genes with their RSSs, both strands) planted on 5 scaffolds, 3 N runs per
+    scaffold.  Every 4 Mb block of every contig depends only on (seed, contig, block), and the planted loci / N runs are
+    patches with fixed coordinates, so a rank can write just the pieces it owns -- straight into pinned memory -- and any
+    sharding sees the same genome."""
+    BLOCK = 1 << 22
+
+    def __init__(self, motifs, canon, scale=1.0, seed=3):
+        import synth
+        rng = np.random.default_rng(seed)
+        sup = np.exp(rng.uniform(np.log(20e6), np.log(250e6), 40))
+        sup = (sup / sup.sum() * 2.9e9 * scale).astype(np.int64)
+        unp = np.exp(rng.uniform(np.log(10e3), np.log(2e6), 460)).astype(np.int64)
+        self.lengths = sup.tolist() + (unp * min(1.0, scale * 4)).astype(np.int64).tolist()
+        self.ids = ["SUPER_%d" % (i + 1) for i in range(40)] + ["scaffold_%d" % i for i in range(460)]
+        self.seed = seed
+        t = np.array([0.295, 0.5, 0.705, 1.0]) * 65536
+        self.lut = np.frombuffer(b"ACGT", np.uint8)[np.searchsorted(t, np.arange(65536), side="right").clip(0, 3)]
+        self.patches = {}                                  # contig -> [(start, uint8 array)]
+        for ci in (2, 7, 11, 23, 31):
+            r = np.random.default_rng([seed, 1000 + ci])
+            L = self.lengths[ci]
+            w = min(L, 2_000_000)
+            lo = int(r.integers(0, max(1, L - w)))
+            win = synth.background(r, w)
+            synth.plant_locus(r, win, motifs, canon["V"], canon["J"], 60, 6, 3, 0, w)
+            self.patches.setdefault(ci, []).append((lo, win))
+        for ci in range(40):
+            r = np.random.default_rng([seed, 2000 + ci])
+            for _ in range(3):
+                n = int(r.integers(100, 50_000))
+                p0 = int(r.integers(0, max(1, self.lengths[ci] - n)))
+                self.patches.setdefault(ci, []).append((p0, np.full(n, ord("N"), np.uint8)))
+
+    def fill(self, ci, a, b, out):
+        """letters [a, b) of contig ci -> out[0 : b - a]"""
+        B = self.BLOCK
+        for blk in range(a // B, (b + B - 1) // B if b > a else a // B):
+            lo, hi = blk * B, min((blk + 1) * B, self.lengths[ci])
+            u = np.random.default_rng([self.seed, ci, blk]).integers(0, 65536, hi - lo, dtype=np.uint16)
+            x, y = max(a, lo), min(b, hi)
+            out[x - a:y - a] = self.lut[u[x - lo:y - lo]]
+        for p0, arr in self.patches.get(ci, ()):
+            x, y = max(a, p0), min(b, p0 + len(arr))
+            if y > x:
+                out[x - a:y - a] = arr[x - p0:y - p0]
+
+
+def strong_config3(a, eng, motifs, canon, rank, world, barrier):
+    """configs[2] strong-scaled: the 3.06 Gb assembly cut into pieces (shard.plan_pieces: contigs, scaffolds longer than
+    48 Mb in ~32 Mb tiles with 512 bases of context), pieces assigned by LPT, every rank loads (pinned ASCII -> H2D ->
+    pack), scans and scores its own pieces, rank 0 gathers the rows.  No data-path collective.  Whole-job time =
+    max over ranks of (load + detect + gather), CUDA-synchronised, between barriers."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from igdetective_b200 import multi, shard
+    from igdetective_b200.fasta import ArraySeq
+    asm = Assembly3(motifs, canon, a.strong_scale)
+    t0 = time.perf_counter()
+    pieces = shard.plan_pieces(asm.lengths, world)[rank]
+    n_mine = sum(p[4] - p[3] for p in pieces)
+    pinned = torch.empty(max(n_mine, 1), dtype=torch.uint8).pin_memory()
+    host = pinned.numpy()
+    off = np.zeros(len(pieces) + 1, np.uint64)
+    part = {}
+    for k, (ci, _, _, p0, p1) in enumerate(pieces):
+        off[k + 1] = off[k] + (p1 - p0)
+        asm.fill(ci, p0, p1, host[int(off[k]):int(off[k + 1])])
+        part[k] = ArraySeq(host[int(off[k]):int(off[k + 1])])
+    t_gen = time.perf_counter() - t0
+    shard.gather_rows({"warmup": []}, asm.ids)                 # first object collective pays communicator set-up
+    samples, merged, scan_ms = [], None, 0.0
+    for it in range(1 + a.strong_reps):
+        barrier()
+        t0 = time.perf_counter()
+        eng.load_contigs((pinned.data_ptr(), off), list(part))
+        t1 = time.perf_counter()
+        rows = multi.detect_pieces(eng, None, asm.ids, pieces, canon, "canonical", part=part)
+        eng.sync()
+        t2 = time.perf_counter()
+        merged = shard.gather_rows(rows, asm.ids)
+        t3 = time.perf_counter()
+        v = [t3 - t0, t1 - t0, t2 - t1, t3 - t2, eng.timing()["scan_ms"], eng.timing()["pack_ms"]]
+        if world > 1:
+            t = torch.tensor(v, dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            v = t.tolist()
+        if it > 0:
+            samples.append(v)
+    if rank != 0:
+        return None
+    med = np.median(np.array(samples), axis=0).tolist()
+    text = "".join("\t".join(map(str, r)) + "\n" for g in ("V", "D", "J") for r in merged[g])
+    bases = int(sum(asm.lengths))
+    return {"workload": "configs[2]: synthetic %.2f Gb assembly, %d contigs (40 SUPER_* scaffolds + 460 unplaced), whole-genome "
+                        "scan + scoring vs combined IGHV/IGHJ, minimap2 prefilter bypassed" % (bases / 1e9, len(asm.lengths)),
+            "scaling": "strong", "n_gpus": world, "bases": bases, "reps": a.strong_reps,
+            "whole_job_s": med[0], "gb_scanned_per_s": bases / med[0] / 1e9,
+            "load_h2d_pack_s": med[1], "scan_and_scoring_s": med[2], "gather_s": med[3],
+            "scan_kernel_ms_max": med[4], "pack_kernel_ms_max": med[5],
+            "timing": "median over reps of the max over ranks; host ASCII in pinned memory, H2D + pack inside",
+            "rank0_pieces": len(pieces), "rank0_bases": int(n_mine), "generate_s_rank0": t_gen,
+            "rows": {g: len(merged[g]) for g in ("V", "D", "J")},
+            "rows_sha1": hashlib.sha1(text.encode()).hexdigest()}
+
+
 class Clocks:
     """nvidia-smi sampler running during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -185,6 +294,10 @@ def gpu_arm(a):
                       "achieved": (len(big) + 3) // 4 / (ms * 1e-3) / 1e9}
         del big
 
+    strong = None
+    if a.strong_reps > 0:
+        del pinned
+        strong = strong_config3(a, eng, motifs, canon, rank, world, barrier)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -242,6 +355,15 @@ def gpu_arm(a):
                                                    % (a.mbases, scan_large["bases"] / 1e6),
                                        "kernel_ms": scan_large["kernel_ms"], "hits": scan_large["hits"],
                                        "gb_per_s_both_strands": scan_large["bases"] / (scan_large["kernel_ms"] * 1e-3) / 1e9}
+    if strong:
+        # the multi-GPU split of the north star (contigs / pieces sharded over the GPUs), strong-scaled at this N; `value`
+        # above stays the same workload at every N (one configs[1] contig per GPU) so that the per-N values are comparable
+        line["strong_config3"] = strong
+        alg3 = (strong["rank0_bases"] + 3) // 4
+        line["roofline_scan_config3"] = {"kernel": "rss_scan_kernel", "bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+                                         "achieved": alg3 / (strong["scan_kernel_ms_max"] * 1e-3) / 1e9,
+                                         "frac": alg3 / (strong["scan_kernel_ms_max"] * 1e-3) / 1e9 / hbm_peak,
+                                         "workload": "rank 0's shard of configs[2] (%d bases)" % strong["rank0_bases"]}
     if not a.no_cpu:
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, stdout=subprocess.DEVNULL)
         line["cpu_baseline"] = cpu_sample(contig, seqs, motifs, canon, kstat["fragments"], a)
@@ -392,6 +514,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mbases", type=float, default=100.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong-reps", type=int, default=3, help="timed repetitions of the strong-scaled configs[2] leg (0 = skip)")
+    ap.add_argument("--strong-scale", type=float, default=1.0, help="size of the configs[2] assembly relative to 3.06 Gb")
     ap.add_argument("--scan-mbases", type=float, default=1000.0,
                     help="size of the extra scan-only measurement (the workload contig repeated; 0 = skip)")
     a = ap.parse_args()

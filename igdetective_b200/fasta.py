@@ -39,6 +39,24 @@ def fasta_dict(path, upper=False):
     return d
 
 
+class ArraySeq:
+    """str-like view of a contig held as a uint8 array (e.g. a slice of pinned host memory): len() and slicing with
+    Python semantics return str; nothing else is copied.  What parent_seq[contig] is for callers that keep genomes
+    as byte buffers."""
+
+    def __init__(self, a):
+        self.a = a
+
+    def __len__(self):
+        return len(self.a)
+
+    def __getitem__(self, s):
+        return self.a[s].tobytes().decode("latin-1")
+
+    def __str__(self):
+        return self.a.tobytes().decode("latin-1")
+
+
 class ContigView:
     """One contig of a NativeFasta: len() and slicing with Python semantics (negative indices wrap,
     out-of-range bounds clamp), returning str -- what the reference does with parent_seq[contig]."""

@@ -19,16 +19,19 @@ from .fasta import NativeFasta, fasta_dict
 from .rss import D, J, V
 
 
-def detect_pieces(eng, seqs, ids, pieces, canonical, order="canonical"):
+def detect_pieces(eng, seqs, ids, pieces, canonical, order="canonical", part=None):
     """igdetective.detect on this rank's pieces (shard.plan_pieces): each piece is loaded as a contig of its own,
-    the rows it owns are kept and moved to contig coordinates.  seqs: {contig id: str-like}."""
+    the rows it owns are kept and moved to contig coordinates.  seqs: {contig id: str-like}.  `part`: {piece
+    number: str-like} already loaded on the engine by the caller (byte buffers in pinned memory)."""
     if not pieces:
         return {V: [], D: [], J: []}
-    part = {}
-    for k, (ci, a, b, p0, p1) in enumerate(pieces):
-        s = seqs[ids[ci]]
-        part[k] = s if (p0 == 0 and p1 == len(s)) else s[p0:p1]
-    _, rows = igdetective.detect(eng, part, canonical, order)
+    load = part is None
+    if load:
+        part = {}
+        for k, (ci, a, b, p0, p1) in enumerate(pieces):
+            s = seqs[ids[ci]]
+            part[k] = s if (p0 == 0 and p1 == len(s)) else s[p0:p1]
+    _, rows = igdetective.detect(eng, part, canonical, order, load=load)
     out = {V: [], D: [], J: []}
     by_piece = {g: {} for g in out}
     for g in out:

@@ -12,7 +12,11 @@ run in libigd_b200.so (hand-written sm_100a CUDA); there is no CPU fallback.
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the igdetective_b200 package: installed / on PYTHONPATH, else $IGD_B200_HOME, else next to this py/ directory
+# (symlinks resolved: the directory may be linked into a reference checkout)
+for _home in (os.environ.get("IGD_B200_HOME"), os.path.dirname(os.path.dirname(os.path.realpath(__file__)))):
+    if _home and os.path.isdir(os.path.join(_home, "igdetective_b200")) and _home not in sys.path:
+        sys.path.insert(0, _home)
 
 from igdetective_b200.igdetective import main  # noqa: E402
 

@@ -8,7 +8,11 @@ these names resolve to igdetective_b200.extract_aligned_genes, whose alignments 
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the igdetective_b200 package: installed / on PYTHONPATH, else $IGD_B200_HOME, else next to this py/ directory
+# (symlinks resolved: the directory may be linked into a reference checkout)
+for _home in (os.environ.get("IGD_B200_HOME"), os.path.dirname(os.path.dirname(os.path.realpath(__file__)))):
+    if _home and os.path.isdir(os.path.join(_home, "igdetective_b200")) and _home not in sys.path:
+        sys.path.insert(0, _home)
 
 from igdetective_b200.extract_aligned_genes import (  # noqa: E402,F401
     Alignment, BioAlign, ComputeAlignment, GpuAligner, PrepareOutputDir, ProcessSamFile, SetupAligner, main)
