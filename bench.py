@@ -313,6 +313,9 @@ def gpu_arm(a):
     achieved = alg_bytes / (scan_ms * 1e-3) / 1e9
     sm_hz = (clk or {}).get("sm_mhz", 1965.0) * 1e6
     int_peak = 148 * 64 * sm_hz / 1e12            # ALU-pipe lane-ops/s (T), 64 lanes/clk/SM
+    sass = gotoh_instruction_counts()
+    traffic = ncu_traffic()
+    alu_per_cell = sass["alu_pipe_per_cell"]
     line = {
         "metric": METRIC, "value": total_bases / (t_dev / a.steps) / 1e9, "unit": UNIT,
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps,
@@ -335,17 +338,21 @@ def gpu_arm(a):
                                  "gotoh": kstat["align_ms"] / (1e3 * t_dev / a.steps)},
         # dominant kernel of the step (97 % of GPU time in the ncu launch list): integer DP, bound by the
         # ALU pipe (neither HBM nor tensor); achieved = cell updates/s x ALU-pipe instructions per cell
-        "roofline": {"kernel": "gotoh_packed_kernel<32,11>", "bound": "alu", "achieved": kstat["gcups"] * kstat["ops_per_cell"] / 1e3,
-                     "peak": int_peak, "unit": "T lane-ops/s", "frac": kstat["gcups"] * kstat["ops_per_cell"] / 1e3 / int_peak,
-                     # dram bytes of one launch of this shape from the ncu --set full capture in profiles/ (inputs are KB per pair)
-                     "traffic": 1378816 if a.mbases == 100.0 else None,
-                     "gcups": kstat["gcups"], "alu_ops_per_cell": kstat["ops_per_cell"],
+        "roofline": {"kernel": "gotoh_packed_kernel<%s,%s>" % V_KERNEL[:2], "bound": "alu", "achieved": kstat["gcups"] * alu_per_cell / 1e3,
+                     "peak": int_peak, "unit": "T lane-ops/s", "frac": kstat["gcups"] * alu_per_cell / 1e3 / int_peak,
+                     # dram bytes of one launch of this kernel (inputs are KB per pair): ncu --set full capture of this round
+                     "traffic": traffic["gotoh_packed"]["dram_bytes_per_launch"], "traffic_source": traffic["gotoh_packed"]["source"],
+                     "gcups": kstat["gcups"], "alu_ops_per_cell": alu_per_cell, "all_ops_per_cell": sass["all_per_cell"],
+                     "fma_ops_per_cell": sass["fma_pipe_per_cell"], "ops_source": sass["source"],
+                     # the same against the issue port: every instruction of the hot path, 128 lanes/clk/SM
+                     "issue_frac": kstat["gcups"] * sass["all_per_cell"] / 1e3 / (2 * int_peak),
                      "peak_source": "148 SMs x 64 ALU lanes/clk x SM clock sampled during the run"},
         # the HBM-bound kernel of the path (north star: scan vs HBM roofline), 0.25 algorithmic bytes per base
         "roofline_scan": {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes": alg_bytes,
                           # dram__bytes_read+write of one launch, ncu --set full capture in profiles/: equals the algorithmic bytes
-                          "traffic": 25554688 if a.mbases == 100.0 else None,
+                          "traffic": traffic["rss_scan_100Mb"]["dram_bytes_per_launch"] if a.mbases == 100.0 else None,
+                          "traffic_source": traffic["rss_scan_100Mb"]["source"],
                           "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"},
     }
     if scan_large:
@@ -372,7 +379,36 @@ def gpu_arm(a):
         dist.destroy_process_group()
 
 
-ALU_OPS_PER_CELL = 7.3      # ALU-pipe instructions per cell in the SASS of gotoh_packed_kernel<32,11,0,false,true>: 80 per 11-cell column step (14.4 incl. the FMA pipe: 38 IMAD + 34 FFMA/FADD)
+V_KERNEL = ("16", "22", "0", "0", "1")       # gotoh_packed_kernel<G, C, MIXED, LONG, FPINC>: the instance the 350-nt V flanks run in
+SASS_JSON = os.path.join(ROOT, "profiles", "r02_sass_counts_gotoh_16x22.json")
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+
+
+def gotoh_instruction_counts():
+    """ALU-pipe / all instructions per DP cell of the dominant kernel, counted in the SASS of the library that is loaded
+    (profiles/sass_derive.py); the committed count of the same derivation is used only where cuobjdump is missing, and a
+    difference between the two is reported.  No typed-in constants: without either source the bench fails."""
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import sass_derive
+    from igdetective_b200 import _lib
+    committed = json.load(open(SASS_JSON)) if os.path.exists(SASS_JSON) else None
+    try:
+        res, _ = sass_derive.derive(_lib.LIB_PATH, V_KERNEL, int(V_KERNEL[1]))
+        res["source"] = "cuobjdump -sass of the loaded library in this run (profiles/sass_derive.py)"
+        if committed and committed["counts"] != res["counts"]:
+            res["source"] += "; differs from the committed " + os.path.relpath(SASS_JSON, ROOT)
+        return res
+    except (OSError, subprocess.CalledProcessError, RuntimeError) as e:
+        if committed is None:
+            raise RuntimeError("no instruction counts: cuobjdump failed (%s) and %s is missing" % (e, SASS_JSON))
+        committed["source"] = "%s (cuobjdump unavailable here: %s)" % (os.path.relpath(SASS_JSON, ROOT), e)
+        return committed
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the two roofline kernels, from the ncu --set full
+    captures of this round (profiles/ncu_traffic.py writes the file from the .ncu-rep reports)."""
+    return json.load(open(TRAFFIC_JSON))
 
 
 def kernel_stats(eng, seqs, canon, igdetective):
@@ -391,8 +427,7 @@ def kernel_stats(eng, seqs, canon, igdetective):
         t = eng.timing()
         ms += t["align_ms"]; cells += t["align_cells"]; pairs += 2 * len(flat) * len(canon[g])
     return {"hits": int(len(scan.hits)), "align_ms": ms, "cells": int(cells), "pairs": int(pairs),
-            "gcups": cells / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "ops_per_cell": ALU_OPS_PER_CELL,
-            "fragments": flat_all}
+            "gcups": cells / (ms * 1e-3) / 1e9 if ms > 0 else 0.0, "fragments": flat_all}
 
 
 # --------------------------------------------------------------------------------------- CPU arms

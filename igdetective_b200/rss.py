@@ -53,16 +53,20 @@ class RssScan:
         self._cache = {}
 
     def _kmer_hits(self, k):
+        """(hits of find_valid_motif_idx for this k, sorted by (contig, pos); first hit of every contig)"""
         if k not in self._kmers:
-            self._kmers[k] = self.engine.scan_kmers(k)
+            kh = self.engine.scan_kmers(k)
+            bounds = np.searchsorted(kh["contig"], np.arange(len(self.ids) + 1))       # one split per k, not a mask per list
+            self._kmers[k] = (kh, bounds)
         return self._kmers[k]
 
     def _first_set(self, sig_type, strand, ci):
         """Ascending scanned-strand indices of the 5' k-mer set of find_valid_rss (:153-160)."""
         k = 7 if HEPT_FIRST[sig_type] else 9
-        kh = self._kmer_hits(k)
+        kh, bounds = self._kmer_hits(k)
         bit = 1 << (SIGNAL_INDEX[sig_type] + (4 if strand == REV else 0))
-        sel = kh[(kh["contig"] == ci) & ((kh["flags"] & bit) != 0)]["pos"].astype(np.int64)
+        mine = kh[bounds[ci]:bounds[ci + 1]]
+        sel = mine[(mine["flags"] & bit) != 0]["pos"].astype(np.int64)
         if strand == REV:
             sel = (self.lens[ci] - sel - k)[::-1]
         return sel.tolist()

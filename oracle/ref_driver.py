@@ -218,6 +218,11 @@ def run(genome_fasta, igcontig_dir, output_dir, ig_gene_dir, py_dir='py', loci=L
 
 
 if __name__ == '__main__':
-    # python oracle/ref_driver.py genome.fasta ig_contigs_dir output_dir ig_gene_dir [py_dir]
+    # python oracle/ref_driver.py genome.fasta ig_contigs_dir output_dir ig_gene_dir [py_dir [module:function]]
+    # the optional last argument names a replacement of CombineIGGenes (same signature) to run in its place
     os.makedirs(sys.argv[3], exist_ok=True)
-    run(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else 'py')
+    combine = None
+    if len(sys.argv) > 6:
+        mod, _, fn = sys.argv[6].partition(':')
+        combine = getattr(importlib.import_module(mod), fn)
+    run(sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else 'py', combine=combine)

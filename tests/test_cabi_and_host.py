@@ -6,7 +6,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import DATAFILES, ROOT, golden_input
+from conftest import DATAFILES, GOLDEN, ROOT, golden_input
 from oracle import igd_oracle as O
 
 
@@ -241,3 +241,33 @@ def test_sparse_host_glue_equals_reference_shapes():
             fs = get_s_fragment_from_RSS(g, strand, info, seqs, sparse=True)
             assert fd == O.s_fragments(g, strand, info, seqs)
             assert list(fs) == list(fd) and all(list(fs[c]) == fd[c] for c in ids)
+
+
+def test_combine_ig_genes_equals_the_reference_definition_and_golden(tmp_path):
+    """iterative.CombineIGGenes (run_iterative_igdetective.py:130-151): the indexed substring filter against the
+    reference's double loop on random sets with planted substrings (both code paths), and byte for byte against the
+    <gene>_combined.fasta files the unmodified driver wrote (same PYTHONHASHSEED: the set order names the sequences)."""
+    import subprocess
+    import sys
+
+    from igdetective_b200 import iterative
+    rng = np.random.default_rng(21)
+
+    def rand(n):
+        return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    for n, lo, hi in ((60, 1, 80), (2500, 16, 60)):
+        base = [rand(int(rng.integers(lo, hi))) for _ in range(n)]
+        extra = [s[int(rng.integers(0, len(s) // 2 + 1)):int(rng.integers(len(s) // 2 + 1, len(s) + 1))] for s in base[::7]]
+        seqs = list(dict.fromkeys(base + extra + ([""] if lo == 1 else [])))
+        want = [any(a != b and b.find(a) != -1 for b in seqs) for a in seqs]
+        assert iterative.contained_in_another(seqs) == want
+        assert sum(want) >= len(extra) // 2
+    case = os.path.join(GOLDEN, "driver", "tri_locus")
+    code = ("import sys; sys.path.insert(0, %r); from igdetective_b200.iterative import CombineIGGenes; "
+            "CombineIGGenes(sys.argv[1], sys.argv[2], sys.argv[3])" % ROOT)
+    for gene in ("IGHV", "IGKV", "IGLV", "TRBV"):
+        out = str(tmp_path / (gene + ".fasta"))
+        subprocess.run([sys.executable, "-c", code, os.path.join(case, "iterative_search", gene + "_iter0", "genes.fasta"),
+                        os.path.join(case, "denovo_search", "predicted_genes_" + gene[:3], "genes_V.tsv"), out],
+                       check=True, env=dict(os.environ, PYTHONHASHSEED="0"))
+        assert open(out).read() == open(os.path.join(case, "iterative_search", gene + "_combined.fasta")).read(), gene

@@ -7,8 +7,9 @@ The golden files under tests/golden/driver/tri_locus were written by the UNMODIF
 minimap2, no-op plotting modules -- tests/golden/make_golden.py:make_driver).  The GPU box has no
 reference checkout, so the driver's glue (locus cropping with |START:|END: headers, the iterative loop
 feeding growing gene FASTAs back into the scoring, CollectLocusSummary) is run from its restatement
-oracle/ref_driver.py, which make_golden.py pins byte for byte against the unmodified driver.  The
-prefilter's output (ig_contigs/) is an input, rebuilt here from the golden summary and manifest."""
+oracle/ref_driver.py, which make_golden.py pins byte for byte against the unmodified driver; its
+CombineIGGenes step runs the product's indexed version (igdetective_b200.iterative).  The prefilter's
+output (ig_contigs/) is an input, rebuilt here from the golden summary and manifest."""
 import gzip
 import os
 import shutil
@@ -66,13 +67,14 @@ def _golden_files():
 def test_combined_genes_tables_through_the_stage_shims(tmp_path):
     work, genome, igc = _prepare(tmp_path)
     env = dict(os.environ, PYTHONHASHSEED="0", PATH=os.path.join(ROOT, "oracle", "stubs") + os.pathsep + os.environ["PATH"])
-    env.pop("PYTHONPATH", None)            # no Bio shim anywhere near the product
+    env["PYTHONPATH"] = ROOT               # the product package only: no Bio shim anywhere near it
     env.pop("IGD_STUB_SAM", None)
     env.pop("IGD_DATAFILES", None)         # the shims find datafiles/ under the working directory, like the reference
     out = work / "out"
     out.mkdir()
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_driver.py"), str(genome), str(igc), str(out),
-                        "datafiles/combined_reference_genes", "py"], cwd=work, env=env, capture_output=True, text=True)
+                        "datafiles/combined_reference_genes", "py", "igdetective_b200.iterative:CombineIGGenes"],
+                       cwd=work, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     files = _golden_files()
     assert any(f.startswith("combined_genes_IGH") for f in files) and any("iterative_search" in f for f in files)
