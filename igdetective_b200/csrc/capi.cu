@@ -285,9 +285,21 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_SEQOFF], rel.data(), (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
     if (n_contigs)
         IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_CHUNK0], h->contig_chunk0.data(), (size_t)n_contigs * 8, cudaMemcpyHostToDevice, h->stream));
+    // contig holding the first chunk of every tile of 512 chunks (-1: the leading pad), for the pack kernel
+    std::vector<int32_t> tile_contig((size_t)h->n_tiles + 1);
+    {
+        int c = -1;
+        for (uint64_t t = 0; t <= h->n_tiles; ++t) {
+            const uint64_t ch = t * IGD_TILE_CHUNKS;
+            while (c + 1 < n_contigs && h->contig_chunk0[c + 1] <= ch) ++c;
+            tile_contig[t] = c;
+        }
+    }
+    if ((rc = igd_reserve(h, S_TILEC, tile_contig.size() * 4))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TILEC], tile_contig.data(), tile_contig.size() * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
     if ((rc = igd_launch_pack(h, (const uint8_t *)h->d_scratch[S_SEQ], (const unsigned long long *)h->d_scratch[S_SEQOFF],
-                              (const unsigned long long *)h->d_scratch[S_CHUNK0], n_contigs))) return rc;
+                              (const unsigned long long *)h->d_scratch[S_CHUNK0], (const int *)h->d_scratch[S_TILEC], n_contigs))) return rc;
     IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));       // rel / offsets are host temporaries
     IGD_CUDA(cudaEventElapsedTime(&h->timing.pack_ms, h->ev0, h->ev1));
@@ -547,13 +559,19 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
     uint64_t n = 0; int rc;
     if ((rc = current_count(h, &n))) return rc;
     if ((rc = pull_hits(h, n))) return rc;
-    struct Rec { uint64_t k0, k1; igd_hit hit; };
-    std::vector<Rec> recs(n);
+    // The raw keys sort by global heptamer position first: after that one sort the contig of a hit is found by walking
+    // the contig table forward, not by a search per hit.  The final order (contig, type, strand, index of the list's
+    // first element in scanned-strand coordinates) is a second sort of 16-byte (key, index) pairs.
+    std::sort(h->host_hits.begin(), h->host_hits.end());
+    std::vector<igd_hit> hits(n);
+    std::vector<std::pair<std::pair<uint64_t, uint64_t>, uint32_t>> keyed(n);
+    uint32_t c = 0;
+    const uint32_t nc = (uint32_t)h->contig_chunk0.size();
     for (uint64_t i = 0; i < n; ++i) {
         const unsigned long long key = h->host_hits[i];
         const uint64_t g = key >> 8;
         const int t = (int)((key >> 4) & 3), strand = (int)((key >> 3) & 1), d = (int)(key & 3);
-        const uint32_t c = contig_of(h, g >> 6);
+        while (c + 1 < nc && h->contig_chunk0[c + 1] <= (g >> 6)) ++c;
         const int64_t hept = (int64_t)(g - h->contig_chunk0[c] * 64);
         const int s1 = h->last_spacer[t] + (d == 0 ? 0 : (d == 1 ? -1 : 1));
         const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
@@ -564,15 +582,14 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
         const int64_t first = hept_first ? hept : nona;
         const int64_t kf = hept_first ? 7 : 9;
         const int64_t scan_idx = strand == 0 ? first : L - first - kf;
-        Rec &r = recs[i];
-        r.k0 = ((uint64_t)c << 8) | ((uint64_t)t << 4) | (uint64_t)strand;
-        r.k1 = (uint64_t)scan_idx;
-        r.hit.hept = hept; r.hit.nona = nona; r.hit.contig = c;
-        r.hit.sig_type = (uint8_t)t; r.hit.strand = (uint8_t)strand; r.hit.spacer = (uint8_t)s1; r.hit.reserved = 0;
+        igd_hit &r = hits[i];
+        r.hept = hept; r.nona = nona; r.contig = c;
+        r.sig_type = (uint8_t)t; r.strand = (uint8_t)strand; r.spacer = (uint8_t)s1; r.reserved = 0;
+        keyed[i] = {{((uint64_t)c << 3) | ((uint64_t)t << 1) | (uint64_t)strand, (uint64_t)scan_idx}, (uint32_t)i};
     }
-    std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.k0 != b.k0 ? a.k0 < b.k0 : a.k1 < b.k1; });
+    std::sort(keyed.begin(), keyed.end());
     h->sorted_hits.resize(n);
-    for (uint64_t i = 0; i < n; ++i) h->sorted_hits[i] = recs[i].hit;
+    for (uint64_t i = 0; i < n; ++i) h->sorted_hits[i] = hits[keyed[i].second];
     h->sorted_hits_valid = true;
     *n_out = n;
     return IGD_OK;
@@ -646,7 +663,8 @@ static int packed_layout_for(const igd_scoring *sc, int nA, int nB)
     if (sc->query_end_open == 0 && sc->query_end_extend == 0)
         lo = std::max(lo, sc->target_internal_open + sc->target_internal_extend * (nB - 1)
                           + std::min(0, sc->mismatch) * std::min(nA, nB));
-    if (nA <= 511 && hi <= 1900 && lo - 8 * 40 >= -1900) return 1;
+    // the short layout stores column j in a frame shifted by -j * te (gotoh.cu): values rise by up to nB * |te|
+    if (nA <= 511 && hi + nB * std::max(0, -sc->target_internal_extend) <= 1900 && lo - 8 * 40 >= -1900) return 1;
     if (nA <= 1023 && hi <= 900 && lo - 2 * 40 >= -820) return 2;
     return 0;
 }

@@ -81,8 +81,8 @@ struct igd_handle {
     int32_t last_spacer[4] = {0, 0, 0, 0};
 
     // generic growable device scratch for the aligner
-    void *d_scratch[16] = {nullptr};
-    size_t scratch_cap[16] = {0};
+    void *d_scratch[20] = {nullptr};
+    size_t scratch_cap[20] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
     void *h_ring = nullptr;       // ring of pinned pieces for the upload of pageable genomes (capi.cu, upload_letters)
@@ -101,7 +101,7 @@ int igd_cuda_fail(cudaError_t e, const char *what);
 
 // growable device scratch slots (capi.cu, detect.cu)
 enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK,
-       S_FRAG, S_BEST, S_COUNT };
+       S_FRAG, S_BEST, S_TILEC, S_COUNT };
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
 // 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
@@ -118,7 +118,7 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n);          // fills h->sorted_hit
 
 // pack.cu
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,
-                    const unsigned long long *d_chunk0, int n_contigs);
+                    const unsigned long long *d_chunk0, const int *d_tile_contig, int n_contigs);
 // rss_scan.cu
 // prepare_only: upload the spacer-dependent table and load / configure the kernel instance, no launch (keeps the
 // first scan's one-off costs out of the timed window)

@@ -13,9 +13,24 @@
 // Only integers cross the bus: 8 bytes per RSS hit in, 16 bytes per candidate and 8 per winner out.
 #include "common.cuh"
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <unordered_map>
 
 namespace {
+
+// IGD_DETECT_TRACE=1: host-clock time of every phase of igd_detect on stderr (profiles/step_profile.py)
+struct Trace {
+    bool on; std::chrono::steady_clock::time_point t0;
+    Trace() : on(getenv("IGD_DETECT_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char *what)
+    {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[igd_detect] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    }
+};
 
 struct FragDesc { unsigned long long g0; int32_t len; int32_t rc; };   // letters [g0, g0+len) of the letter buffer
 
@@ -126,6 +141,7 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
                     const igd_scoring *sc, const igd_detect_params *prm, Acc &acc)
 {
     if (cand.empty() || n_gene <= 0) return IGD_OK;
+    Trace tr;
     int rc;
     bool any_empty = false;
     for (const Cand &c : cand) any_empty |= c.len == 0;
@@ -173,8 +189,10 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
                 h->d_comp, U, (uint8_t *)h->d_scratch[S_TGT]);
             h->timing.total_launches++;
             IGD_CUDA(cudaGetLastError());
+            tr.mark("batch tables + gather launch");
             bool launched = false;
             if ((rc = igd_dense_launch(h, nullptr, toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, true))) return rc;
+            tr.mark("dense launch (host side)");
             if (!launched) {
                 igd_set_error("a (fragment, gene) pair does not fit the packed alignment kernels (gene longer than 511 or scores out of range)");
                 return IGD_ERR_UNSUPPORTED;
@@ -193,6 +211,7 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
             float ms = 0.f;
             IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             acc.ms += ms; acc.cells += h->timing.align_cells; acc.launches += h->timing.align_launches;
+            tr.mark("dense kernels + argmax D2H");
         }
         // ---- threshold (:387) in float64, exactly as the reference evaluates it ------------------------------
         struct Win { size_t cand; Best b; };
@@ -254,6 +273,7 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
             float ms = 0.f;
             IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             acc.ms += ms; acc.launches += h->timing.align_launches;
+            tr.mark("winners' detail pass");
             for (size_t i = 0; i < n; ++i) {
                 const int nA = toff[pt[i] + 1] - toff[pt[i]], nB = gene_off[pq[i] + 1] - gene_off[pq[i]];
                 const Best &b = wins[(size_t)who[i]].b;
@@ -300,9 +320,12 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
     }
     h->vj_rows.clear(); h->d_rows.clear();
     int rc;
+    Trace tr;
     if ((rc = igd_run_rss_scan(h, spacer, n_hits))) return rc;
+    tr.mark("scan");
     uint64_t n = 0;
     if ((rc = igd_sorted_hits(h, &n))) return rc;
+    tr.mark("hits D2H + decode + sort");
     if (!h->d_comp) {
         uint8_t comp[256];
         for (int i = 0; i < 256; ++i) comp[i] = (uint8_t)i;
@@ -372,6 +395,7 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
     }
     h->d_rows = drows[0];
     h->d_rows.insert(h->d_rows.end(), drows[1].begin(), drows[1].end());
+    tr.mark("candidates + D pairing");
     const float scan_ms = h->timing.scan_ms;
     Acc acc;
     for (int gt = 0; gt < 2; ++gt) {

@@ -213,7 +213,15 @@ struct PackedParams {
 // once, the factor is a per-row constant (MIXED = 1: queries are all upper case) that a lower-case query
 // letter swaps by one more FFMA per cell (MIXED = 2).
 // resident CTAs per SM the register allocation aims for: 6 for the shapes that fit 80 registers
-constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : (C == 22 ? 4 : 1); }
+#ifndef IGD_V_FRAME
+#define IGD_V_FRAME 0
+#endif
+#ifndef IGD_V_MB
+#define IGD_V_MB 4
+#endif
+constexpr int packed_min_blocks(int C) { return C <= 11 ? 6 : (C == 22 ? IGD_V_MB : 1); }
+// which instances keep their columns in the shifted frame (see the kernel)
+__host__ __device__ constexpr bool packed_frame(int C, bool LONG) { return !LONG && (C != 22 || IGD_V_FRAME); }
 // MIXED: 0 = no lower-case letter anywhere; 1 = only targets may hold lower-case letters; 2 = queries may too.
 template <int G, int C, int MIXED, bool LONG, bool FPINC>
 __global__ void __launch_bounds__(GT_THREADS, packed_min_blocks(C))
@@ -225,6 +233,13 @@ gotoh_packed_kernel(const PackedParams P)
     const int l = lane % G;
     const int grp = lane / G;
     const int m_clear = P.m_clear, m_pr = P.m_pr, one = P.one;
+    // Column frame: every value stored for column j is the true value minus j * te (the Iy extension score), so that
+    // extending a gap along the row -- Iy(i,j) = max(D(i,j-1) + to, Iy(i,j-1) + te) -- needs no add on the extension
+    // side: max(D + (to - te), Iy) in the frame, ONE VIADDMNMX.  The diagonal step crosses one column (the increment
+    // words carry -te), the vertical step stays in its column (unchanged), the result leaves the frame at the end.
+    // Short layout only: the long layout's 11-bit score field has no room for the frame's + j.
+    constexpr bool FRAME = packed_frame(C, LONG);
+    const int to_te = P.to - P.te;
 
     for (;;) {
         unsigned base = 0;
@@ -276,7 +291,7 @@ gotoh_packed_kernel(const PackedParams P)
             int upX = __shfl_up_sync(0xffffffffu, botX, 1, G);
             if (active && t >= l) {
                 ++j;
-                if (l == 0) { upD = P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j), priority 0
+                if (l == 0) { upD = FRAME ? to_te : P.to + P.te * (j - 1); upX = PK_NEG; }   // row 0: Iy(0,j) = to + te (j-1), priority 0
                 const unsigned braw = B[j - 1];
                 const unsigned b = MIXED ? (braw | (up8(braw) << 8)) : braw;
                 const float bf = (float)(MIXED ? up8(braw) : braw);
@@ -313,11 +328,12 @@ gotoh_packed_kernel(const PackedParams P)
                     const int m = LONG ? E[r] + inc : E[r] * one + inc;
                     const int x = __viaddmax_s32(uD, qo, uX * one + qe);               // Ix(i,j) raw
                     const int xs = (x & m_clear) | m_pr;                               // priority 1 (one LOP3)
-                    const int y = __viaddmax_s32(D[r], P.to, Y[r] * one + P.te) & ~PK_PRMASK; // Iy(i,j), priority 0
+                    // Iy(i,j), priority 0: the extension is free in the column frame
+                    const int y = (FRAME ? __viaddmax_s32(D[r], to_te, Y[r]) : __viaddmax_s32(D[r], P.to, Y[r] * one + P.te)) & ~PK_PRMASK;
                     const int d = __vimax3_s32(m, xs, y);
                     // the diagonal of the next column is updated in place once it has been read, so no
                     // state needs two live copies (saves the register moves of "dc = old D[r]")
-                    E[r] = (r == 0 && l == 0) ? (P.to + P.te * (j - 1)) : (uD & ~PK_PRMASK);
+                    E[r] = (r == 0 && l == 0) ? (FRAME ? to_te : P.to + P.te * (j - 1)) : (uD & ~PK_PRMASK);
                     D[r] = d; Y[r] = y;
                     uD = d; uX = xs;
                 }
@@ -327,7 +343,7 @@ gotoh_packed_kernel(const PackedParams P)
                         int k = 0;
 #pragma unroll
                         for (int r = 0; r < C; ++r) if (r == rs) k = D[r];
-                        P.out_score[out] = k >> PK<LONG>::SHIFT;
+                        P.out_score[out] = (k >> PK<LONG>::SHIFT) + (FRAME ? nB * (P.te >> PK<LONG>::SHIFT) : 0);   // out of the column frame
                         P.out_pay[out] = ((unsigned)k & 511u) | ((((unsigned)k >> 9) & PK<LONG>::IXMASK) << 10);   // wide-kernel layout
                     }
                     ++out; ++q;
@@ -409,13 +425,15 @@ int igd_align_bucket_of(int target_len)
 }
 
 template <bool LONG>
-static void fill_packed(PackedParams &P, const igd_align_job &job)
+static void fill_packed(PackedParams &P, const igd_align_job &job, int C)
 {
     constexpr int S = PK<LONG>::S, PR = PK<LONG>::PR;
     P.tgt = job.d_tgt; P.tgt_off = job.d_tgt_off; P.qry = job.d_qry; P.qry_off = job.d_qry_off;
     P.runs = job.d_runs; P.n_runs = job.n_work;
-    P.inc_match = job.sc.match * S + 2 * PR + 1;
-    P.inc_mismatch = job.sc.mismatch * S + 2 * PR;
+    // column frame of the short-layout kernel: the diagonal step crosses one column, so both increments carry -te
+    const int frame = packed_frame(C, LONG) ? job.sc.target_internal_extend : 0;
+    P.inc_match = (job.sc.match - frame) * S + 2 * PR + 1;
+    P.inc_mismatch = (job.sc.mismatch - frame) * S + 2 * PR;
     P.to = job.sc.target_internal_open * S; P.te = job.sc.target_internal_extend * S;
     P.qio = job.sc.query_internal_open * S; P.qie = job.sc.query_internal_extend * S;
     P.qeo = job.sc.query_end_open * S; P.qee = job.sc.query_end_extend * S;
@@ -426,8 +444,10 @@ static void fill_packed(PackedParams &P, const igd_align_job &job)
 static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
 {
     PackedParams P;
+    static const bool narrow = getenv("IGD_GOTOH_V_SHAPE") && !strcmp(getenv("IGD_GOTOH_V_SHAPE"), "32x11");
+    static const int rows_of[6] = {9, 6, 22, 16, 25, 32};
     if (job.packed == 1) {
-        fill_packed<false>(P, job);
+        fill_packed<false>(P, job, job.bucket == 2 && narrow ? 11 : rows_of[job.bucket]);
         switch (job.bucket) {
         case 0: return launch_packed<8, 9, false>(h, P, job.mixed_case);
         case 1: return launch_packed<32, 6, false>(h, P, job.mixed_case);
@@ -435,13 +455,12 @@ static int launch_gotoh_packed(igd_handle *h, const igd_align_job &job)
             // 16 lanes x 22 rows: the ~29 per-column instructions (query letter, shuffles, boundary selects) are shared by
             // 22 cells instead of 11 -- 13.3 instead of 14.6 instructions per cell, 2.04 instead of 1.90 TCUPS at 128
             // registers / 4 CTAs per SM (8 x 44 at 255 registers / 2 CTAs: 1.96).  IGD_GOTOH_V_SHAPE=32x11 selects the old shape.
-            static const bool narrow = getenv("IGD_GOTOH_V_SHAPE") && !strcmp(getenv("IGD_GOTOH_V_SHAPE"), "32x11");
             return narrow ? launch_packed<32, 11, false>(h, P, job.mixed_case) : launch_packed<16, 22, false>(h, P, job.mixed_case);
         }
         case 3: return launch_packed<32, 16, false>(h, P, job.mixed_case);
         }
     } else {
-        fill_packed<true>(P, job);
+        fill_packed<true>(P, job, rows_of[job.bucket]);
         switch (job.bucket) {
         case 4: return launch_packed<32, 25, true>(h, P, job.mixed_case);
         case 5: return launch_packed<32, 32, true>(h, P, job.mixed_case);

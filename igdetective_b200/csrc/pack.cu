@@ -11,7 +11,9 @@
 // start at any byte: the 16 wanted bytes are cut out of the 32 loaded ones by funnel shifts), classified
 // through a 256-entry table in shared memory whose entries hold the low / high code bit and the
 // "not ACGT" bit in three byte-wide fields, and accumulated with one shift-add per letter; four lanes'
-// results are joined into the chunk's record by shuffles.
+// results are joined into the chunk's record by shuffles.  All eight loads of a group are issued before the
+// arithmetic starts, and the contig of a group comes from a host-made table (one entry per tile of 512 chunks)
+// instead of a binary search, so no warp sits in a chain of dependent loads.
 #include "common.cuh"
 
 namespace {
@@ -22,7 +24,7 @@ __device__ __forceinline__ uint4 ldg_nc_128(const uint8_t *p) { return __ldg((co
 
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restrict__ seq_off,
-            const unsigned long long *__restrict__ chunk0, int n_contigs,
+            const unsigned long long *__restrict__ chunk0, const int *__restrict__ tile_contig, int n_contigs,
             unsigned long long n_chunks, uint4 *__restrict__ planes,
             unsigned long long *__restrict__ inv, uint32_t *__restrict__ invsum)
 {
@@ -45,31 +47,42 @@ pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restric
     const unsigned long long ngroups = (n_chunks + 31) / 32;
 
     for (unsigned long long g = warp; g < ngroups; g += nwarps) {
-        // contig holding the first chunk of the group: last c with chunk0[c] <= chunk (warp-uniform search)
-        int lo = 0, hi = n_contigs;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(&chunk0[mid]) <= g * 32) lo = mid + 1; else hi = mid; }
-        int c = lo - 1;
-        unsigned summary = 0;
+        // contig holding the first chunk of the group's tile (host-made table, one entry per 512 chunks), then forward
+        int c = __ldg(&tile_contig[g >> 4]);
+        // ---- all loads of the group first (8 x 16 bytes per lane in flight), then the arithmetic -------------
+        uint4 A[4], B[4];
+        int nv[4];
+        unsigned kk[4];
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const unsigned long long chunk = g * 32 + (unsigned)it * 8u + (lane >> 2);
             while (c + 1 < n_contigs && __ldg(&chunk0[c + 1]) <= chunk) ++c;
-            int nvalid = 0;
-            const uint8_t *src = seq;
+            nv[it] = 0; kk[it] = 0;
+            A[it] = make_uint4(0, 0, 0, 0); B[it] = make_uint4(0, 0, 0, 0);
             if (c >= 0 && chunk < n_chunks) {
                 const unsigned long long base = (chunk - __ldg(&chunk0[c])) * 64ull + 16u * sub;
                 const unsigned long long o0 = __ldg(&seq_off[c]), len = __ldg(&seq_off[c + 1]) - o0;
-                if (base < len) { nvalid = (int)min(16ull, len - base); src = seq + o0 + base; }
+                if (base < len) {
+                    nv[it] = (int)min(16ull, len - base);
+                    const uint8_t *src = seq + o0 + base;
+                    const uint8_t *a0 = (const uint8_t *)((unsigned long long)src & ~15ull);
+                    kk[it] = (unsigned)((unsigned long long)src & 15ull);
+                    A[it] = ldg_nc_128(a0);
+                    // the second half is wanted only when the letters start inside the first one (and the last
+                    // contig may end in the buffer's last 16 bytes)
+                    if (kk[it]) B[it] = ldg_nc_128(a0 + 16);
+                }
             }
+        }
+        unsigned summary = 0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const unsigned long long chunk = g * 32 + (unsigned)it * 8u + (lane >> 2);
+            const int nvalid = nv[it];
             unsigned acc0 = 0, acc1 = 0;                       // letters 0..7 and 8..15: three 8-bit fields each
             if (nvalid > 0) {
-                const uint8_t *a0 = (const uint8_t *)((unsigned long long)src & ~15ull);
-                const unsigned k = (unsigned)((unsigned long long)src & 15ull);
-                const uint4 A = ldg_nc_128(a0);
-                // the second half is wanted only when the letters start inside the first one (and the last
-                // contig may end in the buffer's last 16 bytes)
-                const uint4 B = k ? ldg_nc_128(a0 + 16) : make_uint4(0, 0, 0, 0);
-                unsigned w0 = A.x, w1 = A.y, w2 = A.z, w3 = A.w, w4 = B.x, w5 = B.y, w6 = B.z, w7 = B.w;
+                const unsigned k = kk[it];
+                unsigned w0 = A[it].x, w1 = A[it].y, w2 = A[it].z, w3 = A[it].w, w4 = B[it].x, w5 = B[it].y, w6 = B[it].z, w7 = B[it].w;
                 if (k & 8u) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7; }
                 if (k & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
                 const unsigned sh = (k & 3u) * 8u;
@@ -115,14 +128,14 @@ pack_kernel(const uint8_t *__restrict__ seq, const unsigned long long *__restric
 } // namespace
 
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,
-                    const unsigned long long *d_chunk0, int n_contigs)
+                    const unsigned long long *d_chunk0, const int *d_tile_contig, int n_contigs)
 {
     const unsigned long long groups = (h->n_chunks + 31) / 32;
     unsigned long long blocks = (groups * 32 + PACK_THREADS - 1) / PACK_THREADS;
-    const unsigned long long cap = (unsigned long long)h->sm_count * 8;          // 8 resident CTAs of 256 threads per SM
+    const unsigned long long cap = (unsigned long long)h->sm_count * 8;          // resident CTAs of 256 threads per SM (registers permitting)
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    pack_kernel<<<(unsigned)blocks, PACK_THREADS, 0, h->stream>>>(d_seq, d_seq_off, d_chunk0, n_contigs,
+    pack_kernel<<<(unsigned)blocks, PACK_THREADS, 0, h->stream>>>(d_seq, d_seq_off, d_chunk0, d_tile_contig, n_contigs,
                                                                   h->n_chunks, h->d_planes, h->d_inv, h->d_invsum);
     h->timing.total_launches++;
     IGD_CUDA(cudaGetLastError());
