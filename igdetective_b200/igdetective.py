@@ -3,7 +3,7 @@ RSS scan and the candidate scoring running on the GPU.
 
     python -m igdetective_b200.igdetective -i genome.fasta -o out_dir -m 1 -l IGH [-r] [-g vdj]
 
-Outputs (byte-identical to the reference on the same input): genes_V.tsv, genes_D.tsv,
+Outputs (byte-identical to the reference run on this repository's BioPython model): genes_V.tsv, genes_D.tsv,
 genes_J.tsv, or rss_<type>.csv with -r  (py/IGDetective.py:227-255,424-436,439-487).
 Extra long options that the reference does not have: --datafiles DIR, --gene_dir NAME,
 --device N, --order reference|canonical.
@@ -248,6 +248,22 @@ def _rows_from_device(res, ids, parent_seq, canonical_genes, scan, order):
     return rows
 
 
+_GENE_TABLES = {}
+
+
+def _gene_table(genes):
+    """(uint8 buffer, int32 offsets) of a canonical-gene dict, built once per dict object (a pipeline passes the same
+    two dicts for every contig set it scores)."""
+    from .engine import concat
+    hit = _GENE_TABLES.get(id(genes))
+    if hit is None or hit[0] is not genes or hit[1] != len(genes):
+        if len(_GENE_TABLES) > 16:
+            _GENE_TABLES.clear()
+        hit = (genes, len(genes), concat(list(genes.values())))
+        _GENE_TABLES[id(genes)] = hit
+    return hit[2]
+
+
 def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=False, load=True, by_seams=False):
     """The module body of py/IGDetective.py:439-487 as a function.
     Returns (input_rss_info, {gene type: rows}) -- rows is None with rss_only.
@@ -268,7 +284,7 @@ def detect(engine, input_seq_dict, canonical_genes, order="reference", rss_only=
             else:
                 engine.load_contigs([str(input_seq_dict[c]) for c in ids], ids)
         try:
-            res = engine.detect(SPACER_LENGTH, list(canonical_genes[V].values()), list(canonical_genes[J].values()),
+            res = engine.detect(SPACER_LENGTH, _gene_table(canonical_genes[V]), _gene_table(canonical_genes[J]),
                                 gene_length=(GENE_LENGTH[V], GENE_LENGTH[J]), d_gene_length=GENE_LENGTH[D],
                                 pi_strict=(PI_CUTOFF["strict"][V], PI_CUTOFF["strict"][J]),
                                 pi_relax=(PI_CUTOFF["relax"][V], PI_CUTOFF["relax"][J]),

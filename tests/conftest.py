@@ -25,6 +25,16 @@ def _oracle_built():
         build.build()
 
 
+@pytest.fixture(autouse=True)
+def _gpu_tests_need_a_device(request):
+    """A test marked `gpu` on a machine without any CUDA device (plain `pytest tests` in the CPU container) is skipped,
+    not failed; on a GPU box the count is >= 1 and nothing is skipped."""
+    if request.node.get_closest_marker("gpu") is not None:
+        from igdetective_b200 import _lib
+        if _lib.load().igd_device_count() == 0:
+            pytest.skip("no CUDA device visible: GPU tests need a B200")
+
+
 @pytest.fixture(scope="session")
 def motifs():
     from oracle import igd_oracle
@@ -39,6 +49,10 @@ def engine(motifs):
         from igdetective_b200 import build
         build.build()
     from igdetective_b200.engine import Engine
+    if _lib.load().igd_device_count() == 0:
+        # a machine without any CUDA device (the CPU container): `pytest tests` reports skips, not errors.  On a GPU box
+        # the count is >= 1 and everything below fails loudly if the library cannot drive the device.
+        pytest.skip("no CUDA device visible: GPU tests need a B200 (run with -m 'not gpu' here)")
     e = Engine(0, motifs)
     yield e
     e.close()
