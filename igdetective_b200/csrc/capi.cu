@@ -198,10 +198,11 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
 // ---- contigs --------------------------------------------------------------------------------------
 
 // Letters -> device.  Pinned (or registered) caller memory goes in one DMA.  Pageable memory of a whole genome
-// would cross the bus at the driver's staging rate (~11 GB/s measured); instead the bytes are copied by several
-// host threads into a small ring of pinned buffers (4 x 8 MiB: pinning memory is itself slow, and several ranks
-// of one box do it at once), each followed by its own DMA, so that the memcpy of one piece overlaps the transfer
-// of the piece before it.
+// would cross the bus at the driver's staging rate (~11 GB/s measured); instead a few host threads, started once per
+// upload, each own one pinned slot of a small ring (4 x 8 MiB: pinning memory is itself slow, and several ranks of
+// one box do it at once) and walk over every fourth piece: copy the piece into the slot, queue its DMA, record the
+// slot's event, and wait for that event before the slot is written again -- so the memcpy of one thread overlaps the
+// transfers of the others.  The copies land in disjoint ranges; whatever follows on the stream is queued after the join.
 static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, size_t nbytes)
 {
     constexpr size_t PIECE = 8u << 20;
@@ -218,24 +219,30 @@ static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, siz
         IGD_CUDA(cudaMallocHost(&h->h_ring, RING * PIECE));
         for (int i = 0; i < RING; ++i) IGD_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     }
-    const unsigned nthreads = std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
-    size_t done = 0;
-    for (int i = 0; done < nbytes; ++i) {
-        const size_t n = std::min(PIECE, nbytes - done);
-        uint8_t *stage = (uint8_t *)h->h_ring + (size_t)(i % RING) * PIECE;
-        if (i >= RING) IGD_CUDA(cudaEventSynchronize(h->ring_ev[i % RING]));       // the DMA that last read this buffer
-        std::vector<std::thread> pool;
-        const size_t per = (n + nthreads - 1) / nthreads;
-        for (unsigned t = 1; t < nthreads; ++t) {
-            const size_t a = std::min(n, t * per), b = std::min(n, a + per);
-            if (b > a) pool.emplace_back([=] { memcpy(stage + a, src + done + a, b - a); });
+    const size_t n_pieces = (nbytes + PIECE - 1) / PIECE;
+    const unsigned nthreads = std::max(1u, std::min((unsigned)RING, std::thread::hardware_concurrency()));
+    cudaError_t errs[RING];
+    for (int i = 0; i < RING; ++i) errs[i] = cudaSuccess;
+    auto worker = [&](unsigned t) {
+        cudaError_t e = cudaSetDevice(h->device);
+        uint8_t *slot = (uint8_t *)h->h_ring + (size_t)t * PIECE;
+        bool used = false;
+        for (size_t i = t; i < n_pieces && e == cudaSuccess; i += nthreads) {
+            const size_t at = i * PIECE, n = std::min(PIECE, nbytes - at);
+            if (used) e = cudaEventSynchronize(h->ring_ev[t]);          // the DMA that last read this slot
+            if (e != cudaSuccess) break;
+            memcpy(slot, src + at, n);
+            e = cudaMemcpyAsync(d_dst + at, slot, n, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) e = cudaEventRecord(h->ring_ev[t], h->stream);
+            used = true;
         }
-        memcpy(stage, src + done, std::min(n, per));
-        for (auto &th : pool) th.join();
-        IGD_CUDA(cudaMemcpyAsync(d_dst + done, stage, n, cudaMemcpyHostToDevice, h->stream));
-        IGD_CUDA(cudaEventRecord(h->ring_ev[i % RING], h->stream));
-        done += n;
-    }
+        errs[t] = e;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &th : pool) th.join();
+    for (unsigned t = 0; t < nthreads; ++t) IGD_CUDA(errs[t]);
     return IGD_OK;
 }
 

@@ -82,3 +82,43 @@ def test_config5_shape_fragmented_assembly_equals_the_oracle(engine, motifs):
     assert len(want["V"]) >= 10
     for g in ("V", "D", "J"):
         assert _norm(got)[g] == _norm(want)[g], g
+
+
+def test_config4_shape_iterative_candidates_vs_all_loci_genes(engine):
+    """configs[3] scaled down: 350-nt V flanks, 70-nt J flanks and 800-nt raw-case windows against the V / J genes of
+    ALL loci of combined_reference_genes (1172 / 235 genes, mixed-case files upper-cased as the stage scripts do):
+    the float64 PI / length matrices of scoring A and the winners of scoring B against the oracle"""
+    import os
+
+    import synth
+    from conftest import DATAFILES
+    from igdetective_b200.scoring import align_fragment_to_genes, window_alignments
+    rng = np.random.default_rng(4)
+    gv, gj = [], []
+    d = os.path.join(DATAFILES, "combined_reference_genes")
+    for fn in sorted(os.listdir(d)):
+        for rid, s in O.fasta_dict(os.path.join(d, fn), upper=True).items():
+            if 0 < len(s) <= 511:
+                (gv if fn[3] == "V" else gj).append((fn[:4] + "|" + rid, s))
+    assert len(gv) > 1000 and len(gj) > 200
+
+    def bg(k):
+        return synth.background(rng, k).tobytes().decode()
+    vf = [(bg(350) + synth.mutate(rng, gv[rng.integers(len(gv))][1], 0.1, 0.01))[-350:] if i % 3 else bg(350) for i in range(24)]
+    jf = [(synth.mutate(rng, gj[rng.integers(len(gj))][1], 0.1, 0.01) + bg(70))[:70] if i % 3 else bg(70) for i in range(40)]
+    for frags, genes in ((vf, gv), (jf, gj)):
+        glist = [g[1] for g in genes]
+        pi, alen = align_fragment_to_genes(frags, glist, engine=engine)
+        wpi, wlen = O.align_fragment_to_genes(frags, glist, threads=8)
+        assert np.array_equal(pi, wpi) and np.array_equal(alen, wlen)
+    wins = []
+    for i in range(12):
+        g = gv[rng.integers(len(gv))][1]
+        w = (bg(300) + synth.mutate(rng, g, 0.1, 0.01) + bg(500))[:800]
+        if i % 2:
+            w = w[:200] + w[200:500].lower() + w[500:]
+        wins.append(O.revcomp(w) if i % 3 == 0 else w)
+    got = window_alignments(engine, wins, gv)
+    for w, (a, strand) in zip(wins, got):
+        want = O.window_best_alignment(w, gv, threads=8)
+        assert want is not None and (a.gene_seq, a.gene_id, a.pi, strand) == want
