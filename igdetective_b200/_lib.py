@@ -59,7 +59,8 @@ EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "i
            "igd_set_motifs", "igd_center_bitmap", "igd_load_contigs", "igd_scan", "igd_fetch_hits", "igd_scan_kmers",
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
            "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows",
-           "igd_detect", "igd_fetch_vj_rows", "igd_fetch_d_rows")
+           "igd_detect", "igd_fetch_vj_rows", "igd_fetch_d_rows", "igd_fasta_open_range", "igd_fasta_range",
+           "igd_fasta_header_byte")
 
 _lib = None
 
@@ -106,6 +107,12 @@ def load():
     lib.igd_fetch_d_rows.restype = ctypes.c_int
     lib.igd_fasta_open.restype = vp
     lib.igd_fasta_open.argtypes = [ctypes.c_char_p]
+    lib.igd_fasta_open_range.restype = vp
+    lib.igd_fasta_open_range.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]
+    lib.igd_fasta_range.argtypes = [vp, u64p, u64p, u64p, u64p]
+    lib.igd_fasta_range.restype = ctypes.c_int
+    lib.igd_fasta_header_byte.argtypes = [vp, i32, u64p]
+    lib.igd_fasta_header_byte.restype = ctypes.c_int
     lib.igd_fasta_close.restype = None
     lib.igd_fasta_close.argtypes = [vp]
     lib.igd_fasta_count.restype = i32

@@ -324,7 +324,16 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
 }
 
 // ---- FASTA ingest -----------------------------------------------------------------------------------
-igd_fasta *igd_fasta_open(const char *path)
+} // extern "C"
+
+// Parses the lines of the file whose first byte lies in [lo, hi), plus `margin` bytes of lines on either side when
+// `ranged` (sharded runs: the margins are the context a neighbouring range's records need, igd_fasta_open_range).
+// Parallel parse: the span is cut at line starts into one piece per thread; every piece is parsed into its own buffer
+// (letters with blanks removed + the headers it contains), then the pieces are concatenated by a parallel copy.
+// Whole-file mode: letters in front of the file's first header are dropped and ids follow the reference's dict
+// semantics.  Range mode: record 0 is the lead (the letters in front of the first header: they continue a record of an
+// earlier range), records keep file order, nothing is merged.
+static igd_fasta *fasta_parse(const char *path, uint64_t lo_req, uint64_t hi_req, uint64_t margin, bool ranged)
 {
     if (!path) { igd_set_error("null path"); return nullptr; }
     const int fd = open(path, O_RDONLY);
@@ -340,20 +349,34 @@ igd_fasta *igd_fasta_open(const char *path)
         igd_set_error("%s is gzip-compressed; igd_fasta_open reads plain FASTA", path); return nullptr;
     }
     if (fsize && madvise((void *)data, fsize, MADV_SEQUENTIAL) != 0) { /* advisory only */ }
-    // Parallel parse: the file is cut at line starts into one piece per thread; every piece is parsed
-    // into its own buffer (letters with blanks removed + the headers it contains), then the pieces are
-    // concatenated by a parallel copy.  Letters in front of the file's first header are dropped.
-    struct Hdr { std::string id; uint64_t at; };         // at = letters of the piece in front of the header
+    // first line start at or after byte p (p itself when it is 0 or follows a newline)
+    auto line_start = [&](size_t p) -> size_t {
+        if (p == 0) return 0;
+        if (p >= fsize) return fsize;
+        const char *nl = (const char *)memchr(data + p - 1, '\n', fsize - (p - 1));
+        return nl ? (size_t)(nl - data) + 1 : fsize;
+    };
+    const size_t own_lo = ranged ? line_start((size_t)std::min<uint64_t>(lo_req, fsize)) : 0;
+    const size_t own_hi = ranged ? std::max(own_lo, line_start((size_t)std::min<uint64_t>(hi_req, fsize))) : fsize;
+    const size_t ext_lo = ranged ? line_start(own_lo > margin ? own_lo - (size_t)margin : 0) : 0;
+    const size_t ext_hi = ranged ? line_start((size_t)std::min<uint64_t>((uint64_t)own_hi + margin, fsize)) : fsize;
+    struct Hdr { std::string id; uint64_t at; uint64_t byte; };     // at = letters of the piece in front of the header
     struct Piece { uint8_t *buf = nullptr; uint64_t n = 0; std::vector<Hdr> hdrs; };
-    unsigned nthreads = std::max(1u, std::min(std::min(std::thread::hardware_concurrency(), 32u), (unsigned)(fsize / (32u << 20)) + 1u));
-    std::vector<size_t> cut(nthreads + 1, fsize);
-    cut[0] = 0;
+    const size_t own_bytes = own_hi - own_lo;
+    unsigned nthreads = std::max(1u, std::min(std::min(std::thread::hardware_concurrency(), 32u), (unsigned)(own_bytes / (32u << 20)) + 1u));
+    // pieces: [pre-margin] own span in nthreads pieces [post-margin]; empty pieces are harmless
+    std::vector<size_t> cut;
+    cut.push_back(ext_lo);
+    cut.push_back(own_lo);
     for (unsigned k = 1; k < nthreads; ++k) {
-        size_t p = std::max(cut[k - 1], fsize / nthreads * k);
-        const char *nl = p < fsize ? (const char *)memchr(data + p, '\n', fsize - p) : nullptr;
-        cut[k] = nl ? (size_t)(nl - data) + 1 : fsize;
+        size_t p = std::max(cut.back(), own_lo + own_bytes / nthreads * k);
+        const char *nl = p < own_hi ? (const char *)memchr(data + p, '\n', own_hi - p) : nullptr;
+        cut.push_back(nl ? std::min((size_t)(nl - data) + 1, own_hi) : own_hi);
     }
-    std::vector<Piece> pieces(nthreads);
+    cut.push_back(own_hi);
+    cut.push_back(ext_hi);
+    const unsigned npieces = (unsigned)cut.size() - 1;
+    std::vector<Piece> pieces(npieces);
     auto blank = [](char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\v' || c == '\f'; };
     auto parse = [&](unsigned k) {
         Piece &pc = pieces[k];
@@ -368,7 +391,7 @@ igd_fasta *igd_fasta_open(const char *path)
                 while (q < le && blank(*q)) ++q;         // the id is the first token of the header
                 const char *b = q;
                 while (q < le && !blank(*q)) ++q;
-                pc.hdrs.push_back({std::string(b, q), (uint64_t)(w - pc.buf)});
+                pc.hdrs.push_back({std::string(b, q), (uint64_t)(w - pc.buf), (uint64_t)(p - data)});
             } else {
                 const char *q = p;
                 while (q < le) {                        // copy the runs between blanks
@@ -384,34 +407,43 @@ igd_fasta *igd_fasta_open(const char *path)
     };
     {
         std::vector<std::thread> th;
-        for (unsigned k = 1; k < nthreads; ++k) th.emplace_back(parse, k);
+        for (unsigned k = 1; k < npieces; ++k) th.emplace_back(parse, k);
         parse(0);
         for (auto &t : th) t.join();
     }
     if (fsize) munmap((void *)data, fsize);
-    // global letter offset of every piece; everything in front of the first header is dropped
-    unsigned first_piece = nthreads;
-    for (unsigned k = 0; k < nthreads && first_piece == nthreads; ++k) if (!pieces[k].hdrs.empty()) first_piece = k;
-    std::vector<uint64_t> base(nthreads + 1, 0), skip(nthreads, 0);
-    for (unsigned k = 0; k < nthreads; ++k) {
-        skip[k] = k < first_piece ? pieces[k].n : (k == first_piece ? pieces[k].hdrs[0].at : 0);
+    // global letter offset of every piece; whole-file mode drops everything in front of the first header
+    unsigned first_piece = npieces;
+    for (unsigned k = 0; k < npieces && first_piece == npieces; ++k) if (!pieces[k].hdrs.empty()) first_piece = k;
+    std::vector<uint64_t> base(npieces + 1, 0), skip(npieces, 0);
+    for (unsigned k = 0; k < npieces; ++k) {
+        if (!ranged) skip[k] = k < first_piece ? pieces[k].n : (k == first_piece ? pieces[k].hdrs[0].at : 0);
         base[k + 1] = base[k] + pieces[k].n - skip[k];
     }
-    const uint64_t total = base[nthreads];
-    struct Rec { std::string id; uint64_t off, len; };
+    const uint64_t total = base[npieces];
+    struct Rec { std::string id; uint64_t off, len, byte; };
     std::vector<Rec> recs;
-    for (unsigned k = first_piece; k < nthreads; ++k)
-        for (const Hdr &hd : pieces[k].hdrs) recs.push_back({hd.id, base[k] + hd.at - skip[k], 0});
+    if (ranged) recs.push_back({std::string(), 0, 0, UINT64_MAX});          // the lead
+    for (unsigned k = ranged ? 0 : first_piece; k < npieces; ++k)
+        for (const Hdr &hd : pieces[k].hdrs) recs.push_back({hd.id, base[k] + hd.at - skip[k], 0, hd.byte});
     for (size_t i = 0; i < recs.size(); ++i) recs[i].len = (i + 1 < recs.size() ? recs[i + 1].off : total) - recs[i].off;
     uint8_t *all = (uint8_t *)malloc((size_t)total + 1);
     {
         auto copy = [&](unsigned k) { memcpy(all + base[k], pieces[k].buf + skip[k], (size_t)(pieces[k].n - skip[k])); free(pieces[k].buf); };
         std::vector<std::thread> th;
-        for (unsigned k = 1; k < nthreads; ++k) th.emplace_back(copy, k);
+        for (unsigned k = 1; k < npieces; ++k) th.emplace_back(copy, k);
         copy(0);
         for (auto &t : th) t.join();
     }
     igd_fasta *f = new igd_fasta();
+    f->range_lo = own_lo; f->range_hi = own_hi;
+    f->own_lo = base[1]; f->own_hi = base[npieces - 1];
+    if (ranged) {
+        f->seq = all;
+        f->off.assign(1, 0);
+        for (const Rec &r : recs) { f->ids.push_back(r.id); f->off.push_back(r.off + r.len); f->hdr_byte.push_back(r.byte); }
+        return f;
+    }
     // dict semantics: a repeated id keeps its first position and takes the last sequence
     std::unordered_map<std::string, size_t> first;
     std::vector<size_t> order;
@@ -426,6 +458,7 @@ igd_fasta *igd_fasta_open(const char *path)
         const Rec &r = recs[order[k]];
         f->ids.push_back(r.id);
         f->off.push_back(f->off.back() + r.len);
+        f->hdr_byte.push_back(r.byte);
     }
     if (in_place) {
         f->seq = all;
@@ -436,6 +469,33 @@ igd_fasta *igd_fasta_open(const char *path)
         free(all);
     }
     return f;
+}
+
+extern "C" {
+
+igd_fasta *igd_fasta_open(const char *path) { return fasta_parse(path, 0, UINT64_MAX, 0, false); }
+
+igd_fasta *igd_fasta_open_range(const char *path, uint64_t byte_lo, uint64_t byte_hi, uint64_t margin_bytes)
+{
+    if (byte_hi < byte_lo) { igd_set_error("byte_hi < byte_lo"); return nullptr; }
+    return fasta_parse(path, byte_lo, byte_hi, margin_bytes, true);
+}
+
+int igd_fasta_range(const igd_fasta *f, uint64_t *byte_lo, uint64_t *byte_hi, uint64_t *own_lo_letter, uint64_t *own_hi_letter)
+{
+    if (!f) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (byte_lo) *byte_lo = f->range_lo;
+    if (byte_hi) *byte_hi = f->range_hi;
+    if (own_lo_letter) *own_lo_letter = f->own_lo;
+    if (own_hi_letter) *own_hi_letter = f->own_hi;
+    return IGD_OK;
+}
+
+int igd_fasta_header_byte(const igd_fasta *f, int32_t i, uint64_t *byte)
+{
+    if (!f || !byte || i < 0 || (size_t)i >= f->ids.size()) { igd_set_error("contig index out of range"); return IGD_ERR_ARG; }
+    *byte = f->hdr_byte[(size_t)i];
+    return IGD_OK;
 }
 
 void igd_fasta_close(igd_fasta *f) { delete f; }

@@ -29,6 +29,9 @@ struct igd_fasta {
     uint8_t *seq = nullptr;            // letters of all contigs, concatenated in dict order (malloc)
     std::vector<uint64_t> off;         // n + 1 offsets
     std::vector<std::string> ids;
+    std::vector<uint64_t> hdr_byte;    // file offset of each record's header line (UINT64_MAX: the lead of a range)
+    uint64_t range_lo = 0, range_hi = 0;   // igd_fasta_open_range: the line-aligned byte range that was asked for ...
+    uint64_t own_lo = 0, own_hi = 0;       // ... and the letters [own_lo, own_hi) of seq that come from it (the rest is margin)
     ~igd_fasta() { free(seq); }
 };
 

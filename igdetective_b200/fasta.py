@@ -86,13 +86,18 @@ class NativeFasta:
     {record id: ContigView} in the reference's dict order.  The letters live in host memory owned by
     the library; Engine.load_fasta(self) sends them to the GPU without a Python copy."""
 
-    def __init__(self, path):
+    def __init__(self, path, byte_range=None, margin=65536):
+        """byte_range=(lo, hi): the range form (igd_fasta_open_range) -- records in file order, record 0 the lead;
+        see RangeFasta for the bookkeeping of a sharded run."""
         import ctypes
 
         from . import _lib
         self._lib = _lib.load()
         self._ct = ctypes
-        self._f = self._lib.igd_fasta_open(str(path).encode())
+        if byte_range is None:
+            self._f = self._lib.igd_fasta_open(str(path).encode())
+        else:
+            self._f = self._lib.igd_fasta_open_range(str(path).encode(), int(byte_range[0]), int(byte_range[1]), int(margin))
         if not self._f:
             raise _lib.IgdError(_lib.IGD_ERR_ARG, self._lib.igd_last_error().decode("utf-8", "replace"))
         self.ids, self.lengths = [], []
@@ -102,6 +107,20 @@ class NativeFasta:
             self.ids.append(cid.value.decode("latin-1"))
             self.lengths.append(n.value)
         self._views = {rid: ContigView(self, i, L) for i, (rid, L) in enumerate(zip(self.ids, self.lengths))}
+        self.byte_range = None
+        if byte_range is not None:
+            lo, hi, a, b = (ctypes.c_uint64() for _ in range(4))
+            _lib.check(self._lib.igd_fasta_range(self._f, ctypes.byref(lo), ctypes.byref(hi), ctypes.byref(a), ctypes.byref(b)))
+            self.byte_range, self.own_letters = (lo.value, hi.value), (a.value, b.value)
+            self.header_bytes = []
+            hb = ctypes.c_uint64()
+            for i in range(len(self.ids)):
+                _lib.check(self._lib.igd_fasta_header_byte(self._f, i, ctypes.byref(hb)))
+                self.header_bytes.append(None if hb.value == 2 ** 64 - 1 else hb.value)
+
+    def view(self, i):
+        """record i as a str-like view (the range form has no unique ids to index by)"""
+        return ContigView(self, i, self.lengths[i])
 
     def read(self, i, start, n):
         from . import _lib

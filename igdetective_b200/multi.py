@@ -44,8 +44,32 @@ def detect_pieces(eng, seqs, ids, pieces, canonical, order="canonical", part=Non
     return out
 
 
+def detect_byte_range(eng, input_path, rank, world, canonical, group=None, margin=65536):
+    """This rank's 1/world of a plain FASTA file: it parses only the lines of its byte range (plus a margin of context
+    either side, igd_fasta_open_range), the ranks exchange what their ranges hold (shard.range_summary: a few KB,
+    one all_gather_object) to agree on the contig table, and every record of the range is loaded as a contig of its
+    own whose rows inside the range are kept.  No rank reads the whole file; the shards are balanced by bytes.
+    Returns (rows in contig coordinates, contig ids of the whole file)."""
+    import torch.distributed as dist
+    size = os.path.getsize(input_path)
+    fa = NativeFasta(input_path, byte_range=(size * rank // world, size * (rank + 1) // world), margin=margin)
+    mine = shard.range_summary(fa)
+    if world > 1:
+        summaries = [None] * world
+        dist.all_gather_object(summaries, mine, group=group)
+    else:
+        summaries = [mine]
+    ids, lens, starts = shard.contig_table(summaries)
+    pieces = shard.range_pieces(fa, ids, lens, starts[rank])
+    part = {k: fa.view(k) for k in range(len(pieces))}
+    eng.load_fasta(fa)
+    return detect_pieces(eng, None, ids, pieces, canonical, "canonical", part=part), ids
+
+
 def run_sharded(input_path, output_path, locus="IGH", datafiles=None, gene_dir="combined_reference_genes",
-                order="canonical", device=None, rank=None, world=None, group=None, tile=32_000_000):
+                order="canonical", device=None, rank=None, world=None, group=None, tile=32_000_000, byte_ranges=None):
+    """byte_ranges: every rank parses only its 1/world of the file (detect_byte_range) instead of the whole file and
+    its share of the pieces; default: on for plain FASTA files when there is more than one rank."""
     import torch.distributed as dist
     if rank is None:
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -54,12 +78,17 @@ def run_sharded(input_path, output_path, locus="IGH", datafiles=None, gene_dir="
     if order != "canonical":
         raise ValueError("sharded runs emit the canonical row order (the reference's order is a property of one "
                          "process's set iteration; use igdetective.run for byte-identical files)")
-    seqs = fasta_dict(input_path) if str(input_path).endswith(".gz") else NativeFasta(input_path)
-    ids = list(seqs.keys())
-    mine = shard.plan_pieces([len(seqs[c]) for c in ids], world, tile)[rank]
+    if byte_ranges is None:
+        byte_ranges = world > 1 and not str(input_path).endswith(".gz")
     canonical = {g: dfiles.load_canonical_genes(locus, g, gene_dir, datafiles) for g in (V, J)}
     with Engine(device, dfiles.load_motifs(datafiles)) as eng:
-        rows = detect_pieces(eng, seqs, ids, mine, canonical, order)
+        if byte_ranges:
+            rows, ids = detect_byte_range(eng, input_path, rank, world, canonical, group)
+        else:
+            seqs = fasta_dict(input_path) if str(input_path).endswith(".gz") else NativeFasta(input_path)
+            ids = list(seqs.keys())
+            mine = shard.plan_pieces([len(seqs[c]) for c in ids], world, tile)[rank]
+            rows = detect_pieces(eng, seqs, ids, mine, canonical, order)
     merged = shard.gather_rows(rows, ids, group) if world > 1 else shard.merge_rows([rows], ids)
     if merged is not None:
         os.makedirs(output_path, exist_ok=True)
@@ -80,12 +109,15 @@ def main(argv=None):
     ap.add_argument("--gene_dir", default="combined_reference_genes")
     ap.add_argument("--order", default="canonical", choices=["canonical"])
     ap.add_argument("--tile", type=int, default=32_000_000, help="contigs longer than 1.5 x this are cut into pieces")
+    ap.add_argument("--whole-file", action="store_true", help="every rank parses the whole FASTA and takes its share of the "
+                    "pieces (LPT) instead of parsing only its byte range of the file")
     a = ap.parse_args(argv)
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        run_sharded(a.input_file, a.output_directory, a.locus, a.datafiles, a.gene_dir, a.order, local, tile=a.tile)
+        run_sharded(a.input_file, a.output_directory, a.locus, a.datafiles, a.gene_dir, a.order, local, tile=a.tile,
+                    byte_ranges=False if a.whole_file else None)
     finally:
         dist.destroy_process_group()
 

@@ -80,6 +80,75 @@ def plan_pieces(lengths, world_size, tile=32_000_000, halo=512):
     return [sorted(x) for x in out]
 
 
+def range_summary(fa):
+    """What a rank tells the others about its byte range of the FASTA (fasta.NativeFasta in range form): the letters
+    of the range in front of its first header (they continue a record that began in an earlier range) and, for every
+    header inside the range, the id and the letters of that record inside the range."""
+    lo, hi = fa.byte_range
+    own_lo, own_hi = fa.own_letters
+    off = [0]
+    for n in fa.lengths:
+        off.append(off[-1] + n)
+    lead_end, recs = own_hi, []
+    for i, hb in enumerate(fa.header_bytes):
+        if hb is not None and lo <= hb < hi:
+            if not recs:
+                lead_end = off[i]
+            recs.append((fa.ids[i], min(off[i + 1], own_hi) - off[i]))
+    return {"lead": max(0, lead_end - own_lo), "recs": recs}
+
+
+def contig_table(summaries):
+    """All ranks' range_summary, in rank order -> (ids, lengths, [(contig open at the start of rank r's range or -1,
+    letters of it in front of the range)]).  Letters in front of the file's first header belong to no record (the
+    reference's reader drops them).  Record ids must be unique: the dict semantics of a repeated id (last sequence, first
+    position) cannot be kept when ranks see different parts of the file."""
+    ids, lens, starts, open_ci = [], [], [], -1
+    for s in summaries:
+        starts.append((open_ci, lens[open_ci] if open_ci >= 0 else 0))
+        if open_ci >= 0:
+            lens[open_ci] += s["lead"]
+        for rid, n in s["recs"]:
+            ids.append(rid)
+            lens.append(n)
+            open_ci = len(ids) - 1
+    if len(set(ids)) != len(ids):
+        raise ValueError("the FASTA repeats a record id: run it in one process (igdetective.run), which keeps the "
+                         "reference's dict semantics for repeated ids")
+    return ids, lens, starts
+
+
+def range_pieces(fa, ids, lens, start, halo=512):
+    """Pieces (contig, own_start, own_end, load_start, load_end) of a rank whose loaded contigs are the records of its
+    range-form FASTA `fa`, one piece per local record, in contig coordinates.  A record owns the letters it holds inside
+    the rank's range; what it holds in the margins is context.  `start` = contig_table(...)[2][rank]."""
+    index = {rid: i for i, rid in enumerate(ids)}
+    own_lo, own_hi = fa.own_letters
+    pieces, off = [], 0
+    for i, n in enumerate(fa.lengths):
+        s0, s1 = max(off, own_lo), min(off + n, own_hi)
+        if i == 0:                                  # the lead: continues the contig that is open at the range's start
+            ci, before = start
+            p0 = before - (own_lo - off)
+            if s1 <= s0 or ci < 0:
+                pieces.append((max(ci, 0), 0, 0, 0, n))
+                off += n
+                continue
+        else:
+            ci, p0 = index[fa.ids[i]], 0
+        if s1 <= s0:
+            pieces.append((ci, 0, 0, p0, p0 + n))
+        else:
+            a, b = p0 + (s0 - off), p0 + (s1 - off)
+            p1 = p0 + n
+            if (p0 > 0 and a - p0 < halo) or (p1 < lens[ci] and p1 - b < halo):
+                raise ValueError("the margin around a byte range holds fewer than %d letters of context: "
+                                 "open the ranges with a larger margin" % halo)
+            pieces.append((ci, a, b, p0, p1))
+        off += n
+    return pieces
+
+
 def own_rows(rows, piece, contig_id):
     """Rows computed on a loaded piece (coordinates relative to load_start, contig id = the piece's) -> the rows
     the piece owns, in contig coordinates.  rows: {gene type: [row]} in the layouts of genes_{V,D,J}.tsv."""

@@ -135,6 +135,19 @@ int        igd_fasta_info(const igd_fasta *f, int32_t i, const char **id, uint64
 int        igd_fasta_read(const igd_fasta *f, int32_t i, uint64_t start, uint64_t len, uint8_t *out);
 int        igd_load_fasta(igd_handle *h, const igd_fasta *f);
 
+/* Range form for sharded runs (one process per GPU, each parsing 1/N of the file): parses the LINES whose first byte
+ * lies in [byte_lo, byte_hi) -- a line belongs to the range that holds its first byte, so consecutive ranges
+ * partition the file -- plus margin_bytes of lines on either side (context for rows next to the range's ends).
+ * Record 0 is the "lead": the letters in front of the first header, which continue a record that started earlier
+ * (id ""; possibly empty); records 1.. are the headers met, in file order, nothing merged.  igd_fasta_range gives
+ * the line-aligned byte range and the letters [own_lo, own_hi) of the concatenated records that come from it (the
+ * rest is margin); igd_fasta_header_byte the file offset of a record's header line (UINT64_MAX for the lead), which
+ * says whether the header lies in the range proper.  No GPU is needed. */
+igd_fasta *igd_fasta_open_range(const char *path, uint64_t byte_lo, uint64_t byte_hi, uint64_t margin_bytes);
+int        igd_fasta_range(const igd_fasta *f, uint64_t *byte_lo, uint64_t *byte_hi,
+                           uint64_t *own_lo_letter, uint64_t *own_hi_letter);
+int        igd_fasta_header_byte(const igd_fasta *f, int32_t i, uint64_t *byte);
+
 /* find_valid_motif_idx + find_valid_rss over both strands and the four signal
  * types (py/IGDetective.py:138-177, call site :443) in one pass over the packed
  * contigs.  spacer[t] = SPACER_LENGTH of signal type t.  Hits stay on the

@@ -271,3 +271,55 @@ def test_combine_ig_genes_equals_the_reference_definition_and_golden(tmp_path):
                         os.path.join(case, "denovo_search", "predicted_genes_" + gene[:3], "genes_V.tsv"), out],
                        check=True, env=dict(os.environ, PYTHONHASHSEED="0"))
         assert open(out).read() == open(os.path.join(case, "iterative_search", gene + "_combined.fasta")).read(), gene
+
+
+def test_byte_range_reader_partitions_the_file_and_rebuilds_every_contig(tmp_path):
+    """igd_fasta_open_range + shard.range_summary / contig_table / range_pieces (the per-rank parse of a sharded run):
+    for 1..60 ranks the parts the ranks OWN, put back in contig coordinates, are exactly the records of the whole-file
+    reader -- with wrapped and unwrapped lines, CRLF, blank lines, an empty record, letters in front of the first
+    header, a header in the file's last line, ranges without any header and ranges smaller than a line."""
+    from igdetective_b200 import shard
+    from igdetective_b200.fasta import NativeFasta
+    rng = np.random.default_rng(8)
+
+    def rand(n):
+        return "".join("ACGTNacgt"[i] for i in rng.integers(0, 9, n))
+    recs = [("c%d" % i, rand(int(n))) for i, n in enumerate([5000, 0, 1, 61, 12000, 3, 700, 2500, 60, 9000])]
+    text = "ACGTAC\nGT\n"                                        # dropped: in front of the first header
+    for i, (rid, s) in enumerate(recs):
+        text += ">%s some description\n" % rid
+        w = (60, 1000000, 7)[i % 3]
+        eol = "\r\n" if i % 4 == 1 else "\n"
+        for k in range(0, len(s), w):
+            text += s[k:k + w] + eol
+        if i % 5 == 2:
+            text += "\n"
+    text += ">last_without_letters"
+    recs.append(("last_without_letters", ""))
+    path = str(tmp_path / "awkward.fa")
+    open(path, "w", newline="").write(text)
+    whole = NativeFasta(path)
+    assert [(r, str(whole[r])) for r in whole.ids] == recs
+    size = os.path.getsize(path)
+    for world in (1, 2, 3, 7, 16, 60):
+        fas = [NativeFasta(path, byte_range=(size * r // world, size * (r + 1) // world), margin=2000) for r in range(world)]
+        assert [f.byte_range[0] for f in fas[1:]] == [f.byte_range[1] for f in fas[:-1]]            # the ranges tile the file
+        ids, lens, starts = shard.contig_table([shard.range_summary(f) for f in fas])
+        assert ids == [r for r, _ in recs] and lens == [len(s) for _, s in recs], world
+        built = {r: ["?"] * len(s) for r, s in recs}
+        for r, f in enumerate(fas):
+            for k, (ci, a, b, p0, p1) in enumerate(shard.range_pieces(f, ids, lens, starts[r], halo=16)):
+                view = f.view(k)
+                assert p1 - p0 == len(view)
+                if b > a:
+                    piece = view[a - p0:b - p0]
+                    assert built[ids[ci]][a:b] == ["?"] * (b - a)                                      # owned once
+                    built[ids[ci]][a:b] = list(piece)
+                    assert str(view) == recs[ci][1][p0:p1]                                             # context = the contig's own letters
+        assert {r: "".join(v) for r, v in built.items()} == dict(recs), world
+    # a repeated id cannot be sharded by byte ranges
+    dup = str(tmp_path / "dup.fa")
+    open(dup, "w").write(">a\nACGT\n>b\nAC\n>a\nGGGG\n")
+    f = NativeFasta(dup, byte_range=(0, os.path.getsize(dup)))
+    with pytest.raises(ValueError):
+        shard.contig_table([shard.range_summary(f)])
