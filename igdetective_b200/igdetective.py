@@ -183,11 +183,10 @@ def _rows_from_device(res, ids, parent_seq, canonical_genes, scan, order):
         gene, strand, contig = (V, J)[gt], (FWD, REV)[sd], ids[ci]
         s = parent_seq[contig]
         if flen > 0:
-            frag = s[fstart:fstart + flen]
-            if strand == REV:
-                frag = reverse_complement(frag)
-            frag = frag.upper()
-            if chr(direction) == "-":
+            # the aligned orientation of the fragment: reverse-complemented once for a '-' strand RSS and once more when
+            # the reverse complement aligned better (:309-317) -- two flips cancel
+            frag = s[fstart:fstart + flen].upper()
+            if (strand == REV) != (direction == 45):                # 45 == ord('-')
                 frag = reverse_complement(frag)
             end = start + alen
             query = frag[start:ient]
