@@ -275,6 +275,9 @@ def gpu_arm(a):
         scan_samples.append(eng.timing()["scan_ms"])
     scan_ms = float(np.mean(scan_samples))
     kstat = kernel_stats(eng, seqs, canon, igdetective)
+    flush.zero_(); barrier()
+    step(False)
+    tdet = eng.timing()              # the library's CUDA-event times of one resident step (igd_detect)
     t_e2e, h2d, d2h, _ = timed(True, a.steps)
     clk = clocks.stop() if clocks else None
     # scan kernel alone at assembly scale (rank 0): the workload contig repeated, so that the fixed cost of a launch
@@ -332,10 +335,17 @@ def gpu_arm(a):
         "clocks": clk,
         "scan": {"kernel_ms": scan_ms, "gb_per_s_both_strands": n_bases / (scan_ms * 1e-3) / 1e9,
                  "hits": kstat["hits"]},
+        # the packed Gotoh kernel on ALL (candidate, gene, orientation) pairs of the step, as the matrix-returning seam
+        # align_fragment_to_genes computes them: the kernel measurement behind `roofline`
         "align": {"kernel_ms": kstat["align_ms"], "gcups": kstat["gcups"], "pairs": kstat["pairs"],
                   "cells": kstat["cells"]},
+        # what the step itself runs: LCS bounds + the alignments that can matter (exact pruning, csrc/detect.cu) + the
+        # winners' detail pass
+        "scoring_in_step": {"kernel_ms": tdet["align_ms"], "dp_cells": int(tdet["align_cells"]),
+                            "fraction_of_all_cells": tdet["align_cells"] / max(kstat["cells"], 1),
+                            "launches": int(tdet["align_launches"])},
         "kernel_share_of_step": {"rss_scan": scan_ms / (1e3 * t_dev / a.steps),
-                                 "gotoh": kstat["align_ms"] / (1e3 * t_dev / a.steps)},
+                                 "scoring_kernels": tdet["align_ms"] / (1e3 * t_dev / a.steps)},
         # dominant kernel of the step (97 % of GPU time in the ncu launch list): integer DP, bound by the
         # ALU pipe (neither HBM nor tensor); achieved = cell updates/s x ALU-pipe instructions per cell
         "roofline": {"kernel": "gotoh_packed_kernel<%s,%s>" % V_KERNEL[:2], "bound": "alu", "achieved": kstat["gcups"] * alu_per_cell / 1e3,

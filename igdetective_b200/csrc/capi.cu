@@ -626,19 +626,17 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
     uint64_t n = 0; int rc;
     if ((rc = current_count(h, &n))) return rc;
     if ((rc = pull_hits(h, n))) return rc;
-    // The raw keys sort by global heptamer position first: after that one sort the contig of a hit is found by walking
-    // the contig table forward, not by a search per hit.  The final order (contig, type, strand, index of the list's
-    // first element in scanned-strand coordinates) is a second sort of 16-byte (key, index) pairs.
-    std::sort(h->host_hits.begin(), h->host_hits.end());
+    // One pass decodes every key (contig by binary search over the chunk table) and builds a 64-bit sort key
+    // contig (26 bits) | type (2) | strand (1) | index of the list's first element in scanned-strand coordinates (35);
+    // one sort of 16-byte (key, index) pairs gives the final order.
     std::vector<igd_hit> hits(n);
-    std::vector<std::pair<std::pair<uint64_t, uint64_t>, uint32_t>> keyed(n);
-    uint32_t c = 0;
-    const uint32_t nc = (uint32_t)h->contig_chunk0.size();
+    std::vector<std::pair<uint64_t, uint32_t>> keyed(n);
+    bool fits = h->contig_chunk0.size() < (1u << 26) && n < 0xffffffffull;
     for (uint64_t i = 0; i < n; ++i) {
         const unsigned long long key = h->host_hits[i];
         const uint64_t g = key >> 8;
         const int t = (int)((key >> 4) & 3), strand = (int)((key >> 3) & 1), d = (int)(key & 3);
-        while (c + 1 < nc && h->contig_chunk0[c + 1] <= (g >> 6)) ++c;
+        const uint32_t c = contig_of(h, g >> 6);
         const int64_t hept = (int64_t)(g - h->contig_chunk0[c] * 64);
         const int s1 = h->last_spacer[t] + (d == 0 ? 0 : (d == 1 ? -1 : 1));
         const bool hept_first = (t == IGD_SIG_V || t == IGD_SIG_D_RIGHT);
@@ -652,9 +650,22 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
         igd_hit &r = hits[i];
         r.hept = hept; r.nona = nona; r.contig = c;
         r.sig_type = (uint8_t)t; r.strand = (uint8_t)strand; r.spacer = (uint8_t)s1; r.reserved = 0;
-        keyed[i] = {{((uint64_t)c << 3) | ((uint64_t)t << 1) | (uint64_t)strand, (uint64_t)scan_idx}, (uint32_t)i};
+        fits = fits && scan_idx >= 0 && scan_idx < (1ll << 35);
+        keyed[i] = {((uint64_t)c << 38) | ((uint64_t)t << 36) | ((uint64_t)strand << 35) | (uint64_t)scan_idx, (uint32_t)i};
     }
-    std::sort(keyed.begin(), keyed.end());
+    if (fits) {
+        std::sort(keyed.begin(), keyed.end());
+    } else {                                        // contigs beyond 2^35 bases or 2^26 contigs: compare field by field
+        std::sort(keyed.begin(), keyed.end(), [&](const std::pair<uint64_t, uint32_t> &x, const std::pair<uint64_t, uint32_t> &y) {
+            const igd_hit &a = hits[x.second], &b = hits[y.second];
+            if (a.contig != b.contig) return a.contig < b.contig;
+            if (a.sig_type != b.sig_type) return a.sig_type < b.sig_type;
+            if (a.strand != b.strand) return a.strand < b.strand;
+            const bool hf = (a.sig_type == IGD_SIG_V || a.sig_type == IGD_SIG_D_RIGHT);
+            const int64_t fa = hf ? a.hept : a.nona, fb = hf ? b.hept : b.nona;
+            return a.strand == 0 ? fa < fb : fa > fb;
+        });
+    }
     h->sorted_hits.resize(n);
     for (uint64_t i = 0; i < n; ++i) h->sorted_hits[i] = hits[keyed[i].second];
     h->sorted_hits_valid = true;
@@ -710,7 +721,8 @@ int igd_case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t q
 }
 extern "C" {
 
-static bool packed_scheme_ok(const igd_scoring *sc)
+} // extern "C"
+bool igd_packed_scheme_ok(const igd_scoring *sc)
 {
     const int g[] = {sc->target_internal_open, sc->target_internal_extend, sc->query_internal_open,
                      sc->query_internal_extend, sc->query_end_open, sc->query_end_extend};
@@ -718,7 +730,7 @@ static bool packed_scheme_ok(const igd_scoring *sc)
     return sc->match >= -40 && sc->match <= 40 && sc->mismatch >= -40 && sc->mismatch <= 40;
 }
 // 0: two-register kernel, 1: packed short layout, 2: packed long layout (see gotoh.cu)
-static int packed_layout_for(const igd_scoring *sc, int nA, int nB)
+int igd_packed_layout_for(const igd_scoring *sc, int nA, int nB)
 {
     if (nB > 511) return 0;                                        // 9-bit matches field
     const int hi = std::max(0, sc->match) * std::min(nA, nB);
@@ -735,6 +747,8 @@ static int packed_layout_for(const igd_scoring *sc, int nA, int nB)
     if (nA <= 1023 && hi <= 900 && lo - 2 * 40 >= -820) return 2;
     return 0;
 }
+
+extern "C" {
 
 int igd_align_batch(igd_handle *h,
                     const uint8_t *tgt, const int32_t *tgt_off, int32_t n_tgt,
@@ -765,7 +779,7 @@ int igd_align_batch(igd_handle *h,
     const size_t tbytes = (size_t)tgt_off[n_tgt], qbytes = (size_t)qry_off[n_qry];
     const int mixed = igd_case_mix(tgt, tbytes, qry, qbytes);
     const bool detail = start || ient;
-    const bool packed_ok = !detail && packed_scheme_ok(sc);
+    const bool packed_ok = !detail && igd_packed_scheme_ok(sc);
     constexpr int NB = 6;
     std::vector<int32_t> work[3][NB];                  // [kernel: 0 two-register, 1 packed short, 2 packed long][bucket]
     std::vector<int64_t> trivial;                      // empty target: closed form
@@ -781,7 +795,7 @@ int igd_align_batch(igd_handle *h,
         }
         if (nA == 0) { trivial.push_back(p); continue; }
         const int b = igd_align_bucket_of(nA);
-        int k = packed_ok ? packed_layout_for(sc, nA, nB) : 0;
+        int k = packed_ok ? igd_packed_layout_for(sc, nA, nB) : 0;
         if ((k == 1 && b > 3) || (k == 2 && b < 4)) k = 0;      // packed kernels exist for shapes 0-3 (short) and 4-5 (long)
         work[k][b].push_back((int32_t)p);
         cells += (uint64_t)nA * (uint64_t)nB;
@@ -914,7 +928,7 @@ int igd_dense_launch(igd_handle *h,
     if (n_pairs > 0x7fffffff) { igd_set_error("more than 2^31-1 pairs in one call"); return IGD_ERR_ARG; }
     int max_q = 0, min_q = 1 << 30;
     for (int q = 0; q < n_qry; ++q) { const int n = qry_off[q + 1] - qry_off[q]; max_q = std::max(max_q, n); min_q = std::min(min_q, n); }
-    bool fast = n_pairs > 0 && min_q >= 1 && max_q <= IGD_MAX_QUERY_LEN && packed_scheme_ok(sc)
+    bool fast = n_pairs > 0 && min_q >= 1 && max_q <= IGD_MAX_QUERY_LEN && igd_packed_scheme_ok(sc)
              && sc->target_end_open == sc->target_internal_open && sc->target_end_extend == sc->target_internal_extend
              && sc->target_internal_extend >= sc->target_internal_open && sc->query_internal_extend >= sc->query_internal_open
              && sc->query_end_extend >= sc->query_end_open;
@@ -927,8 +941,8 @@ int igd_dense_launch(igd_handle *h,
         if (nA == 0) continue;
         const int b = igd_align_bucket_of(nA);
         // the packed word must hold the longest and the shortest query alike
-        const int k = std::min(packed_layout_for(sc, nA, max_q), packed_layout_for(sc, nA, min_q)) == 0 ? 0
-                    : std::max(packed_layout_for(sc, nA, max_q), packed_layout_for(sc, nA, min_q));
+        const int k = std::min(igd_packed_layout_for(sc, nA, max_q), igd_packed_layout_for(sc, nA, min_q)) == 0 ? 0
+                    : std::max(igd_packed_layout_for(sc, nA, max_q), igd_packed_layout_for(sc, nA, min_q));
         if ((b <= 3 && k != 1) || (b >= 4 && k != 2)) { fast = false; break; }
         tl[b].push_back(t);
         cells += (uint64_t)nA * qsum;

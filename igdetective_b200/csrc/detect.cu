@@ -133,6 +133,196 @@ int empty_fragment_best(igd_handle *h, const uint8_t *gene, const int32_t *gene_
     return IGD_OK;
 }
 
+
+// ---- exact pruning of the scoring ---------------------------------------------------------------
+// What the stage needs per fragment is np.argmax over the genes of PI (first maximum, py/IGDetective.py:473) and that
+// gene's (PI, length) for the cut-off test (:387) -- not the whole PI matrix.  With the bound of lcs.cu,
+//     PI(f, g) <= UB(f, g) = (max(LCS(f, g), LCS(rc(f), g)) - 1) / len(g) * 100     for both orientations,
+// a gene whose UB is below the best PI found so far can neither be the first maximum nor tie with it, and a fragment
+// all of whose UBs are below the lowest cut-off yields no row whatever its argmax is.  Two rounds of the packed Gotoh
+// kernel are therefore enough: the sixteen genes with the largest UB of every fragment, then every gene with
+// UB >= thr(f), thr = the best PI of round one, or the cut-off when that best lies below it.  The threshold can only
+// rise afterwards, so nothing else is ever needed.  Rationals are compared exactly by cross-multiplication; the cut-off
+// test uses the same float64 expression as the reference (monotone in the rational, so UB bounds it too).  Rows are
+// identical to the unpruned path (tests/test_gpu_pipeline.py::test_pruned_scoring_equals_full_scoring); planted genes
+// need 1-15 of 490 alignments per orientation, background candidates (best PI ~ 54 < 60 <= UB ~ 69) need them all.
+constexpr size_t PRUNE_TOP = 16;
+struct PrunedPair { int32_t u, q0, count, slot; };           // fwd results at slot + k, reverse-complement at slot + count + k
+
+// DP over the listed (fragment, gene) pairs, both orientations; per fragment `lists[u]` must be ascending
+static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &lists, const std::vector<int32_t> &toff,
+                       const int32_t *gene_off, int32_t n_gene, const igd_scoring *sc, int mixed, Acc &acc,
+                       std::vector<Best> &best, std::vector<uint8_t> &done)
+{
+    constexpr int NB = 6;
+    const int32_t U = (int32_t)lists.size();
+    size_t n_pairs = 0;
+    for (const auto &l : lists) n_pairs += 2 * l.size();
+    if (n_pairs == 0) return IGD_OK;
+    const size_t slots = (size_t)h->sm_count * 16;
+    const int chunk = (int)std::min<size_t>(64, std::max<size_t>(1, n_pairs / (slots * 16)));
+    std::vector<int4> runs[NB];
+    std::vector<PrunedPair> pp;
+    size_t slot = 0;
+    uint64_t cells = 0;
+    for (int32_t u = 0; u < U; ++u) {
+        const std::vector<int32_t> &l = lists[(size_t)u];
+        const int nA = toff[2 * u + 1] - toff[2 * u];
+        const int b = igd_align_bucket_of(nA);
+        for (size_t i = 0; i < l.size();) {
+            int n = 1;
+            while (i + n < l.size() && n < chunk && l[i + n] == l[i] + n) ++n;
+            runs[b].push_back(make_int4(2 * u, l[i], n, (int)slot));
+            runs[b].push_back(make_int4(2 * u + 1, l[i], n, (int)(slot + n)));
+            pp.push_back({u, l[i], n, (int32_t)slot});
+            for (int k = 0; k < n; ++k) cells += 2ull * (uint64_t)nA * (uint64_t)(gene_off[l[i] + k + 1] - gene_off[l[i] + k]);
+            slot += 2 * (size_t)n;
+            i += n;
+        }
+    }
+    int rc;
+    std::vector<int4> all;
+    size_t roff[NB + 1];
+    for (int b = 0; b < NB; ++b) { roff[b] = all.size(); all.insert(all.end(), runs[b].begin(), runs[b].end()); }
+    roff[NB] = all.size();
+    if ((rc = igd_reserve(h, S_RUNS, all.size() * sizeof(int4)))) return rc;
+    if ((rc = igd_reserve(h, S_SCORE, n_pairs * 4))) return rc;
+    if ((rc = igd_reserve(h, S_PAY, n_pairs * 4))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
+    h->timing.align_launches = 0;
+    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    for (int b = 0; b < 4; ++b) {
+        if (roff[b + 1] == roff[b]) continue;
+        igd_align_job job;
+        job.d_tgt = (const uint8_t *)h->d_scratch[S_TGT]; job.d_tgt_off = (const int32_t *)h->d_scratch[S_TGTOFF];
+        job.d_qry = (const uint8_t *)h->d_scratch[S_QRY]; job.d_qry_off = (const int32_t *)h->d_scratch[S_QRYOFF];
+        job.d_pair_t = nullptr; job.d_pair_q = nullptr; job.d_work = nullptr;
+        job.d_runs = (const int4 *)h->d_scratch[S_RUNS] + roff[b];
+        job.n_work = (int32_t)(roff[b + 1] - roff[b]);
+        job.bucket = b; job.mixed_case = mixed; job.packed = 1; job.pay_mode = 0; job.sc = *sc;
+        job.d_score = (int32_t *)h->d_scratch[S_SCORE]; job.d_pay = (uint32_t *)h->d_scratch[S_PAY];
+        job.d_counter = (unsigned int *)(h->d_count + 8 + NB + b);
+        if ((rc = igd_launch_gotoh(h, job))) return rc;
+    }
+    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if ((rc = igd_stage_reserve(h, n_pairs * 4))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_PAY], n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    acc.ms += ms; acc.cells += cells; acc.launches += h->timing.align_launches;
+    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   round: %zu pairs in %zu runs (chunk %d), %.3f ms of kernels, %.1f GCUPS\n",
+                                            n_pairs, all.size(), chunk, ms, cells / (ms * 1e6));
+    const uint32_t *pay = (const uint32_t *)h->h_stage;
+    for (const PrunedPair &p : pp)
+        for (int k = 0; k < p.count; ++k) {
+            const int32_t g = p.q0 + k;
+            const uint32_t f = pay[p.slot + k], r = pay[p.slot + p.count + k];
+            const bool fwd = (f & 1023u) > (r & 1023u);
+            const uint32_t w = fwd ? f : r;
+            const int m = (int)(w & 1023u), alen = (gene_off[g + 1] - gene_off[g]) + (int)((w >> 10) & 1023u);
+            done[(size_t)p.u * n_gene + g] = 1;
+            Best &b = best[(size_t)p.u];
+            const long long l = (long long)(m - 1) * b.alen, rr = (long long)(b.matches - 1) * alen;
+            if (b.gene < 0 || l > rr || (l == rr && g < b.gene)) b = {g, m, alen, fwd ? 1 : 0};
+        }
+    return IGD_OK;
+}
+
+// best[u] = what argmax_pick_kernel would give for the fragments that can yield a row, and SOME (gene, PI below every
+// cut-off) for the others.  *applicable = false when the tables do not fit this path (the caller then scores densely).
+static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<int32_t> &toff,
+                           const uint8_t *gene, const int32_t *gene_off, int32_t n_gene,
+                           const igd_scoring *sc, const igd_detect_params *prm, int mixed, Acc &acc,
+                           std::vector<int4> &best_out, bool *applicable)
+{
+    *applicable = false;
+    const bool enabled = !(getenv("IGD_DETECT_PRUNE") && atoi(getenv("IGD_DETECT_PRUNE")) == 0);     // read per call: tests compare both
+    if (!enabled || n_gene < 64 || n_gene > 2048 || U < 1 || !igd_packed_scheme_ok(sc)) return IGD_OK;
+    if (sc->target_end_open != sc->target_internal_open || sc->target_end_extend != sc->target_internal_extend ||
+        sc->target_internal_extend < sc->target_internal_open || sc->query_internal_extend < sc->query_internal_open ||
+        sc->query_end_extend < sc->query_end_open) return IGD_OK;
+    int max_q = 0, min_q = 1 << 30;
+    for (int q = 0; q < n_gene; ++q) { const int n = gene_off[q + 1] - gene_off[q]; max_q = std::max(max_q, n); min_q = std::min(min_q, n); }
+    if (min_q < 1 || max_q > 511) return IGD_OK;
+    for (int32_t u = 0; u < U; ++u) {
+        const int nA = toff[2 * u + 1] - toff[2 * u];
+        if (nA < 1 || nA > 511 || igd_align_bucket_of(nA) > 3 || igd_packed_layout_for(sc, nA, max_q) != 1 ||
+            igd_packed_layout_for(sc, nA, min_q) != 1) return IGD_OK;
+    }
+    *applicable = true;
+    Trace tr;
+    int rc;
+    const size_t qbytes = (size_t)gene_off[n_gene];
+    if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_QRYOFF, ((size_t)n_gene + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_LCS, (size_t)2 * U * n_gene * 2))) return rc;
+    if ((rc = igd_reserve(h, S_MASKS, (size_t)n_gene * 5 * 16 * 4))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRY], gene, qbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], gene_off, ((size_t)n_gene + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    h->timing.align_launches = 0;
+    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * U,
+                             (const uint8_t *)h->d_scratch[S_QRY], (const int32_t *)h->d_scratch[S_QRYOFF], n_gene, max_q,
+                             (uint32_t *)h->d_scratch[S_MASKS], (uint16_t *)h->d_scratch[S_LCS]))) return rc;
+    const int K = (int)std::min<size_t>(PRUNE_TOP, (size_t)n_gene);
+    if ((rc = igd_reserve(h, S_UB, (size_t)U * n_gene * 2))) return rc;
+    if ((rc = igd_reserve(h, S_TOP, (size_t)U * K * 4))) return rc;
+    if ((rc = igd_launch_ub_topk(h, (const uint16_t *)h->d_scratch[S_LCS], (const int32_t *)h->d_scratch[S_QRYOFF], U, n_gene, K,
+                                 (uint16_t *)h->d_scratch[S_UB], (int32_t *)h->d_scratch[S_TOP]))) return rc;
+    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    // bounds of the better orientation (LCS; the bound on the match count is LCS - 1) and, per fragment, the K genes
+    // with the largest bounds: round one (the gene with the best PI is among the 16 largest bounds for every planted
+    // gene of the bench workload, among the 2 largest for two thirds of them)
+    std::vector<uint16_t> ub((size_t)U * n_gene);
+    std::vector<int32_t> top((size_t)U * K);
+    IGD_CUDA(cudaMemcpyAsync(ub.data(), h->d_scratch[S_UB], ub.size() * 2, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(top.data(), h->d_scratch[S_TOP], top.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    acc.ms += ms; acc.launches += h->timing.align_launches;
+    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   LCS kernels %.3f ms for %d x %d pairs\n", ms, 2 * U, n_gene);
+    tr.mark("LCS bounds + D2H");
+    std::vector<std::vector<int32_t>> lists((size_t)U);
+    for (int32_t u = 0; u < U; ++u) {
+        std::vector<int32_t> &l = lists[(size_t)u];
+        for (int k = 0; k < K; ++k) if (top[(size_t)u * K + k] >= 0) l.push_back(top[(size_t)u * K + k]);
+        std::sort(l.begin(), l.end());
+    }
+    std::vector<Best> best((size_t)U, Best{-1, 0, 1, 0});
+    std::vector<uint8_t> done((size_t)U * n_gene, 0);
+    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
+    tr.mark("round 1 (largest bounds)");
+    const double cut = std::min(prm->pi_strict[gt], prm->pi_relax[gt]);
+    size_t needed = 0, n_below = 0, n_small = 0;
+    for (int32_t u = 0; u < U; ++u) {
+        std::vector<int32_t> &l = lists[(size_t)u];
+        l.clear();
+        const Best &b = best[(size_t)u];
+        const double pi = (double)(b.matches - 1) / (double)b.alen * 100.0;
+        const bool by_best = b.gene >= 0 && pi >= cut;
+        for (int32_t g = 0; g < n_gene; ++g) {
+            if (done[(size_t)u * n_gene + g]) continue;
+            const int32_t num = (int32_t)ub[(size_t)u * n_gene + g] - 1;
+            const long long len = gene_off[g + 1] - gene_off[g];
+            const bool need = by_best ? (long long)num * b.alen >= (long long)(b.matches - 1) * len
+                                      : (double)num / (double)len * 100.0 >= cut;
+            if (need) l.push_back(g);
+        }
+        needed += l.size();
+        n_below += by_best ? 0 : 1;
+        n_small += l.size() <= 16 ? 1 : 0;
+    }
+    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   after round 1: %zu of %d fragments below the cut-off (all bounded genes needed), %zu need <= 16 genes, %zu pairs\n", n_below, U, n_small, needed);
+    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
+    tr.mark("round 2 (bounds >= threshold)");
+    best_out.resize((size_t)U);
+    for (int32_t u = 0; u < U; ++u) best_out[(size_t)u] = make_int4(best[(size_t)u].gene, best[(size_t)u].matches, best[(size_t)u].alen, best[(size_t)u].fwd);
+    return IGD_OK;
+}
+
 struct Cand { uint32_t hit; int64_t start; int32_t len; int32_t rc; };
 
 // One gene type (V or J): score the candidates cand[] against the gene table, append the winners' rows.
@@ -190,8 +380,11 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
             h->timing.total_launches++;
             IGD_CUDA(cudaGetLastError());
             tr.mark("batch tables + gather launch");
+            bool pruned = false;
+            if ((rc = best_by_pruning(h, gt, U, toff, gene, gene_off, n_gene, sc, prm, mixed, acc, best, &pruned))) return rc;
             bool launched = false;
-            if ((rc = igd_dense_launch(h, nullptr, toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, true))) return rc;
+            if (!pruned && (rc = igd_dense_launch(h, nullptr, toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, true))) return rc;
+            if (pruned) goto have_best;
             tr.mark("dense launch (host side)");
             if (!launched) {
                 igd_set_error("a (fragment, gene) pair does not fit the packed alignment kernels (gene longer than 511 or scores out of range)");
@@ -213,6 +406,7 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
             acc.ms += ms; acc.cells += h->timing.align_cells; acc.launches += h->timing.align_launches;
             tr.mark("dense kernels + argmax D2H");
         }
+have_best:
         // ---- threshold (:387) in float64, exactly as the reference evaluates it ------------------------------
         struct Win { size_t cand; Best b; };
         std::vector<Win> wins;
