@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <functional>
 #include <unordered_map>
 
 namespace {
@@ -150,15 +151,18 @@ constexpr size_t PRUNE_TOP = 16;
 struct PrunedPair { int32_t u, q0, count, slot; };           // fwd results at slot + k, reverse-complement at slot + count + k
 
 // DP over the listed (fragment, gene) pairs, both orientations; per fragment `lists[u]` must be ascending
+// after_launch (optional): more work for the stream, queued behind the round's kernels and finished by the round's
+// synchronisation; extra_stage: pinned bytes it may fill behind the round's own read-back (its argument)
 static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &lists, const std::vector<int32_t> &toff,
                        const int32_t *gene_off, int32_t n_gene, const igd_scoring *sc, int mixed, Acc &acc,
-                       std::vector<Best> &best, std::vector<uint8_t> &done)
+                       std::vector<Best> &best, std::vector<uint8_t> &done,
+                       size_t extra_stage = 0, const std::function<int(uint8_t *)> &after_launch = nullptr)
 {
     constexpr int NB = 6;
     const int32_t U = (int32_t)lists.size();
     size_t n_pairs = 0;
     for (const auto &l : lists) n_pairs += 2 * l.size();
-    if (n_pairs == 0) return IGD_OK;
+    if (n_pairs == 0 && !after_launch) return IGD_OK;
     const size_t slots = (size_t)h->sm_count * 16;
     const int chunk = (int)std::min<size_t>(64, std::max<size_t>(1, n_pairs / (slots * 16)));
     std::vector<int4> runs[NB];
@@ -188,7 +192,8 @@ static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &l
     if ((rc = igd_reserve(h, S_RUNS, all.size() * sizeof(int4)))) return rc;
     if ((rc = igd_reserve(h, S_SCORE, n_pairs * 4))) return rc;
     if ((rc = igd_reserve(h, S_PAY, n_pairs * 4))) return rc;
-    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = igd_stage_reserve(h, n_pairs * 4 + extra_stage))) return rc;
+    if (!all.empty()) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
     h->timing.align_launches = 0;
     IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -205,9 +210,9 @@ static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &l
         job.d_counter = (unsigned int *)(h->d_count + 8 + NB + b);
         if ((rc = igd_launch_gotoh(h, job))) return rc;
     }
+    if (after_launch && (rc = after_launch((uint8_t *)h->h_stage + n_pairs * 4))) return rc;
     IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
-    if ((rc = igd_stage_reserve(h, n_pairs * 4))) return rc;
-    IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_PAY], n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (n_pairs) IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_PAY], n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -285,6 +290,8 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     acc.ms += ms; acc.launches += h->timing.align_launches;
     if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   LCS kernels %.3f ms for %d x %d pairs\n", ms, 2 * U, n_gene);
     tr.mark("LCS bounds + D2H");
+    // Round one: the K largest bounds of every fragment.
+    const double cut = std::min(prm->pi_strict[gt], prm->pi_relax[gt]);
     std::vector<std::vector<int32_t>> lists((size_t)U);
     for (int32_t u = 0; u < U; ++u) {
         std::vector<int32_t> &l = lists[(size_t)u];
@@ -295,14 +302,21 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     std::vector<uint8_t> done((size_t)U * n_gene, 0);
     if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
     tr.mark("round 1 (largest bounds)");
-    const double cut = std::min(prm->pi_strict[gt], prm->pi_relax[gt]);
-    size_t needed = 0, n_below = 0, n_small = 0;
+    // Round two.  A fragment whose best PI so far reaches the cut-off needs the genes whose LCS bound reaches that PI
+    // (a few relatives).  One that stays below resembles no gene -- most candidates of a real genome -- and its LCS bounds
+    // rule out nothing ((LCS - 1) / len ~ 0.69 for unrelated DNA against a cut-off of 0.60): it gets the K5 bound against
+    // every remaining gene, queued behind this round's alignments, and round three aligns what K5 lets through.
+    const bool ybound_ok = cut >= 50.0 && !(getenv("IGD_DETECT_YBOUND") && atoi(getenv("IGD_DETECT_YBOUND")) == 0);
+    std::vector<int32_t> yslot((size_t)U, -1);
+    std::vector<int4> yruns[2];
+    size_t ywords = 0, needed = 0, n_below = 0;
+    std::vector<int32_t> below;
     for (int32_t u = 0; u < U; ++u) {
         std::vector<int32_t> &l = lists[(size_t)u];
         l.clear();
         const Best &b = best[(size_t)u];
-        const double pi = (double)(b.matches - 1) / (double)b.alen * 100.0;
-        const bool by_best = b.gene >= 0 && pi >= cut;
+        const bool by_best = b.gene >= 0 && (double)(b.matches - 1) / (double)b.alen * 100.0 >= cut;
+        if (!by_best) { ++n_below; if (ybound_ok) { below.push_back(u); continue; } }
         for (int32_t g = 0; g < n_gene; ++g) {
             if (done[(size_t)u * n_gene + g]) continue;
             const int32_t num = (int32_t)ub[(size_t)u * n_gene + g] - 1;
@@ -312,12 +326,63 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
             if (need) l.push_back(g);
         }
         needed += l.size();
-        n_below += by_best ? 0 : 1;
-        n_small += l.size() <= 16 ? 1 : 0;
     }
-    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   after round 1: %zu of %d fragments below the cut-off (all bounded genes needed), %zu need <= 16 genes, %zu pairs\n", n_below, U, n_small, needed);
-    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
-    tr.mark("round 2 (bounds >= threshold)");
+    if (!below.empty()) {
+        const size_t groups = (size_t)h->sm_count * 6 * 8;
+        const int ychunk = (int)std::min<size_t>(64, std::max<size_t>(2, below.size() * (size_t)n_gene / (groups * 4)));
+        for (int32_t u : below) {
+            const int nA = toff[2 * u + 1] - toff[2 * u];
+            yslot[(size_t)u] = (int32_t)ywords;
+            for (int32_t g = 0; g < n_gene; g += ychunk)
+                yruns[nA <= 352 ? 0 : 1].push_back(make_int4(u, g, std::min(ychunk, n_gene - g), (int)(ywords + g)));
+            ywords += (size_t)n_gene;
+        }
+    }
+    auto launch_ybound = [&](uint8_t *stage) -> int {
+        if (ywords == 0) return IGD_OK;
+        int rc2;
+        std::vector<int4> all = yruns[0];
+        all.insert(all.end(), yruns[1].begin(), yruns[1].end());
+        if ((rc2 = igd_reserve(h, S_QCLS, qbytes))) return rc2;
+        if ((rc2 = igd_reserve(h, S_YRUNS, all.size() * sizeof(int4)))) return rc2;
+        if ((rc2 = igd_reserve(h, S_Y, ywords * 4))) return rc2;
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 2 * sizeof(unsigned long long), h->stream));
+        if ((rc2 = igd_launch_gene_classes(h, (const uint8_t *)h->d_scratch[S_QRY], qbytes, (uint8_t *)h->d_scratch[S_QCLS]))) return rc2;
+        for (int shape = 0; shape < 2; ++shape)
+            if ((rc2 = igd_launch_ybound(h, shape, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF],
+                                         (const uint8_t *)h->d_scratch[S_QCLS], (const int32_t *)h->d_scratch[S_QRYOFF],
+                                         (const int4 *)h->d_scratch[S_YRUNS] + (shape ? yruns[0].size() : 0), (int)yruns[shape].size(),
+                                         (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape)))) return rc2;
+        IGD_CUDA(cudaMemcpyAsync(stage, h->d_scratch[S_Y], ywords * 4, cudaMemcpyDeviceToHost, h->stream));
+        return IGD_OK;
+    };
+    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   after round 1: %zu of %d fragments below the cut-off, %zu pairs for the others\n", n_below, U, needed);
+    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done, ywords * 4, launch_ybound))) return rc;
+    tr.mark("round 2 (LCS bounds >= best PI; K5 bounds of the fragments below the cut-off)");
+    if (ywords) {
+        const uint32_t *yb = (const uint32_t *)((const uint8_t *)h->h_stage + needed * 2 * 4);
+        size_t n_ypass = 0;
+        for (auto &l : lists) l.clear();
+        for (int32_t u : below) {
+            std::vector<int32_t> &l = lists[(size_t)u];
+            const uint32_t *y = yb + yslot[(size_t)u];
+            for (int32_t g = 0; g < n_gene; ++g) {
+                if (done[(size_t)u * n_gene + g]) continue;
+                const double len = (double)(gene_off[g + 1] - gene_off[g]);
+                if (((double)ub[(size_t)u * n_gene + g] - 1.0) / len * 100.0 < cut) continue;
+                // PI >= cut (>= 50) in either orientation needs 50 (2 m - c) >= cut len + 100 (lcs.cu, K5); the factor keeps
+                // the comparison on the safe side of the product's rounding
+                const int ymax = (int)std::max(y[g] & 0xffffu, y[g] >> 16);
+                if (50.0 * (double)ymax >= (cut * len + 100.0) * (1.0 - 1e-12)) l.push_back(g);
+            }
+            n_ypass += l.size();
+        }
+        if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   K5: %zu of %zu bounded pairs may reach the cut-off\n", n_ypass, ywords);
+        // round three reuses the pinned buffer the bounds sit in: they are consumed by now
+        if (n_ypass && (rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
+        tr.mark("round 3 (K5 bounds >= cut-off)");
+    }
     best_out.resize((size_t)U);
     for (int32_t u = 0; u < U; ++u) best_out[(size_t)u] = make_int4(best[(size_t)u].gene, best[(size_t)u].matches, best[(size_t)u].alen, best[(size_t)u].fwd);
     return IGD_OK;

@@ -1,5 +1,5 @@
-// K4: an upper bound on BioAlign.NumMatches() for every (target, gene) pair, used by igd_detect to skip alignments that
-// cannot matter.
+// K4 / K5: upper bounds on BioAlign's match count and PI for (target, gene) pairs, used by igd_detect to skip alignments
+// that cannot matter.  K4 (LCS, bit-parallel) first; K5 (a one-state DP that charges insertions, below) where K4 is too weak.
 //
 // The columns that NumMatches counts (py/extract_aligned_genes.py:33-38: equal upper-cased letters inside the gene
 // range) form a common subsequence of the upper-cased fragment and gene, whatever alignment BioPython returns, so
@@ -14,6 +14,7 @@
 // targets letter by letter (the letter is warp-uniform, so the choice of mask set is a uniform branch).
 #include "common.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -143,6 +144,113 @@ ub_topk_kernel(const uint16_t *__restrict__ lcs, const int32_t *__restrict__ qry
     }
 }
 
+// cls[i] = letter_class(qry[i]): the shift amount the bound kernel below uses for a gene letter
+__global__ void __launch_bounds__(256)
+gene_class_kernel(const uint8_t *__restrict__ qry, size_t n, uint8_t *__restrict__ cls)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        cls[i] = (uint8_t)letter_class(qry[i]);
+}
+
+// K5: Y(fragment, gene) = max over ALL alignments of  2 x (equal upper-cased letters) - (fragment letters inserted between
+// the first and the last gene letter).  For the alignment BioPython returns, with m equal columns and c inserted letters
+// inside the gene range, PI = (m - 1) / (len(gene) + c) (py/extract_aligned_genes.py:33-41, 52-53), so PI >= p with
+// p >= 1/2 gives  2 m - c >= 2 p len(gene) + 2,  hence  Y < 2 p len(gene) + 2  proves PI < p.  Unlike the LCS bound
+// ((LCS - 1) / len(gene) ~ 0.69 for unrelated DNA: useless against the 0.60 cut-off) this one charges the insertions a
+// long common subsequence needs: Y / (2 len) ~ 0.55 for unrelated pairs, and no unrelated pair of the bench workloads
+// reaches 0.60.  One DP state per cell, H(i,j) = max(H(i-1,j-1) + 2 [a_i == b_j], H(i-1,j) - 1, H(i,j-1)) with
+// H(i,0) = H(0,j) = 0 and free vertical moves in the last column (trailing fragment letters), so the answer arrives in
+// the bottom row.  Two cells per instruction: the fragment (low half) and its reverse complement (high half) against
+// the same gene share every control decision, letters are one-hot (bit class + 1 of each half), so the increment word is
+// (A >> class(b_j)) & 0x00020002 and a cell pair costs SHF + LOP3 + 2 VIADDMNMX.S16x2 -- a fifth of the Gotoh kernel per
+// alignment.  Same systolic mapping and run-mode work items as gotoh_packed_kernel: G lanes x C rows, runs of
+// consecutive genes, persistent grid.
+struct YParams {
+    const uint8_t *tgt; const int32_t *tgt_off;          // rows 2u / 2u + 1: fragment u / its reverse complement (same length)
+    const uint8_t *qcls; const int32_t *qry_off;
+    const int4 *runs; int n_runs;                        // {u, first gene, count, first output slot}
+    uint32_t *out;                                       // Y(rc) << 16 | Y(forward)
+    unsigned int *counter;
+};
+
+template <int G, int C>
+__global__ void __launch_bounds__(128, C > 16 ? 6 : 8)
+ybound_kernel(const YParams P)
+{
+    constexpr int GROUPS_PER_WARP = 32 / G;
+    const unsigned lane = threadIdx.x & 31u;
+    const int l = lane % G, grp = lane / G;
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(P.counter, (unsigned)GROUPS_PER_WARP);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= (unsigned)P.n_runs) break;
+        const bool have = base + grp < (unsigned)P.n_runs;
+        int nA = 0, nB = 1, nq = 0, out = 0, q = 0, steps = 0;
+        const uint8_t *B = P.qcls;
+        unsigned A[C], H[C];
+        if (have) {
+            const int4 run = P.runs[base + grp];
+            const int a0 = P.tgt_off[2 * run.x], a1 = P.tgt_off[2 * run.x + 1];
+            nA = a1 - a0;
+            q = run.y; nq = run.z; out = run.w;
+            const int b0 = P.qry_off[q];
+            nB = P.qry_off[q + 1] - b0;
+            B += b0;
+            steps = P.qry_off[q + nq] - b0 + G - 1;
+#pragma unroll
+            for (int r = 0; r < C; ++r) {
+                const int i = l * C + r;
+                A[r] = i < nA ? (2u << letter_class(P.tgt[a0 + i])) | (2u << (16 + letter_class(P.tgt[a1 + i]))) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < C; ++r) A[r] = 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < C; ++r) H[r] = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
+        unsigned bot = 0u, diag_top = 0u;
+        int j = 0;
+        bool active = have && nA >= 1;
+        for (int t = 0; t < steps; ++t) {
+            unsigned up = __shfl_up_sync(0xffffffffu, bot, 1, G);
+            if (active && t >= l) {
+                ++j;
+                if (l == 0) up = 0u;                                     // row 0: H(0, j) = 0
+                const unsigned sh = B[j - 1];
+                const bool lastcol = j == nB;
+                const unsigned pen = lastcol ? 0u : 0xffffffffu;         // -1 in both halves
+                unsigned dg = diag_top, u = up;
+#pragma unroll
+                for (int r = 0; r < C; ++r) {
+                    const unsigned inc = (A[r] >> sh) & 0x00020002u;
+                    const unsigned left = H[r];
+                    const unsigned v = __viaddmax_s16x2(u, pen, __viaddmax_s16x2(dg, inc, left));
+                    dg = left; H[r] = v; u = v;
+                }
+                diag_top = up;
+                bot = u;
+                if (lastcol) {
+                    if (l == G - 1) P.out[out] = u;
+                    ++out; ++q;
+                    if (--nq > 0) {
+                        B += nB;
+                        nB = P.qry_off[q + 1] - P.qry_off[q];
+                        j = 0;
+                        diag_top = 0u;
+#pragma unroll
+                        for (int r = 0; r < C; ++r) H[r] = 0u;
+                    } else {
+                        active = false;
+                    }
+                }
+            }
+        }
+    }
+}
+
 } // namespace
 
 int igd_launch_ub_topk(igd_handle *h, const uint16_t *d_lcs, const int32_t *d_qry_off, int n_unique, int n_qry, int K,
@@ -175,5 +283,90 @@ int igd_launch_lcs(igd_handle *h, const uint8_t *d_tgt, const int32_t *d_tgt_off
     IGD_CUDA(cudaGetLastError());
     h->timing.total_launches += 2;
     h->timing.align_launches += 2;
+    return IGD_OK;
+}
+
+int igd_launch_gene_classes(igd_handle *h, const uint8_t *d_qry, size_t n, uint8_t *d_cls)
+{
+    if (n == 0) return IGD_OK;
+    gene_class_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, (size_t)h->sm_count * 8), 256, 0, h->stream>>>(d_qry, n, d_cls);
+    IGD_CUDA(cudaGetLastError());
+    h->timing.total_launches++; h->timing.align_launches++;
+    return IGD_OK;
+}
+
+// out[slot + k] = Y(rc) << 16 | Y(forward) for fragment u against gene q0 + k of every run {u, q0, count, slot};
+// shape 0: fragments of at most 352 letters (16 lanes x 22 rows), 1: at most 512 (32 x 16).  *d_counter must be zero.
+int igd_launch_ybound(igd_handle *h, int shape, const uint8_t *d_tgt, const int32_t *d_tgt_off, const uint8_t *d_qcls,
+                      const int32_t *d_qry_off, const int4 *d_runs, int n_runs, uint32_t *d_out, unsigned int *d_counter)
+{
+    if (n_runs <= 0) return IGD_OK;
+    YParams P;
+    P.tgt = d_tgt; P.tgt_off = d_tgt_off; P.qcls = d_qcls; P.qry_off = d_qry_off; P.runs = d_runs; P.n_runs = n_runs;
+    P.out = d_out; P.counter = d_counter;
+    const int groups_per_cta = shape == 0 ? 128 / 16 : 128 / 32;
+    const unsigned blocks = (unsigned)std::max(1, std::min((n_runs + groups_per_cta - 1) / groups_per_cta, h->sm_count * (shape == 0 ? 6 : 8)));
+    if (shape == 0) ybound_kernel<16, 22><<<blocks, 128, 0, h->stream>>>(P);
+    else            ybound_kernel<32, 16><<<blocks, 128, 0, h->stream>>>(P);
+    IGD_CUDA(cudaGetLastError());
+    h->timing.total_launches++; h->timing.align_launches++;
+    return IGD_OK;
+}
+
+// C ABI (include/igd_b200.h): both bounds for every (fragment, gene) pair -- what igd_detect's pruning uses, exposed so
+// that the tests can hold the kernels against a plain restatement of the two recurrences.
+extern "C" int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t *tgt_off, int32_t n_frag,
+                                const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                                uint16_t *lcs, uint32_t *ybound)
+{
+    if (!h || !tgt_off || !qry_off || n_frag < 0 || n_qry < 0 || (n_frag && n_qry && (!tgt || !qry || !lcs || !ybound))) {
+        igd_set_error("bad arguments to igd_match_bounds"); return IGD_ERR_ARG;
+    }
+    if (n_frag == 0 || n_qry == 0) return IGD_OK;
+    int max_q = 0;
+    for (int q = 0; q < n_qry; ++q) {
+        const int n = qry_off[q + 1] - qry_off[q];
+        if (n < 1 || n > 511) { igd_set_error("igd_match_bounds: gene lengths must lie in 1..511"); return IGD_ERR_TOO_LONG; }
+        max_q = std::max(max_q, n);
+    }
+    std::vector<int4> runs[2];
+    for (int u = 0; u < n_frag; ++u) {
+        const int nA = tgt_off[2 * u + 1] - tgt_off[2 * u];
+        if (nA != tgt_off[2 * u + 2] - tgt_off[2 * u + 1]) { igd_set_error("igd_match_bounds: rows 2u and 2u+1 must have the same length"); return IGD_ERR_ARG; }
+        if (nA < 1 || nA > 512) { igd_set_error("igd_match_bounds: fragment lengths must lie in 1..512"); return IGD_ERR_TOO_LONG; }
+        for (int g = 0; g < n_qry; g += 64) runs[nA <= 352 ? 0 : 1].push_back(make_int4(u, g, std::min(64, n_qry - g), u * n_qry + g));
+    }
+    IGD_CUDA(cudaSetDevice(h->device));
+    const size_t tbytes = (size_t)tgt_off[2 * n_frag], qbytes = (size_t)qry_off[n_qry], cells = (size_t)n_frag * n_qry;
+    std::vector<int4> all = runs[0];
+    all.insert(all.end(), runs[1].begin(), runs[1].end());
+    int rc;
+    if ((rc = igd_reserve(h, S_TGT, tbytes))) return rc;
+    if ((rc = igd_reserve(h, S_TGTOFF, ((size_t)2 * n_frag + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_QRYOFF, ((size_t)n_qry + 1) * 4))) return rc;
+    if ((rc = igd_reserve(h, S_QCLS, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_MASKS, (size_t)n_qry * 5 * 16 * 4))) return rc;
+    if ((rc = igd_reserve(h, S_LCS, 2 * cells * 2))) return rc;
+    if ((rc = igd_reserve(h, S_YRUNS, all.size() * sizeof(int4)))) return rc;
+    if ((rc = igd_reserve(h, S_Y, cells * 4))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGT], tgt, tbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TGTOFF], tgt_off, ((size_t)2 * n_frag + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRY], qry, qbytes, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, ((size_t)n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 2 * sizeof(unsigned long long), h->stream));
+    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * n_frag,
+                             (const uint8_t *)h->d_scratch[S_QRY], (const int32_t *)h->d_scratch[S_QRYOFF], n_qry, max_q,
+                             (uint32_t *)h->d_scratch[S_MASKS], (uint16_t *)h->d_scratch[S_LCS]))) return rc;
+    if ((rc = igd_launch_gene_classes(h, (const uint8_t *)h->d_scratch[S_QRY], qbytes, (uint8_t *)h->d_scratch[S_QCLS]))) return rc;
+    for (int shape = 0; shape < 2; ++shape)
+        if ((rc = igd_launch_ybound(h, shape, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF],
+                                    (const uint8_t *)h->d_scratch[S_QCLS], (const int32_t *)h->d_scratch[S_QRYOFF],
+                                    (const int4 *)h->d_scratch[S_YRUNS] + (shape ? runs[0].size() : 0), (int)runs[shape].size(),
+                                    (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape)))) return rc;
+    IGD_CUDA(cudaMemcpyAsync(lcs, h->d_scratch[S_LCS], 2 * cells * 2, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaMemcpyAsync(ybound, h->d_scratch[S_Y], cells * 4, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaStreamSynchronize(h->stream));
     return IGD_OK;
 }

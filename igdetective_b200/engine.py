@@ -291,6 +291,26 @@ class Engine:
         self.d2h_bytes += 8 + 8 * int(nh.value) + 16 * n_cand + 8 * int(nvj.value)
         return {"hits": hits, "vj": vj, "d": d}
 
+    def match_bounds(self, fragments, genes):
+        """Upper bounds on the match count / PI of fragments[u] (and its reverse complement) against genes[g]
+        (igd_match_bounds): (lcs [U, 2, G] uint16, y [U, 2, G] uint16), index 1 = reverse complement."""
+        from .fasta import reverse_complement
+        rows = []
+        for f in fragments:
+            f = str(f).upper()
+            rows += [f, reverse_complement(f)]
+        tb, to = concat(rows)
+        qb, qo = concat(genes)
+        tb, qb = np.ascontiguousarray(tb, np.uint8), np.ascontiguousarray(qb, np.uint8)
+        to, qo = np.ascontiguousarray(to, np.int32), np.ascontiguousarray(qo, np.int32)
+        U, G = len(fragments), len(genes)
+        lcs = np.zeros((U, 2, G), np.uint16)
+        y = np.zeros((U, G), np.uint32)
+        _lib.check(self._lib.igd_match_bounds(self._h, tb.ctypes.data if tb.size else None, to.ctypes.data, U,
+                                              qb.ctypes.data if qb.size else None, qo.ctypes.data, G,
+                                              lcs.ctypes.data, y.ctypes.data))
+        return lcs, np.stack([(y & 0xffff).astype(np.uint16), (y >> 16).astype(np.uint16)], axis=1)
+
     def sync(self):
         _lib.check(self._lib.igd_sync(self._h))
 

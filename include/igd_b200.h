@@ -286,6 +286,18 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
 int igd_fetch_vj_rows(igd_handle *h, igd_vj_row *out, uint64_t capacity);
 int igd_fetch_d_rows(igd_handle *h, igd_d_row *out, uint64_t capacity);
 
+/* The two upper bounds igd_detect prunes its scoring with, for every (fragment, gene) pair -- not a reference
+ * interface: exposed so that tests can hold the bound kernels against the plain recurrences.
+ *   tgt rows 2u / 2u + 1: fragment u and its reverse complement (same length, 1..512); genes 1..511 letters.
+ *   lcs[2u + o][g]  = LCS(upper(row 2u + o), upper(gene g)) >= the equal columns of ANY alignment, i.e. >= BioAlign's
+ *                     NumMatches() + 1 (py/extract_aligned_genes.py:33-38), so PI <= (lcs - 1) / len(gene) * 100.
+ *   ybound[u][g]    = Y(row 2u + 1, g) << 16 | Y(row 2u, g),  Y = max over all alignments of 2 x equal columns - fragment
+ *                     letters inserted inside the gene range; PI >= p (p >= 50) implies Y >= p / 50 * len(gene) + 2.
+ * Letters other than A, C, G, T (either case) form one class that matches itself: still upper bounds. */
+int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t *tgt_off, int32_t n_frag,
+                     const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
+                     uint16_t *lcs, uint32_t *ybound);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,3 +199,36 @@ def gotoh_model(A, B, sc, pay_mode=0):
         Dk, Dp, Yk, Yp = nDk, nDp, nYk, nYp
     k, p = Dk[nA], Dp[nA]
     return k >> 2, p & 1023, (p >> 20) & 1023, (p >> 10) & 1023
+
+
+# ----------------------------------------------------------------------------- pruning bounds (csrc/lcs.cu)
+def _classes(s):
+    """letter classes of the bound kernels: A, C, G, T (either case) and one class for everything else"""
+    s = np.frombuffer(s.upper().encode(), np.uint8)
+    c = np.full(len(s), 4, np.int64)
+    for k, ch in enumerate(b"ACGT"):
+        c[s == ch] = k
+    return c
+
+
+def lcs_bound(a, b):
+    """K4: length of the longest common subsequence of the class strings (plain row-by-row recurrence)"""
+    ca, cb = _classes(a), _classes(b)
+    prev = np.zeros(len(cb) + 1, np.int64)
+    for x in ca:
+        t = np.maximum(prev[:-1] + (cb == x), prev[1:])
+        prev = np.concatenate([[0], np.maximum.accumulate(t)])
+    return int(prev[-1])
+
+
+def y_bound(a, b):
+    """K5: max over all alignments of 2 x equal columns - fragment letters inserted inside the gene range:
+    H(i,j) = max(H(i-1,j-1) + 2 [a_i == b_j], H(i-1,j) - [j < len(b)], H(i,j-1)), H(i,0) = H(0,j) = 0, answer H(len(a), len(b))"""
+    ca, cb = _classes(a), _classes(b)
+    pen = np.ones(len(cb), np.int64)
+    pen[-1] = 0
+    prev = np.zeros(len(cb) + 1, np.int64)
+    for x in ca:
+        t = np.maximum(prev[:-1] + 2 * (cb == x), prev[1:] - pen)
+        prev = np.concatenate([[0], np.maximum.accumulate(np.maximum(t, 0))])
+    return int(prev[-1])

@@ -125,3 +125,31 @@ def test_gotoh_model_equals_oracle(seed):
         assert lead + len(g) + intx == int(s["end"]), (a, g)
         assert intx == intx2
         assert len(a) - trail == int(s["ient"]), (a, g)
+
+
+def test_pruning_bounds_hold_for_the_oracle_alignments():
+    """csrc/lcs.cu's two recurrences bound what the aligner returns: m equal columns <= LCS and, with c letters inserted
+    inside the gene range, 2 m - c <= Y -- related, diverged and unrelated pairs, lower-case and N letters included."""
+    import synth
+    rng = np.random.default_rng(21)
+    genes = ["".join(rng.choice(list("ACGT"), n)) for n in (40, 96, 150)]
+    genes.append(genes[1][:50].lower() + genes[1][50:])
+    frags = []
+    for i in range(9):
+        g = genes[i % len(genes)].upper()
+        body = synth.mutate(rng, g, 0.05 * i, 0.02 * (i % 3)) if i % 4 else ""
+        f = "".join(rng.choice(list("ACGTN"), 60, p=[0.24, 0.24, 0.24, 0.24, 0.04])) + body + "".join(rng.choice(list("ACGT"), 30))
+        frags.append(f[-170:])
+    pt, pq = np.meshgrid(np.arange(len(frags)), np.arange(len(genes)), indexing="ij")
+    st = O.align_stats(frags, genes, pt.ravel(), pq.ravel())
+    k = 0
+    tight = 0
+    for f in frags:
+        for g in genes:
+            m, c = int(st["matches"][k]), int(st["end"][k]) - int(st["start"][k]) - len(g)
+            assert c >= 0 and m <= KM.lcs_bound(f, g), (f, g)
+            y = KM.y_bound(f, g)
+            assert 2 * m - c <= y, (f, g, m, c, y)
+            tight += 2 * m - c == y
+            k += 1
+    assert tight > 0                     # the bound is attained (closely related pairs), not vacuous
