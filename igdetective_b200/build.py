@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libigd_b200.so")
-SOURCES = ["capi.cu", "pack.cu", "rss_scan.cu", "gotoh.cu", "detect.cu", "lcs.cu"]
+SOURCES = ["capi.cu", "pack.cu", "rss_scan.cu", "gotoh.cu", "detect.cu", "lcs.cu", "hits.cu"]
 EXTRA = os.environ.get("IGD_NVCC_EXTRA", "").split()
 NVCC_FLAGS = EXTRA + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

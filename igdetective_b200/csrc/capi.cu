@@ -625,8 +625,14 @@ int igd_sorted_hits(igd_handle *h, uint64_t *n_out)
     IGD_CUDA(cudaSetDevice(h->device));
     uint64_t n = 0; int rc;
     if ((rc = current_count(h, &n))) return rc;
+    const bool on_device = !(getenv("IGD_HITS_ON_HOST") && atoi(getenv("IGD_HITS_ON_HOST")) != 0);      // read per call: tests compare both
+    if (on_device) {
+        bool done = false;
+        if ((rc = igd_sort_hits_device(h, n, &done))) return rc;
+        if (done) { h->sorted_hits_valid = true; *n_out = n; return IGD_OK; }
+    }
     if ((rc = pull_hits(h, n))) return rc;
-    // One pass decodes every key (contig by binary search over the chunk table) and builds a 64-bit sort key
+    // Host path (coordinates beyond the device's order key, or IGD_HITS_ON_HOST=1): one pass decodes every key (contig by binary search over the chunk table) and builds a 64-bit sort key
     // contig (26 bits) | type (2) | strand (1) | index of the list's first element in scanned-strand coordinates (35);
     // one sort of 16-byte (key, index) pairs gives the final order.
     std::vector<igd_hit> hits(n);

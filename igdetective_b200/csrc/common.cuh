@@ -104,7 +104,7 @@ int igd_cuda_fail(cudaError_t e, const char *what);
 
 // growable device scratch slots (capi.cu, detect.cu)
 enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK,
-       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_COUNT };
+       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_COUNT };
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
 // 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
@@ -125,10 +125,12 @@ int igd_launch_ub_topk(igd_handle *h, const uint16_t *d_lcs, const int32_t *d_qr
 int igd_launch_gene_classes(igd_handle *h, const uint8_t *d_qry, size_t n, uint8_t *d_cls);
 // Y bound (lcs.cu, K5): out[slot + k] = Y(rc) << 16 | Y(forward) per run {fragment, first gene, count, slot}
 int igd_launch_ybound(igd_handle *h, int shape, const uint8_t *d_tgt, const int32_t *d_tgt_off, const uint8_t *d_qcls,
-                      const int32_t *d_qry_off, const int4 *d_runs, int n_runs, uint32_t *d_out, unsigned int *d_counter);
+                      const int32_t *d_qry_off, const int4 *d_runs, int n_runs, uint32_t *d_out, unsigned int *d_counter,
+                      double cut, uint2 *d_pass, unsigned int *d_pass_count, unsigned int pass_cap);
 // scan + hit decoding shared by igd_scan / igd_fetch_hits / igd_detect
 int igd_run_rss_scan(igd_handle *h, const int32_t spacer[4], uint64_t *n_hits);
 int igd_sorted_hits(igd_handle *h, uint64_t *n);          // fills h->sorted_hits from the last RSS scan
+int igd_sort_hits_device(igd_handle *h, uint64_t n, bool *done);   // hits.cu: the same on the device
 
 // pack.cu
 int igd_launch_pack(igd_handle *h, const uint8_t *d_seq, const unsigned long long *d_seq_off,

@@ -328,8 +328,8 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
         needed += l.size();
     }
     if (!below.empty()) {
-        const size_t groups = (size_t)h->sm_count * 6 * 8;
-        const int ychunk = (int)std::min<size_t>(64, std::max<size_t>(2, below.size() * (size_t)n_gene / (groups * 4)));
+        const size_t groups = (size_t)h->sm_count * 4 * 8;
+        const int ychunk = (int)std::min<size_t>(64, std::max<size_t>(2, below.size() * (size_t)n_gene / (groups * 16)));   // >= 16 runs per lane group
         for (int32_t u : below) {
             const int nA = toff[2 * u + 1] - toff[2 * u];
             yslot[(size_t)u] = (int32_t)ywords;
@@ -338,46 +338,62 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
             ywords += (size_t)n_gene;
         }
     }
+    // IGD_DETECT_YPASS_CAP: tests shrink the list to exercise the overflow path
+    const unsigned pass_cap = getenv("IGD_DETECT_YPASS_CAP") ? (unsigned)std::max(1, atoi(getenv("IGD_DETECT_YPASS_CAP")))
+                                                             : (unsigned)std::max<size_t>(4096, ywords / 64);
     auto launch_ybound = [&](uint8_t *stage) -> int {
         if (ywords == 0) return IGD_OK;
         int rc2;
         std::vector<int4> all = yruns[0];
         all.insert(all.end(), yruns[1].begin(), yruns[1].end());
-        if ((rc2 = igd_reserve(h, S_QCLS, qbytes))) return rc2;
+        if ((rc2 = igd_reserve(h, S_QCLS, qbytes + 16))) return rc2;
         if ((rc2 = igd_reserve(h, S_YRUNS, all.size() * sizeof(int4)))) return rc2;
         if ((rc2 = igd_reserve(h, S_Y, ywords * 4))) return rc2;
+        if ((rc2 = igd_reserve(h, S_YPASS, (size_t)pass_cap * sizeof(uint2)))) return rc2;
         IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-        IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 2 * sizeof(unsigned long long), h->stream));
+        IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 3 * sizeof(unsigned long long), h->stream));
         if ((rc2 = igd_launch_gene_classes(h, (const uint8_t *)h->d_scratch[S_QRY], qbytes, (uint8_t *)h->d_scratch[S_QCLS]))) return rc2;
         for (int shape = 0; shape < 2; ++shape)
             if ((rc2 = igd_launch_ybound(h, shape, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF],
                                          (const uint8_t *)h->d_scratch[S_QCLS], (const int32_t *)h->d_scratch[S_QRYOFF],
                                          (const int4 *)h->d_scratch[S_YRUNS] + (shape ? yruns[0].size() : 0), (int)yruns[shape].size(),
-                                         (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape)))) return rc2;
-        IGD_CUDA(cudaMemcpyAsync(stage, h->d_scratch[S_Y], ywords * 4, cudaMemcpyDeviceToHost, h->stream));
+                                         (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape),
+                                         cut, (uint2 *)h->d_scratch[S_YPASS], (unsigned int *)(h->d_count + 34), pass_cap))) return rc2;
+        // the verdicts only: {count, pairs that may reach the cut-off}; the bounds themselves stay on the device
+        IGD_CUDA(cudaMemcpyAsync(stage, h->d_count + 34, 8, cudaMemcpyDeviceToHost, h->stream));
+        IGD_CUDA(cudaMemcpyAsync(stage + 8, h->d_scratch[S_YPASS], (size_t)pass_cap * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
         return IGD_OK;
     };
     if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   after round 1: %zu of %d fragments below the cut-off, %zu pairs for the others\n", n_below, U, needed);
-    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done, ywords * 4, launch_ybound))) return rc;
+    if ((rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done, ywords ? 8 + (size_t)pass_cap * sizeof(uint2) : 0, launch_ybound))) return rc;
     tr.mark("round 2 (LCS bounds >= best PI; K5 bounds of the fragments below the cut-off)");
     if (ywords) {
-        const uint32_t *yb = (const uint32_t *)((const uint8_t *)h->h_stage + needed * 2 * 4);
+        const uint8_t *stage = (const uint8_t *)h->h_stage + needed * 2 * 4;
+        const unsigned n_pass = *(const unsigned *)stage;
+        std::vector<uint2> pass((const uint2 *)(stage + 8), (const uint2 *)(stage + 8) + std::min(n_pass, pass_cap));
+        if (n_pass > pass_cap) {                         // more than 1 in 64 (never seen): read the bounds, test them here
+            std::vector<uint32_t> yb(ywords);
+            IGD_CUDA(cudaMemcpyAsync(yb.data(), h->d_scratch[S_Y], ywords * 4, cudaMemcpyDeviceToHost, h->stream));
+            IGD_CUDA(cudaStreamSynchronize(h->stream));
+            pass.clear();
+            for (int32_t u : below)
+                for (int32_t g = 0; g < n_gene; ++g) {
+                    const uint32_t y = yb[(size_t)yslot[(size_t)u] + g];
+                    const double len = (double)(gene_off[g + 1] - gene_off[g]);
+                    if (50.0 * (double)std::max(y & 0xffffu, y >> 16) >= (cut * len + 100.0) * (1.0 - 1e-12)) pass.push_back(make_uint2((unsigned)u, (unsigned)g));
+                }
+        }
         size_t n_ypass = 0;
         for (auto &l : lists) l.clear();
-        for (int32_t u : below) {
-            std::vector<int32_t> &l = lists[(size_t)u];
-            const uint32_t *y = yb + yslot[(size_t)u];
-            for (int32_t g = 0; g < n_gene; ++g) {
-                if (done[(size_t)u * n_gene + g]) continue;
-                const double len = (double)(gene_off[g + 1] - gene_off[g]);
-                if (((double)ub[(size_t)u * n_gene + g] - 1.0) / len * 100.0 < cut) continue;
-                // PI >= cut (>= 50) in either orientation needs 50 (2 m - c) >= cut len + 100 (lcs.cu, K5); the factor keeps
-                // the comparison on the safe side of the product's rounding
-                const int ymax = (int)std::max(y[g] & 0xffffu, y[g] >> 16);
-                if (50.0 * (double)ymax >= (cut * len + 100.0) * (1.0 - 1e-12)) l.push_back(g);
-            }
-            n_ypass += l.size();
+        for (const uint2 &p : pass) {
+            const int32_t u = (int32_t)p.x, g = (int32_t)p.y;
+            if (done[(size_t)u * n_gene + g]) continue;
+            const double len = (double)(gene_off[g + 1] - gene_off[g]);
+            if (((double)ub[(size_t)u * n_gene + g] - 1.0) / len * 100.0 < cut) continue;
+            lists[(size_t)u].push_back(g);
+            ++n_ypass;
         }
+        for (int32_t u : below) std::sort(lists[(size_t)u].begin(), lists[(size_t)u].end());
         if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   K5: %zu of %zu bounded pairs may reach the cut-off\n", n_ypass, ywords);
         // round three reuses the pinned buffer the bounds sit in: they are consumed by now
         if (n_ypass && (rc = prune_round(h, lists, toff, gene_off, n_gene, sc, mixed, acc, best, done))) return rc;
@@ -598,6 +614,9 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
     // hits are sorted by (contig, type, strand, list index): one block per contig, eight sub-lists inside
     std::vector<Cand> cand[2][2];                       // [V, J][strand]
     std::vector<igd_d_row> drows[2];
+    std::vector<std::pair<int64_t, uint32_t>> dl;           // (heptamer, list position)
+    std::vector<std::pair<uint32_t, uint32_t>> win;         // per D_right hit: its window [x, y) of dl
+    std::vector<uint32_t> sel;
     for (size_t b0 = 0; b0 < hits.size();) {
         size_t b1 = b0;
         while (b1 < hits.size() && hits[b1].contig == hits[b0].contig) ++b1;
@@ -627,19 +646,45 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
         for (int s = 0; s < 2; ++s) {
             const size_t l0 = lo[IGD_SIG_D_LEFT][s], l1 = hi[IGD_SIG_D_LEFT][s], r0 = lo[IGD_SIG_D_RIGHT][s], r1 = hi[IGD_SIG_D_RIGHT][s];
             if (l0 == l1 || r0 == r1) continue;
-            std::vector<std::pair<int64_t, uint32_t>> dl;           // (heptamer, list position)
-            for (size_t i = l0; i < l1; ++i) dl.push_back({hits[i].hept, (uint32_t)(i - l0)});
-            std::sort(dl.begin(), dl.end());
+            // D_left by heptamer, ascending: the list is ordered by its nonamers in scanned-strand coordinates, so it is
+            // (nearly) ascending on '+' and descending on '-' already
+            dl.clear();
+            if (s == 0) for (size_t i = l0; i < l1; ++i) dl.push_back({hits[i].hept, (uint32_t)(i - l0)});
+            else        for (size_t i = l1; i-- > l0;)   dl.push_back({hits[i].hept, (uint32_t)(i - l0)});
+            if (!std::is_sorted(dl.begin(), dl.end())) std::sort(dl.begin(), dl.end());
             const int64_t span = prm->d_gene_length + 7;
-            std::vector<uint32_t> sel;
+            // '+': left = dl, right = dr: dr-span <= dl <= dr-1;  '-': left = dr, right = dl: dr+1 <= dl <= dr+span.
+            // The D_right list ascends by heptamer on '+' and descends on '-': walked by ascending heptamer, both window
+            // ends only move forward (two pointers instead of two binary searches per D_right hit).
+            win.assign(r1 - r0, std::make_pair((uint32_t)0, (uint32_t)0));
+            {
+                size_t x = 0, y = 0;
+                bool ascending = true;
+                int64_t prev = INT64_MIN;
+                for (size_t n = 0; n < r1 - r0 && ascending; ++n) {
+                    const size_t k = s == 0 ? r0 + n : r1 - 1 - n;
+                    ascending = hits[k].hept >= prev; prev = hits[k].hept;
+                }
+                for (size_t n = 0; n < r1 - r0; ++n) {
+                    const size_t k = s == 0 ? r0 + n : r1 - 1 - n;
+                    const int64_t dr = hits[k].hept;
+                    const int64_t a = s == 0 ? dr - span : dr + 1, b = s == 0 ? dr - 1 : dr + span;
+                    if (ascending) {
+                        while (x < dl.size() && dl[x].first < a) ++x;
+                        if (y < x) y = x;
+                        while (y < dl.size() && dl[y].first <= b) ++y;
+                    } else {
+                        x = (size_t)(std::lower_bound(dl.begin(), dl.end(), std::make_pair(a, (uint32_t)0)) - dl.begin());
+                        y = (size_t)(std::upper_bound(dl.begin(), dl.end(), std::make_pair(b, (uint32_t)0xffffffffu)) - dl.begin());
+                    }
+                    win[k - r0] = {(uint32_t)x, (uint32_t)y};
+                }
+            }
             for (size_t k = r0; k < r1; ++k) {
-                const int64_t dr = hits[k].hept;
-                // '+': left = dl, right = dr: dr-span <= dl <= dr-1;  '-': left = dr, right = dl: dr+1 <= dl <= dr+span
-                const int64_t a = s == 0 ? dr - span : dr + 1, b = s == 0 ? dr - 1 : dr + span;
-                auto x = std::lower_bound(dl.begin(), dl.end(), std::make_pair(a, (uint32_t)0));
-                auto y = std::upper_bound(dl.begin(), dl.end(), std::make_pair(b, (uint32_t)0xffffffffu));
+                const size_t x = win[k - r0].first, y = win[k - r0].second;
+                if (x == y) continue;
                 sel.clear();
-                for (auto it = x; it != y; ++it) sel.push_back(it->second);
+                for (size_t it = x; it < y; ++it) sel.push_back(dl[it].second);
                 std::sort(sel.begin(), sel.end());
                 for (uint32_t p : sel) {
                     const igd_hit &l = hits[l0 + p];

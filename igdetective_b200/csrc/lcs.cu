@@ -161,9 +161,8 @@ gene_class_kernel(const uint8_t *__restrict__ qry, size_t n, uint8_t *__restrict
 // reaches 0.60.  One DP state per cell, H(i,j) = max(H(i-1,j-1) + 2 [a_i == b_j], H(i-1,j) - 1, H(i,j-1)) with
 // H(i,0) = H(0,j) = 0 and free vertical moves in the last column (trailing fragment letters), so the answer arrives in
 // the bottom row.  Two cells per instruction: the fragment (low half) and its reverse complement (high half) against
-// the same gene share every control decision, letters are one-hot (bit class + 1 of each half), so the increment word is
-// (A >> class(b_j)) & 0x00020002 and a cell pair costs SHF + LOP3 + 2 VIADDMNMX.S16x2 -- a fifth of the Gotoh kernel per
-// alignment.  Same systolic mapping and run-mode work items as gotoh_packed_kernel: G lanes x C rows, runs of
+// the same gene share every control decision, and a cell pair costs PRMT + 2 IMAD + VIMNMX3.S16x2 (ybound_column below)
+// against 13.8 instructions per cell of the Gotoh kernel.  Same systolic mapping and run-mode work items as gotoh_packed_kernel: G lanes x C rows, runs of
 // consecutive genes, persistent grid.
 struct YParams {
     const uint8_t *tgt; const int32_t *tgt_off;          // rows 2u / 2u + 1: fragment u / its reverse complement (same length)
@@ -171,29 +170,56 @@ struct YParams {
     const int4 *runs; int n_runs;                        // {u, first gene, count, first output slot}
     uint32_t *out;                                       // Y(rc) << 16 | Y(forward)
     unsigned int *counter;
+    // optional: the pairs whose bound reaches the cut-off, as {fragment, gene}, appended in no particular order
+    double cut; uint2 *pass; unsigned int *pass_count; unsigned int pass_cap;
+    int one;                                             // 1, opaque to the compiler: x * one + y is an IMAD
 };
 
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// The K5 recurrence in the ROW FRAME: every value of row i is stored plus i, so the vertical move (score - 1) is the
+// stored value of the row above unchanged, the diagonal move carries + 1 on top of its 2 [match], and a cell is
+// max3(diag + inc, up + pen, left).  Per cell pair: PRMT (increment look-up: the row's four bytes per orientation, 3 where
+// the row letter is that class and 1 elsewhere, selected by the column's class; the upper byte of each half comes from
+// the selector's sign-replication mode and is zero), one IMAD (an add of packed halves, on the FMA pipe) and one
+// VIMNMX3.S16x2 that updates the row's value in place (in the gene's last column, where the vertical move is free, the
+// row above enters with + 1 per half: a second copy of the loop, taken once per gene).  The diagonal term of the NEXT column, M = H(i-1, j) + inc(j + 1),
+// is formed while H(i-1, j) is at hand (the gene letters are read one column ahead), so no state needs a second live
+// copy and the loop has no register moves.  A gene letter that is none of A, C, G, T selects zero bytes (a diagonal move worth one less than a mismatch,
+// never more than one below the true recurrence per such column) and 3 per such letter is added to the result -- its
+// possible match and that one -- which keeps the bound a bound.
+__device__ __forceinline__ unsigned ybound_selector(unsigned c) { return c < 4u ? 0x8480u + 0x0101u * c : 0x8888u; }   // bytes Af[c], 0, Ar[c], 0
+
 template <int G, int C>
-__global__ void __launch_bounds__(128, C > 16 ? 6 : 8)
+__global__ void __launch_bounds__(128, C > 16 ? 4 : 5)
 ybound_kernel(const YParams P)
 {
     constexpr int GROUPS_PER_WARP = 32 / G;
     const unsigned lane = threadIdx.x & 31u;
     const int l = lane % G, grp = lane / G;
+    const unsigned one = (unsigned)P.one;
+    const unsigned row0 = (unsigned)(l * C) * 0x00010001u;                  // frame offset of the row above this lane's first
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(P.counter, (unsigned)GROUPS_PER_WARP);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= (unsigned)P.n_runs) break;
         const bool have = base + grp < (unsigned)P.n_runs;
-        int nA = 0, nB = 1, nq = 0, out = 0, q = 0, steps = 0;
+        int nA = 0, nB = 1, nq = 0, out = 0, q = 0, steps = 0, frag = 0;
         const uint8_t *B = P.qcls;
-        unsigned A[C], H[C];
+        unsigned Af[C], Ar[C], H[C], M[C];
+#pragma unroll
+        for (int r = 0; r < C; ++r) Af[r] = Ar[r] = 0x01010101u;
         if (have) {
             const int4 run = P.runs[base + grp];
             const int a0 = P.tgt_off[2 * run.x], a1 = P.tgt_off[2 * run.x + 1];
             nA = a1 - a0;
-            q = run.y; nq = run.z; out = run.w;
+            q = run.y; nq = run.z; out = run.w; frag = run.x;
             const int b0 = P.qry_off[q];
             nB = P.qry_off[q + 1] - b0;
             B += b0;
@@ -201,47 +227,80 @@ ybound_kernel(const YParams P)
 #pragma unroll
             for (int r = 0; r < C; ++r) {
                 const int i = l * C + r;
-                A[r] = i < nA ? (2u << letter_class(P.tgt[a0 + i])) | (2u << (16 + letter_class(P.tgt[a1 + i]))) : 0u;
+                if (i < nA) {
+                    const int cf = letter_class(P.tgt[a0 + i]), cr = letter_class(P.tgt[a1 + i]);
+                    Af[r] = cf < 4 ? 0x01010101u + (2u << (8 * cf)) : 0x03030303u;   // other letters: taken to match every column
+                    Ar[r] = cr < 4 ? 0x01010101u + (2u << (8 * cr)) : 0x03030303u;
+                }
             }
-        } else {
+        }
+        unsigned c_cur = have ? B[0] : 0u, c_pref = have ? B[1] : 0u;
+        {
+            const unsigned sel = ybound_selector(c_cur);
 #pragma unroll
-            for (int r = 0; r < C; ++r) A[r] = 0u;
+            for (int r = 0; r < C; ++r) {
+                H[r] = row0 + (unsigned)(r + 1) * 0x00010001u;                       // column 0: H = 0
+                M[r] = row0 + (unsigned)r * 0x00010001u + prmt(Af[r], Ar[r], sel);
+            }
         }
 #pragma unroll
-        for (int r = 0; r < C; ++r) H[r] = 0u;
-#pragma unroll
         for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, o));
-        unsigned bot = 0u, diag_top = 0u;
+        unsigned bot = 0u, other = 0u;
         int j = 0;
         bool active = have && nA >= 1;
         for (int t = 0; t < steps; ++t) {
             unsigned up = __shfl_up_sync(0xffffffffu, bot, 1, G);
             if (active && t >= l) {
                 ++j;
-                if (l == 0) up = 0u;                                     // row 0: H(0, j) = 0
-                const unsigned sh = B[j - 1];
+                if (l == 0) up = 0u;                                     // row 0: H(0, j) = 0, frame offset 0
                 const bool lastcol = j == nB;
-                const unsigned pen = lastcol ? 0u : 0xffffffffu;         // -1 in both halves
-                unsigned dg = diag_top, u = up;
+                const unsigned c_next = c_pref;                          // read one step ago: the load is off the critical path
+                c_pref = B[j + 1];                                       // (the table has spare bytes at its end)
+                const unsigned sel = ybound_selector(c_next);
+                other += c_cur < 4u ? 0u : 0x00030003u;
+                c_cur = c_next;
+                unsigned uprev = up;
+                if (!lastcol) {
 #pragma unroll
-                for (int r = 0; r < C; ++r) {
-                    const unsigned inc = (A[r] >> sh) & 0x00020002u;
-                    const unsigned left = H[r];
-                    const unsigned v = __viaddmax_s16x2(u, pen, __viaddmax_s16x2(dg, inc, left));
-                    dg = left; H[r] = v; u = v;
+                    for (int r = 0; r < C; ++r) {
+                        H[r] = __vimax3_s16x2(M[r], uprev, H[r]);
+                        M[r] = uprev * one + prmt(Af[r], Ar[r], sel);
+                        uprev = H[r];
+                    }
+                } else {                                                 // the vertical move is free: + 1 per half in the frame
+#pragma unroll
+                    for (int r = 0; r < C; ++r) {
+                        H[r] = __vimax3_s16x2(M[r], uprev + 0x00010001u, H[r]);
+                        M[r] = uprev * one + prmt(Af[r], Ar[r], sel);
+                        uprev = H[r];
+                    }
                 }
-                diag_top = up;
-                bot = u;
+                bot = uprev;
                 if (lastcol) {
-                    if (l == G - 1) P.out[out] = u;
+                    if (l == G - 1) {
+                        const unsigned y = uprev - (unsigned)(G * C) * 0x00010001u + other;      // out of the row frame
+                        P.out[out] = y;
+                        if (P.pass) {
+                            // PI >= cut (>= 50) in either orientation needs 50 Y >= cut len + 100; the factor keeps the
+                            // comparison on the safe side of the product's rounding
+                            const double ymax = (double)max(y & 0xffffu, y >> 16);
+                            if (50.0 * ymax >= (P.cut * (double)nB + 100.0) * (1.0 - 1e-12)) {
+                                const unsigned k = atomicAdd(P.pass_count, 1u);
+                                if (k < P.pass_cap) P.pass[k] = make_uint2((unsigned)frag, (unsigned)q);
+                            }
+                        }
+                    }
                     ++out; ++q;
+                    other = 0u;
                     if (--nq > 0) {
                         B += nB;
                         nB = P.qry_off[q + 1] - P.qry_off[q];
                         j = 0;
-                        diag_top = 0u;
 #pragma unroll
-                        for (int r = 0; r < C; ++r) H[r] = 0u;
+                        for (int r = 0; r < C; ++r) {
+                            H[r] = row0 + (unsigned)(r + 1) * 0x00010001u;
+                            M[r] = row0 + (unsigned)r * 0x00010001u + prmt(Af[r], Ar[r], sel);   // sel: the next gene's first letter
+                        }
                     } else {
                         active = false;
                     }
@@ -298,14 +357,16 @@ int igd_launch_gene_classes(igd_handle *h, const uint8_t *d_qry, size_t n, uint8
 // out[slot + k] = Y(rc) << 16 | Y(forward) for fragment u against gene q0 + k of every run {u, q0, count, slot};
 // shape 0: fragments of at most 352 letters (16 lanes x 22 rows), 1: at most 512 (32 x 16).  *d_counter must be zero.
 int igd_launch_ybound(igd_handle *h, int shape, const uint8_t *d_tgt, const int32_t *d_tgt_off, const uint8_t *d_qcls,
-                      const int32_t *d_qry_off, const int4 *d_runs, int n_runs, uint32_t *d_out, unsigned int *d_counter)
+                      const int32_t *d_qry_off, const int4 *d_runs, int n_runs, uint32_t *d_out, unsigned int *d_counter,
+                      double cut, uint2 *d_pass, unsigned int *d_pass_count, unsigned int pass_cap)
 {
     if (n_runs <= 0) return IGD_OK;
     YParams P;
     P.tgt = d_tgt; P.tgt_off = d_tgt_off; P.qcls = d_qcls; P.qry_off = d_qry_off; P.runs = d_runs; P.n_runs = n_runs;
     P.out = d_out; P.counter = d_counter;
+    P.cut = cut; P.pass = d_pass; P.pass_count = d_pass_count; P.pass_cap = pass_cap; P.one = 1;
     const int groups_per_cta = shape == 0 ? 128 / 16 : 128 / 32;
-    const unsigned blocks = (unsigned)std::max(1, std::min((n_runs + groups_per_cta - 1) / groups_per_cta, h->sm_count * (shape == 0 ? 6 : 8)));
+    const unsigned blocks = (unsigned)std::max(1, std::min((n_runs + groups_per_cta - 1) / groups_per_cta, h->sm_count * (shape == 0 ? 4 : 5)));
     if (shape == 0) ybound_kernel<16, 22><<<blocks, 128, 0, h->stream>>>(P);
     else            ybound_kernel<32, 16><<<blocks, 128, 0, h->stream>>>(P);
     IGD_CUDA(cudaGetLastError());
@@ -345,7 +406,7 @@ extern "C" int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t
     if ((rc = igd_reserve(h, S_TGTOFF, ((size_t)2 * n_frag + 1) * 4))) return rc;
     if ((rc = igd_reserve(h, S_QRY, qbytes))) return rc;
     if ((rc = igd_reserve(h, S_QRYOFF, ((size_t)n_qry + 1) * 4))) return rc;
-    if ((rc = igd_reserve(h, S_QCLS, qbytes))) return rc;
+    if ((rc = igd_reserve(h, S_QCLS, qbytes + 16))) return rc;
     if ((rc = igd_reserve(h, S_MASKS, (size_t)n_qry * 5 * 16 * 4))) return rc;
     if ((rc = igd_reserve(h, S_LCS, 2 * cells * 2))) return rc;
     if ((rc = igd_reserve(h, S_YRUNS, all.size() * sizeof(int4)))) return rc;
@@ -364,7 +425,7 @@ extern "C" int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t
         if ((rc = igd_launch_ybound(h, shape, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF],
                                     (const uint8_t *)h->d_scratch[S_QCLS], (const int32_t *)h->d_scratch[S_QRYOFF],
                                     (const int4 *)h->d_scratch[S_YRUNS] + (shape ? runs[0].size() : 0), (int)runs[shape].size(),
-                                    (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape)))) return rc;
+                                    (uint32_t *)h->d_scratch[S_Y], (unsigned int *)(h->d_count + 32 + shape), 0.0, nullptr, nullptr, 0))) return rc;
     IGD_CUDA(cudaMemcpyAsync(lcs, h->d_scratch[S_LCS], 2 * cells * 2, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaMemcpyAsync(ybound, h->d_scratch[S_Y], cells * 4, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));

@@ -293,7 +293,8 @@ int igd_fetch_d_rows(igd_handle *h, igd_d_row *out, uint64_t capacity);
  *                     NumMatches() + 1 (py/extract_aligned_genes.py:33-38), so PI <= (lcs - 1) / len(gene) * 100.
  *   ybound[u][g]    = Y(row 2u + 1, g) << 16 | Y(row 2u, g),  Y = max over all alignments of 2 x equal columns - fragment
  *                     letters inserted inside the gene range; PI >= p (p >= 50) implies Y >= p / 50 * len(gene) + 2.
- * Letters other than A, C, G, T (either case) form one class that matches itself: still upper bounds. */
+ * Letters other than A, C, G, T (either case): one class that matches itself in the LCS; in Y such a fragment letter
+ * matches every A, C, G, T and such a gene letter adds 3 (tests/kernel_model.py:y_bound) -- still upper bounds. */
 int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t *tgt_off, int32_t n_frag,
                      const uint8_t *qry, const int32_t *qry_off, int32_t n_qry,
                      uint16_t *lcs, uint32_t *ybound);

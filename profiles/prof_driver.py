@@ -1,5 +1,5 @@
 """Small driver for ncu captures: runs only the scan kernel or only the Gotoh kernel on the bench
-workload.  usage: python profiles/prof_driver.py scan|align [mbases] [iters]"""
+workload.  usage: python profiles/prof_driver.py scan|align|windows|bounds [mbases] [iters]"""
 import os
 import sys
 
@@ -23,6 +23,20 @@ if what == "scan":
     for _ in range(iters):
         n = eng.scan_rss_count(SPACER_LENGTH)
         print("hits", n, eng.timing()["scan_ms"], "ms")
+elif what == "bounds":
+    import time
+    import synth
+    rng = np.random.default_rng(5)
+    genes = list(canon["V"].values())
+    frags = [synth.background(rng, 350).tobytes().decode() for _ in range(int(mbases))]   # here: number of unrelated 350-nt fragments
+    for _ in range(iters):
+        eng.sync()
+        t0 = time.perf_counter()
+        lcs, y = eng.match_bounds(frags, genes)
+        dt = time.perf_counter() - t0
+        glen = np.array([len(g) for g in genes])
+        print("bounds: %d x %d pairs in %.2f ms (both kernels + copies); (LCS - 1) / len mean %.3f, Y / (2 len) mean %.3f max %.3f"
+              % (len(frags), len(genes), dt * 1e3, ((lcs - 1) / glen).mean(), (y / (2.0 * glen)).mean(), (y / (2.0 * glen)).max()))
 elif what == "windows":
     import synth
     rng = np.random.default_rng(1)

@@ -222,13 +222,18 @@ def lcs_bound(a, b):
 
 
 def y_bound(a, b):
-    """K5: max over all alignments of 2 x equal columns - fragment letters inserted inside the gene range:
-    H(i,j) = max(H(i-1,j-1) + 2 [a_i == b_j], H(i-1,j) - [j < len(b)], H(i,j-1)), H(i,0) = H(0,j) = 0, answer H(len(a), len(b))"""
+    """K5: max over all alignments of 2 x equal columns - fragment letters inserted inside the gene range, as the kernel
+    states it: H(i,j) = max(H(i-1,j-1) + 2 [a_i ~ b_j], H(i-1,j) - [j < len(b)], H(i,j-1)), H(i,0) = H(0,j) = 0, answer
+    H(len(a), len(b)) + 3 x (gene letters outside ACGT).  a_i ~ b_j: equal classes, or a_i outside ACGT (taken to match
+    every A, C, G, T); a gene letter outside ACGT matches nothing and its diagonal move costs 1 -- the + 3 covers its
+    possible match and that 1, so the value is >= the plain recurrence in which such letters match each other."""
     ca, cb = _classes(a), _classes(b)
     pen = np.ones(len(cb), np.int64)
     pen[-1] = 0
+    other = cb == 4
     prev = np.zeros(len(cb) + 1, np.int64)
     for x in ca:
-        t = np.maximum(prev[:-1] + 2 * (cb == x), prev[1:] - pen)
+        eq = ((cb == x) | (x == 4)) & ~other
+        t = np.maximum(prev[:-1] + 2 * eq - other, prev[1:] - pen)
         prev = np.concatenate([[0], np.maximum.accumulate(np.maximum(t, 0))])
-    return int(prev[-1])
+    return int(prev[-1]) + 3 * int(other.sum())

@@ -134,6 +134,7 @@ def test_pruning_bounds_hold_for_the_oracle_alignments():
     rng = np.random.default_rng(21)
     genes = ["".join(rng.choice(list("ACGT"), n)) for n in (40, 96, 150)]
     genes.append(genes[1][:50].lower() + genes[1][50:])
+    genes.append(genes[2][:70] + "NNR" + genes[2][73:])
     frags = []
     for i in range(9):
         g = genes[i % len(genes)].upper()
