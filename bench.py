@@ -343,7 +343,14 @@ def gpu_arm(a):
         # winners' detail pass
         "scoring_in_step": {"kernel_ms": tdet["align_ms"], "dp_cells": int(tdet["align_cells"]),
                             "fraction_of_all_cells": tdet["align_cells"] / max(kstat["cells"], 1),
-                            "launches": int(tdet["align_launches"])},
+                            "launches": int(tdet["align_launches"]),
+                            # how the kernel time splits: Gotoh kernels (small batches: three rounds + the winners' detail
+                            # pass), K4 = LCS bound + top-K, K5 = insertion-charging bound of the fragments that resemble no gene
+                            "gotoh_ms": tdet["dp_ms"], "gotoh_gcups": tdet["align_cells"] / max(tdet["dp_ms"], 1e-6) / 1e6,
+                            "k4_lcs_ms": tdet["lcs_ms"], "k4_letter_pairs": int(tdet["lcs_cells"]),
+                            "k4_tera_letter_pairs_per_s": tdet["lcs_cells"] / max(tdet["lcs_ms"], 1e-6) / 1e9,
+                            "k5_ms": tdet["k5_ms"], "k5_letter_pairs": int(tdet["k5_cells"]),
+                            "k5_tera_letter_pairs_per_s": tdet["k5_cells"] / max(tdet["k5_ms"], 1e-6) / 1e9},
         "kernel_share_of_step": {"rss_scan": scan_ms / (1e3 * t_dev / a.steps),
                                  "scoring_kernels": tdet["align_ms"] / (1e3 * t_dev / a.steps)},
         # dominant kernel of the step (97 % of GPU time in the ncu launch list): integer DP, bound by the

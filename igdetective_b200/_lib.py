@@ -46,7 +46,9 @@ class Timing(ctypes.Structure):
     _fields_ = [("pack_ms", ctypes.c_float), ("scan_ms", ctypes.c_float), ("align_ms", ctypes.c_float),
                 ("scan_launches", ctypes.c_uint32), ("align_launches", ctypes.c_uint32),
                 ("scan_bases", ctypes.c_uint64), ("align_cells", ctypes.c_uint64),
-                ("total_launches", ctypes.c_uint64)]
+                ("total_launches", ctypes.c_uint64),
+                ("dp_ms", ctypes.c_float), ("lcs_ms", ctypes.c_float), ("k5_ms", ctypes.c_float), ("reserved_f", ctypes.c_float),
+                ("lcs_cells", ctypes.c_uint64), ("k5_cells", ctypes.c_uint64)]
 
 
 class IgdError(RuntimeError):

@@ -72,7 +72,7 @@ igd_handle *igd_create(int device)
     h->device = device;
     h->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
-           && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess
+           && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess && cudaEventCreate(&h->ev2) == cudaSuccess
            && cudaMalloc(&h->d_count, 64 * sizeof(unsigned long long)) == cudaSuccess
            && cudaMalloc(&h->d_lut7, 16384) == cudaSuccess && cudaMalloc(&h->d_lut9, 262144) == cudaSuccess
            && cudaMalloc(&h->d_any9, 32768) == cudaSuccess && cudaMalloc(&h->d_any9c, 32768) == cudaSuccess && cudaMalloc(&h->d_need7, 16384) == cudaSuccess && cudaMalloc(&h->d_any7, 2048) == cudaSuccess;
@@ -94,6 +94,7 @@ void igd_destroy(igd_handle *h)
     if (h->h_ring) { cudaFreeHost(h->h_ring); for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ring_ev[i]); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

@@ -38,7 +38,7 @@ struct igd_fasta {
 struct igd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     int sm_count = 148;
     bool fp_increment_ok = false;  // exact denormal arithmetic verified on this device (gotoh.cu, FPINC)
 

@@ -101,7 +101,7 @@ struct SliceKey {
 struct SliceHash {
     size_t operator()(const SliceKey &k) const { return (size_t)(k.g0 * 0x9E3779B97F4A7C15ull) ^ ((size_t)k.len << 1) ^ (size_t)k.rc; }
 };
-struct Acc { float ms = 0.f; uint64_t cells = 0; unsigned launches = 0; };
+struct Acc { float ms = 0.f; uint64_t cells = 0; unsigned launches = 0; float lcs_ms = 0.f, k5_ms = 0.f; uint64_t lcs_cells = 0, k5_cells = 0; };
 
 // the 'A' * len(gene) stand-in of an empty fragment (py/IGDetective.py:339-340), per gene: pick word as in
 // pick_orientation_kernel (host pair-table path: a few hundred short pairs, and only when an empty fragment exists)
@@ -210,15 +210,18 @@ static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &l
         job.d_counter = (unsigned int *)(h->d_count + 8 + NB + b);
         if ((rc = igd_launch_gotoh(h, job))) return rc;
     }
-    if (after_launch && (rc = after_launch((uint8_t *)h->h_stage + n_pairs * 4))) return rc;
     IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (after_launch && (rc = after_launch((uint8_t *)h->h_stage + n_pairs * 4))) return rc;
+    IGD_CUDA(cudaEventRecord(h->ev2, h->stream));
     if (n_pairs) IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_PAY], n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
-    float ms = 0.f;
+    float ms = 0.f, ms_after = 0.f;
     IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    acc.ms += ms; acc.cells += cells; acc.launches += h->timing.align_launches;
-    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   round: %zu pairs in %zu runs (chunk %d), %.3f ms of kernels, %.1f GCUPS\n",
-                                            n_pairs, all.size(), chunk, ms, cells / (ms * 1e6));
+    IGD_CUDA(cudaEventElapsedTime(&ms_after, h->ev1, h->ev2));
+    acc.ms += ms + ms_after; acc.cells += cells; acc.launches += h->timing.align_launches;
+    if (after_launch) acc.k5_ms += ms_after;
+    if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   round: %zu pairs in %zu runs (chunk %d), %.3f ms of kernels, %.1f GCUPS; queued behind them: %.3f ms\n",
+                                            n_pairs, all.size(), chunk, ms, cells / (ms * 1e6 + 1e-9), ms_after);
     const uint32_t *pay = (const uint32_t *)h->h_stage;
     for (const PrunedPair &p : pp)
         for (int k = 0; k < p.count; ++k) {
@@ -288,6 +291,8 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     float ms = 0.f;
     IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     acc.ms += ms; acc.launches += h->timing.align_launches;
+    acc.lcs_ms += ms;
+    for (int32_t u = 0; u < U; ++u) acc.lcs_cells += 2ull * (uint64_t)(toff[2 * u + 1] - toff[2 * u]) * (uint64_t)gene_off[n_gene];
     if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   LCS kernels %.3f ms for %d x %d pairs\n", ms, 2 * U, n_gene);
     tr.mark("LCS bounds + D2H");
     // Round one: the K largest bounds of every fragment.
@@ -336,6 +341,7 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
             for (int32_t g = 0; g < n_gene; g += ychunk)
                 yruns[nA <= 352 ? 0 : 1].push_back(make_int4(u, g, std::min(ychunk, n_gene - g), (int)(ywords + g)));
             ywords += (size_t)n_gene;
+            acc.k5_cells += 2ull * (uint64_t)nA * (uint64_t)gene_off[n_gene];
         }
     }
     // IGD_DETECT_YPASS_CAP: tests shrink the list to exercise the overflow path
@@ -710,6 +716,8 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
     }
     h->timing.scan_ms = scan_ms;
     h->timing.align_ms = acc.ms; h->timing.align_cells = acc.cells; h->timing.align_launches = acc.launches;
+    h->timing.lcs_ms = acc.lcs_ms; h->timing.k5_ms = acc.k5_ms; h->timing.dp_ms = acc.ms - acc.lcs_ms - acc.k5_ms;
+    h->timing.lcs_cells = acc.lcs_cells; h->timing.k5_cells = acc.k5_cells;
     *n_vj_rows = h->vj_rows.size();
     *n_d_rows = h->d_rows.size();
     return IGD_OK;

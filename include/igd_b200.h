@@ -90,6 +90,10 @@ typedef struct {
     uint64_t scan_bases;       /* contig bases covered by the last scan */
     uint64_t align_cells;      /* sum len(target)*len(query) over pairs (x passes) of the last align call */
     uint64_t total_launches;   /* kernels launched by this handle since igd_create */
+    /* igd_detect only: how align_ms splits.  dp_ms: the Gotoh kernels (align_cells are theirs); lcs_ms: the LCS bound,
+     * its top-K selection (K4); k5_ms: the insertion-charging bound (K5) over k5_cells letter pairs (both orientations) */
+    float    dp_ms, lcs_ms, k5_ms, reserved_f;
+    uint64_t lcs_cells, k5_cells;
 } igd_timing;
 
 const char *igd_last_error(void);
