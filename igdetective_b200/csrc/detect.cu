@@ -470,6 +470,10 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
             bool pruned = false;
             if ((rc = best_by_pruning(h, gt, U, toff, gene, gene_off, n_gene, sc, prm, mixed, acc, best, &pruned))) return rc;
             bool launched = false;
+            if (!pruned) {                              // allocations first: nothing but launches between the timing events
+                if ((rc = igd_reserve(h, S_PICK, (size_t)U * n_gene * 4))) return rc;
+                if ((rc = igd_reserve(h, S_BEST, (size_t)U * sizeof(int4)))) return rc;
+            }
             if (!pruned && (rc = igd_dense_launch(h, nullptr, toff.data(), 2 * U, gene, gene_off, n_gene, sc, &launched, true))) return rc;
             if (pruned) goto have_best;
             tr.mark("dense launch (host side)");
@@ -477,8 +481,6 @@ int score_gene_type(igd_handle *h, int gt, const std::vector<Cand> &cand,
                 igd_set_error("a (fragment, gene) pair does not fit the packed alignment kernels (gene longer than 511 or scores out of range)");
                 return IGD_ERR_UNSUPPORTED;
             }
-            if ((rc = igd_reserve(h, S_PICK, (size_t)U * n_gene * 4))) return rc;
-            if ((rc = igd_reserve(h, S_BEST, (size_t)U * sizeof(int4)))) return rc;
             if ((rc = igd_launch_pick(h, (const uint32_t *)h->d_scratch[S_PAY], (const int32_t *)h->d_scratch[S_QRYOFF],
                                       U, n_gene, (uint32_t *)h->d_scratch[S_PICK]))) return rc;
             argmax_pick_kernel<<<(unsigned)(((size_t)U * 32 + 255) / 256), 256, 0, h->stream>>>(
