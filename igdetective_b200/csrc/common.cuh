@@ -104,7 +104,7 @@ int igd_cuda_fail(cudaError_t e, const char *what);
 
 // growable device scratch slots (capi.cu, detect.cu)
 enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK,
-       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_COUNT };
+       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_TCLS, S_COUNT };
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
 // 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
@@ -118,7 +118,7 @@ int igd_dense_launch(igd_handle *h, const uint8_t *tgt, const int32_t *tgt_off, 
 bool igd_packed_scheme_ok(const igd_scoring *sc);
 int igd_packed_layout_for(const igd_scoring *sc, int nA, int nB);     // 0: two-register kernel, 1 / 2: packed short / long layout
 // lcs.cu: out[t][g] = LCS(upper(target t), upper(gene g)), an upper bound on BioAlign's match count + 1
-int igd_launch_lcs(igd_handle *h, const uint8_t *d_tgt, const int32_t *d_tgt_off, int n_tgt,
+int igd_launch_lcs(igd_handle *h, const uint8_t *d_tgt, const int32_t *d_tgt_off, int n_tgt, size_t tbytes,
                    const uint8_t *d_qry, const int32_t *d_qry_off, int n_qry, int max_q, uint32_t *d_masks, uint16_t *d_out);
 int igd_launch_ub_topk(igd_handle *h, const uint16_t *d_lcs, const int32_t *d_qry_off, int n_unique, int n_qry, int K,
                        uint16_t *d_ub, int32_t *d_top);

@@ -271,7 +271,7 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], gene_off, ((size_t)n_gene + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     h->timing.align_launches = 0;
     IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * U,
+    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * U, (size_t)toff[2 * U],
                              (const uint8_t *)h->d_scratch[S_QRY], (const int32_t *)h->d_scratch[S_QRYOFF], n_gene, max_q,
                              (uint32_t *)h->d_scratch[S_MASKS], (uint16_t *)h->d_scratch[S_LCS]))) return rc;
     const int K = (int)std::min<size_t>(PRUNE_TOP, (size_t)n_gene);

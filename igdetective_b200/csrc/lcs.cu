@@ -26,16 +26,22 @@ __device__ __forceinline__ int letter_class(unsigned c)
     return c == 'A' ? 0 : (c == 'C' ? 1 : (c == 'G' ? 2 : (c == 'T' ? 3 : 4)));
 }
 
-// masks[g][class][w]: bit i of word w = upper(gene g)[32 w + i] is in the class
+// masks[g][class][w]: bit i of word w = upper(gene g)[32 w + i] is in the class.  One thread per (gene, word).
 __global__ void __launch_bounds__(LCS_THREADS)
 gene_masks_kernel(const uint8_t *__restrict__ qry, const int32_t *__restrict__ qry_off, int n_qry, int W, uint32_t *__restrict__ masks)
 {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = k / W, w = k - g * W;
     if (g >= n_qry) return;
     const int b0 = qry_off[g], n = qry_off[g + 1] - b0;
-    uint32_t *m = masks + (size_t)g * 5 * W;
-    for (int k = 0; k < 5 * W; ++k) m[k] = 0u;
-    for (int i = 0; i < n && i < 32 * W; ++i) m[letter_class(qry[b0 + i]) * W + (i >> 5)] |= 1u << (i & 31);
+    uint32_t m[5] = {0u, 0u, 0u, 0u, 0u};
+    for (int i = 32 * w; i < n && i < 32 * w + 32; ++i) {
+        const int c = letter_class(qry[b0 + i]);
+#pragma unroll
+        for (int x = 0; x < 5; ++x) m[x] |= (c == x ? 1u : 0u) << (i & 31);
+    }
+#pragma unroll
+    for (int x = 0; x < 5; ++x) masks[((size_t)g * 5 + x) * W + w] = m[x];
 }
 
 // V += U over W words with carry propagation; blocks of four words, the carry travels in a register between blocks
@@ -61,9 +67,37 @@ __device__ __forceinline__ void add_words(const uint32_t (&v)[W], const uint32_t
     }
 }
 
+// u += v over eleven words in one carry chain (u and v are disjoint register sets: 22 operands)
+__device__ __forceinline__ void add_in_place_11(uint32_t (&u)[11], const uint32_t (&v)[11])
+{
+    asm("add.cc.u32 %0, %0, %11;\n\taddc.cc.u32 %1, %1, %12;\n\taddc.cc.u32 %2, %2, %13;\n\taddc.cc.u32 %3, %3, %14;\n\t"
+        "addc.cc.u32 %4, %4, %15;\n\taddc.cc.u32 %5, %5, %16;\n\taddc.cc.u32 %6, %6, %17;\n\taddc.cc.u32 %7, %7, %18;\n\t"
+        "addc.cc.u32 %8, %8, %19;\n\taddc.cc.u32 %9, %9, %20;\n\taddc.u32 %10, %10, %21;"
+        : "+r"(u[0]), "+r"(u[1]), "+r"(u[2]), "+r"(u[3]), "+r"(u[4]), "+r"(u[5]), "+r"(u[6]), "+r"(u[7]), "+r"(u[8]), "+r"(u[9]), "+r"(u[10])
+        : "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]));
+}
+
+template <int W>
+__device__ __forceinline__ void lcs_row(uint32_t (&V)[W], const uint32_t (&M)[W])
+{
+    uint32_t U[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) U[w] = V[w] & M[w];
+    if constexpr (W == 11) {
+        add_in_place_11(U, V);                                                   // U = V + (V & M)
+#pragma unroll
+        for (int w = 0; w < W; ++w) V[w] = U[w] | (V[w] & ~M[w]);                // one LOP3
+    } else {
+        uint32_t S[W];
+        add_words<W>(V, U, S);
+#pragma unroll
+        for (int w = 0; w < W; ++w) V[w] = S[w] | (V[w] ^ U[w]);
+    }
+}
+
 template <int W>
 __global__ void __launch_bounds__(LCS_THREADS)
-lcs_bound_kernel(const uint8_t *__restrict__ tgt, const int32_t *__restrict__ tgt_off, int n_tgt, int tgt_per_block,
+lcs_bound_kernel(const uint8_t *__restrict__ tgt /* class bytes */, const int32_t *__restrict__ tgt_off, int n_tgt, int tgt_per_block,
                  const int32_t *__restrict__ qry_off, int n_qry, const uint32_t *__restrict__ masks, uint16_t *__restrict__ out)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,22 +115,14 @@ lcs_bound_kernel(const uint8_t *__restrict__ tgt, const int32_t *__restrict__ tg
 #pragma unroll
         for (int w = 0; w < W; ++w) V[w] = 0xffffffffu;
         for (int i = 0; i < nA; ++i) {
-            const int c = letter_class(__ldg(&tgt[a0 + i]));                    // the same letter for every thread
-            uint32_t U[W], S[W];
-#define IGD_LCS_ROW(C)                                                                                   \
-            {                                                                                            \
-                _Pragma("unroll") for (int w = 0; w < W; ++w) U[w] = V[w] & M[C][w];                      \
-                add_words<W>(V, U, S);                                                                   \
-                _Pragma("unroll") for (int w = 0; w < W; ++w) V[w] = S[w] | (V[w] ^ U[w]);               \
-            }
+            const int c = __ldg(&tgt[a0 + i]);                                  // class byte: the same for every thread
             switch (c) {
-            case 0: IGD_LCS_ROW(0) break;
-            case 1: IGD_LCS_ROW(1) break;
-            case 2: IGD_LCS_ROW(2) break;
-            case 3: IGD_LCS_ROW(3) break;
-            default: IGD_LCS_ROW(4) break;
+            case 0: lcs_row<W>(V, M[0]); break;
+            case 1: lcs_row<W>(V, M[1]); break;
+            case 2: lcs_row<W>(V, M[2]); break;
+            case 3: lcs_row<W>(V, M[3]); break;
+            default: lcs_row<W>(V, M[4]); break;
             }
-#undef IGD_LCS_ROW
         }
         if (have) {
             int zeros = 0;
@@ -324,12 +350,17 @@ int igd_launch_ub_topk(igd_handle *h, const uint16_t *d_lcs, const int32_t *d_qr
 
 // out[t][g] = LCS(upper(target t), upper(gene g)) for the targets / genes resident in S_TGT / S_QRY (uint16, n_tgt x n_qry);
 // max_q = longest gene (<= 512).  d_masks: 5 * W words per gene of scratch.
-int igd_launch_lcs(igd_handle *h, const uint8_t *d_tgt, const int32_t *d_tgt_off, int n_tgt,
+int igd_launch_lcs(igd_handle *h, const uint8_t *d_tgt, const int32_t *d_tgt_off, int n_tgt, size_t tbytes,
                    const uint8_t *d_qry, const int32_t *d_qry_off, int n_qry, int max_q, uint32_t *d_masks, uint16_t *d_out)
 {
     if (max_q > 512) { igd_set_error("igd_launch_lcs: gene longer than 512"); return IGD_ERR_TOO_LONG; }
     const int W = max_q <= 352 ? 11 : 16;
-    gene_masks_kernel<<<(n_qry + LCS_THREADS - 1) / LCS_THREADS, LCS_THREADS, 0, h->stream>>>(d_qry, d_qry_off, n_qry, W, d_masks);
+    // class bytes of the target letters, once, instead of a classification per thread and row
+    int rc;
+    if ((rc = igd_reserve(h, S_TCLS, tbytes + 16))) return rc;
+    if ((rc = igd_launch_gene_classes(h, d_tgt, tbytes, (uint8_t *)h->d_scratch[S_TCLS]))) return rc;
+    d_tgt = (const uint8_t *)h->d_scratch[S_TCLS];
+    gene_masks_kernel<<<(n_qry * W + LCS_THREADS - 1) / LCS_THREADS, LCS_THREADS, 0, h->stream>>>(d_qry, d_qry_off, n_qry, W, d_masks);
     IGD_CUDA(cudaGetLastError());
     const int gene_blocks = (n_qry + LCS_THREADS - 1) / LCS_THREADS;
     // enough CTAs for every SM to hold several, few enough that the masks are loaded for more than one target
@@ -417,7 +448,7 @@ extern "C" int igd_match_bounds(igd_handle *h, const uint8_t *tgt, const int32_t
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_QRYOFF], qry_off, ((size_t)n_qry + 1) * 4, cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
     IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 2 * sizeof(unsigned long long), h->stream));
-    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * n_frag,
+    if ((rc = igd_launch_lcs(h, (const uint8_t *)h->d_scratch[S_TGT], (const int32_t *)h->d_scratch[S_TGTOFF], 2 * n_frag, tbytes,
                              (const uint8_t *)h->d_scratch[S_QRY], (const int32_t *)h->d_scratch[S_QRYOFF], n_qry, max_q,
                              (uint32_t *)h->d_scratch[S_MASKS], (uint16_t *)h->d_scratch[S_LCS]))) return rc;
     if ((rc = igd_launch_gene_classes(h, (const uint8_t *)h->d_scratch[S_QRY], qbytes, (uint8_t *)h->d_scratch[S_QCLS]))) return rc;
