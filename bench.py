@@ -7,7 +7,9 @@ Workload (BASELINE.json configs[1]): one synthetic 100 Mb contig per GPU, seed 2
 background, 300 V + 30 D + 12 J mutated genes with their RSSs in 3 clusters, 20 N runs, 45 %
 soft-masked; scored against combined_reference_genes IGHV (490) / IGHJ (13).
 One step = one pass of the hot path: RSS scan of both strands for the 4 signal types, D pairing,
-fragment extraction, scoring of every V / J candidate against every gene in both orientations,
+fragment extraction, scoring of every V / J candidate against every gene in both orientations
+(the V table by exact pruning: bounds prove which alignments cannot matter, csrc/lcs.cu + detect.cu;
+rows identical to the all-pairs scoring, which `align` / `roofline` time separately),
 argmax + threshold + the winners' detail pass -> the rows of genes_{V,D,J}.tsv.
   value : Gb scanned per second over the whole step, contigs resident in HBM (packed)
   e2e   : the same through the public API from HOST buffers (pinned ASCII contig H2D + pack
@@ -353,8 +355,8 @@ def gpu_arm(a):
                             "k5_tera_letter_pairs_per_s": tdet["k5_cells"] / max(tdet["k5_ms"], 1e-6) / 1e9},
         "kernel_share_of_step": {"rss_scan": scan_ms / (1e3 * t_dev / a.steps),
                                  "scoring_kernels": tdet["align_ms"] / (1e3 * t_dev / a.steps)},
-        # dominant kernel of the step (97 % of GPU time in the ncu launch list): integer DP, bound by the
-        # ALU pipe (neither HBM nor tensor); achieved = cell updates/s x ALU-pipe instructions per cell
+        # largest kernel of the step (60 % of GPU time in the ncu launch list, K5 20 %, K4 7 %): integer DP, bound by the
+        # ALU pipe (neither HBM nor tensor); achieved = cell updates/s x ALU-pipe instructions per cell, on all pairs
         "roofline": {"kernel": "gotoh_packed_kernel<%s,%s>" % V_KERNEL[:2], "bound": "alu", "achieved": kstat["gcups"] * alu_per_cell / 1e3,
                      "peak": int_peak, "unit": "T lane-ops/s", "frac": kstat["gcups"] * alu_per_cell / 1e3 / int_peak,
                      # dram bytes of one launch of this kernel (inputs are KB per pair): ncu --set full capture of this round
