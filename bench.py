@@ -123,18 +123,37 @@ def strong_config3(a, eng, motifs, canon, rank, world, barrier):
         part[k] = ArraySeq(host[int(off[k]):int(off[k + 1])])
     t_gen = time.perf_counter() - t0
     shard.gather_rows({"warmup": []}, asm.ids)                 # first object collective pays communicator set-up
-    samples, merged, scan_ms = [], None, 0.0
+    samples, merged, scan_ms, tm = [], None, 0.0, []
+    # auto: one group per ~400 MB of this rank's letters (3 Gb on one GPU: 8 groups; an eighth of it: one load, one detect)
+    groups = max(1, a.strong_groups) if a.strong_groups > 0 else int(max(1, min(8, n_mine // 400_000_000)))
+    engines = [eng]
+    if groups > 1:
+        from igdetective_b200.engine import Engine
+        for _ in range(max(1, a.strong_handles - 1)):          # more handles (streams) on the same GPU
+            engines.append(Engine(eng.device, motifs))
     for it in range(1 + a.strong_reps):
         barrier()
         t0 = time.perf_counter()
-        eng.load_contigs((pinned.data_ptr(), off), list(part))
-        t1 = time.perf_counter()
-        rows = multi.detect_pieces(eng, None, asm.ids, pieces, canon, "canonical", part=part)
-        eng.sync()
-        t2 = time.perf_counter()
+        if groups > 1:
+            # the pieces in `groups` runs over two handles: group k + 1 is uploaded while group k is scanned and scored
+            tm = []
+            rows = multi.detect_pieces_pipelined(engines, asm.ids, pieces, canon, part, (pinned.data_ptr(), off), groups, tm)
+            t2 = time.perf_counter()
+            t1 = t0 + sum(x[1] for x in tm)                    # time spent uploading (the rest overlaps it)
+            t_detect = sum(x[2] for x in tm)
+        else:
+            eng.load_contigs((pinned.data_ptr(), off), list(part))
+            t1 = time.perf_counter()
+            rows = multi.detect_pieces(eng, None, asm.ids, pieces, canon, "canonical", part=part)
+            eng.sync()
+            t2 = time.perf_counter()
+            t_detect = t2 - t1
         merged = shard.gather_rows(rows, asm.ids)
         t3 = time.perf_counter()
-        v = [t3 - t0, t1 - t0, t2 - t1, t3 - t2, eng.timing()["scan_ms"], eng.timing()["pack_ms"]]
+        if groups > 1:                                         # kernel times: sums over the groups (together they cover the shard)
+            v = [t3 - t0, t1 - t0, t_detect, t3 - t2, sum(x[3] for x in tm), sum(x[4] for x in tm)]
+        else:
+            v = [t3 - t0, t1 - t0, t_detect, t3 - t2, eng.timing()["scan_ms"], eng.timing()["pack_ms"]]
         if world > 1:
             t = torch.tensor(v, dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -153,6 +172,11 @@ def strong_config3(a, eng, motifs, canon, rank, world, barrier):
             "load_h2d_pack_s": med[1], "scan_and_scoring_s": med[2], "gather_s": med[3],
             "scan_kernel_ms_max": med[4], "pack_kernel_ms_max": med[5],
             "timing": "median over reps of the max over ranks; host ASCII in pinned memory, H2D + pack inside",
+            "pipeline": ("%d groups of pieces over %d handles: the upload of group k + 1 overlaps the scan + scoring of group k, so "
+                         "load_h2d_pack_s + scan_and_scoring_s (sums over the groups, like scan_kernel_ms_max) exceed "
+                         "whole_job_s; the pack kernels are queued without a wait and not timed (0)" % (groups, len(engines))) if groups > 1 else "none (one load, one detect)",
+            "groups_timeline_rank0": [{"group": x[0], "upload_start_s": x[6], "upload_s": x[1], "detect_s": x[2],
+                                       "scoring_kernel_ms": x[7]} for x in sorted(tm)] if groups > 1 else None,
             "rank0_pieces": len(pieces), "rank0_bases": int(n_mine), "generate_s_rank0": t_gen,
             "rows": {g: len(merged[g]) for g in ("V", "D", "J")},
             "rows_sha1": hashlib.sha1(text.encode()).hexdigest()}
@@ -365,7 +389,13 @@ def gpu_arm(a):
                      "fma_ops_per_cell": sass["fma_pipe_per_cell"], "ops_source": sass["source"],
                      # the same against the issue port: every instruction of the hot path, 128 lanes/clk/SM
                      "issue_frac": kstat["gcups"] * sass["all_per_cell"] / 1e3 / (2 * int_peak),
-                     "peak_source": "148 SMs x 64 ALU lanes/clk x SM clock sampled during the run"},
+                     "peak_source": "148 SMs x 64 ALU lanes/clk x SM clock sampled during the run",
+                     # what the number is measured on, and what the same kernel does inside the timed steps
+                     "measured_on": "all (candidate, gene, orientation) pairs of the step in one dense pass of this kernel after "
+                                    "the timed steps (`align`); the step itself aligns only the pairs its bounds leave over",
+                     "in_step": {"kernel_ms": tdet["dp_ms"], "cells": int(tdet["align_cells"]),
+                                 "gcups": tdet["align_cells"] / max(tdet["dp_ms"], 1e-6) / 1e6,
+                                 "share_of_step": tdet["dp_ms"] / (1e3 * t_dev / a.steps)}},
         # the HBM-bound kernel of the path (north star: scan vs HBM roofline), 0.25 algorithmic bytes per base
         "roofline_scan": {"kernel": "rss_scan_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
                           "unit": "GB/s", "frac": achieved / hbm_peak, "algorithmic_bytes": alg_bytes,
@@ -573,6 +603,8 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--strong-reps", type=int, default=3, help="timed repetitions of the strong-scaled configs[2] leg (0 = skip)")
     ap.add_argument("--strong-scale", type=float, default=1.0, help="size of the configs[2] assembly relative to 3.06 Gb")
+    ap.add_argument("--strong-handles", type=int, default=4, help="configs[2] leg: handles the groups rotate over")
+    ap.add_argument("--strong-groups", type=int, default=0, help="configs[2] leg: groups of pieces pipelined over the handles (1 = one load, one detect; 0 = one per ~400 MB)")
     ap.add_argument("--scan-mbases", type=float, default=1000.0,
                     help="size of the extra scan-only measurement (the workload contig repeated; 0 = skip)")
     a = ap.parse_args()

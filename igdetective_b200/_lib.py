@@ -62,7 +62,7 @@ EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "i
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
            "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows",
            "igd_detect", "igd_fetch_vj_rows", "igd_fetch_d_rows", "igd_fasta_open_range", "igd_fasta_range",
-           "igd_fasta_header_byte", "igd_match_bounds")
+           "igd_fasta_header_byte", "igd_match_bounds", "igd_load_contigs_async")
 
 _lib = None
 
@@ -88,6 +88,8 @@ def load():
     lib.igd_set_motifs.argtypes = [vp, vp, vp]
     lib.igd_center_bitmap.argtypes = [vp, vp]
     lib.igd_load_contigs.argtypes = [vp, vp, vp, i32]
+    lib.igd_load_contigs_async.argtypes = [vp, vp, vp, i32]
+    lib.igd_load_contigs_async.restype = ctypes.c_int
     lib.igd_scan.argtypes = [vp, vp, u64p]
     lib.igd_fetch_hits.argtypes = [vp, vp, ctypes.c_uint64]
     lib.igd_scan_kmers.argtypes = [vp, i32, u64p]

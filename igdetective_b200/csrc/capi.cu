@@ -91,7 +91,8 @@ void igd_destroy(igd_handle *h)
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
     if (h->h_stage) cudaFreeHost(h->h_stage);
-    if (h->h_ring) { cudaFreeHost(h->h_ring); for (int i = 0; i < 4; ++i) cudaEventDestroy(h->ring_ev[i]); }
+    if (h->h_ring) cudaFreeHost(h->h_ring);
+    for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -204,7 +205,7 @@ int igd_set_motifs(igd_handle *h, const uint8_t *flags7, const uint8_t *flags9)
 // one box do it at once) and walk over every fourth piece: copy the piece into the slot, queue its DMA, record the
 // slot's event, and wait for that event before the slot is written again -- so the memcpy of one thread overlaps the
 // transfers of the others.  The copies land in disjoint ranges; whatever follows on the stream is queued after the join.
-static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, size_t nbytes)
+static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, size_t nbytes, bool throttle = false)
 {
     constexpr size_t PIECE = 8u << 20;
     constexpr int RING = 4;
@@ -212,13 +213,32 @@ static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, siz
     const bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
                         (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged);
     cudaGetLastError();                                    // unregistered host memory may report an error on old drivers
-    if (pinned || nbytes < (64u << 20)) {
+    if (pinned && !throttle) {
+        IGD_CUDA(cudaMemcpyAsync(d_dst, src, nbytes, cudaMemcpyHostToDevice, h->stream));
+        return IGD_OK;
+    }
+    if (pinned) {
+        // A copy engine works through its queue in order: behind one 0.8 GB transfer -- or behind a hundred queued pieces
+        // of it -- the small table copies of another handle of this GPU (a pipeline that scores one set of contigs while
+        // the next is uploaded) wait for milliseconds each.  So: pieces, and never more than two of them queued.
+        if (!h->ring_ev[0])
+            for (int i = 0; i < RING; ++i) IGD_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+        size_t k = 0;
+        for (size_t at = 0; at < nbytes; at += PIECE, ++k) {
+            if (k >= 2) IGD_CUDA(cudaEventSynchronize(h->ring_ev[k & 1]));
+            IGD_CUDA(cudaMemcpyAsync(d_dst + at, src + at, std::min(PIECE, nbytes - at), cudaMemcpyHostToDevice, h->stream));
+            IGD_CUDA(cudaEventRecord(h->ring_ev[k & 1], h->stream));
+        }
+        return IGD_OK;
+    }
+    if (nbytes < (64u << 20)) {
         IGD_CUDA(cudaMemcpyAsync(d_dst, src, nbytes, cudaMemcpyHostToDevice, h->stream));
         return IGD_OK;
     }
     if (!h->h_ring) {
         IGD_CUDA(cudaMallocHost(&h->h_ring, RING * PIECE));
-        for (int i = 0; i < RING; ++i) IGD_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
+        if (!h->ring_ev[0])
+            for (int i = 0; i < RING; ++i) IGD_CUDA(cudaEventCreateWithFlags(&h->ring_ev[i], cudaEventDisableTiming));
     }
     const size_t n_pieces = (nbytes + PIECE - 1) / PIECE;
     const unsigned nthreads = std::max(1u, std::min((unsigned)RING, std::thread::hardware_concurrency()));
@@ -247,7 +267,11 @@ static int upload_letters(igd_handle *h, uint8_t *d_dst, const uint8_t *src, siz
     return IGD_OK;
 }
 
-int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs)
+} // extern "C"
+
+// wait = false: returns once the caller's letters have crossed the bus (they may be reused); the pack kernel stays queued
+// on the handle's stream, where every later call of the handle is ordered behind it
+static int load_contigs_impl(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs, bool wait)
 {
     if (!h || !offsets || n_contigs < 0 || (!seq && n_contigs > 0 && offsets[n_contigs] > 0)) {
         igd_set_error("bad arguments to igd_load_contigs"); return IGD_ERR_ARG;
@@ -287,7 +311,7 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     for (int c = 0; c <= n_contigs; ++c) rel[c] = offsets[c] - offsets[0];
     h->contig_seq_off = rel;
     if (nbytes) {
-        int rc2 = upload_letters(h, (uint8_t *)h->d_scratch[S_SEQ], seq + offsets[0], nbytes);
+        int rc2 = upload_letters(h, (uint8_t *)h->d_scratch[S_SEQ], seq + offsets[0], nbytes, !wait);
         if (rc2) return rc2;
     }
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_SEQOFF], rel.data(), (size_t)(n_contigs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
@@ -305,12 +329,6 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
     }
     if ((rc = igd_reserve(h, S_TILEC, tile_contig.size() * 4))) return rc;
     IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TILEC], tile_contig.data(), tile_contig.size() * 4, cudaMemcpyHostToDevice, h->stream));
-    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
-    if ((rc = igd_launch_pack(h, (const uint8_t *)h->d_scratch[S_SEQ], (const unsigned long long *)h->d_scratch[S_SEQOFF],
-                              (const unsigned long long *)h->d_scratch[S_CHUNK0], (const int *)h->d_scratch[S_TILEC], n_contigs))) return rc;
-    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
-    IGD_CUDA(cudaStreamSynchronize(h->stream));       // rel / offsets are host temporaries
-    IGD_CUDA(cudaEventElapsedTime(&h->timing.pack_ms, h->ev0, h->ev1));
     // hit buffer sized for the k-mer scan's ~1 % density with slack; regrown on overflow
     const uint64_t want = std::max<uint64_t>(1u << 20, h->total_bases / 32);
     if (want > h->hit_cap) {
@@ -318,10 +336,34 @@ int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets,
         IGD_CUDA(cudaMalloc(&h->d_hits, want * sizeof(unsigned long long)));
         h->hit_cap = want;
     }
+    IGD_CUDA(cudaEventRecord(h->ev2, h->stream));     // every copy from host memory is in front of this
+    IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = igd_launch_pack(h, (const uint8_t *)h->d_scratch[S_SEQ], (const unsigned long long *)h->d_scratch[S_SEQOFF],
+                              (const unsigned long long *)h->d_scratch[S_CHUNK0], (const int *)h->d_scratch[S_TILEC], n_contigs))) return rc;
+    IGD_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (wait) {
+        IGD_CUDA(cudaStreamSynchronize(h->stream));
+        IGD_CUDA(cudaEventElapsedTime(&h->timing.pack_ms, h->ev0, h->ev1));
+    } else {
+        IGD_CUDA(cudaEventSynchronize(h->ev2));       // rel / offsets / the caller's letters are free again
+        h->timing.pack_ms = 0.f;                      // not waited for
+    }
     h->contigs_loaded = true;
     h->last_scan_kind = 0;
     h->sorted_hits_valid = false;
     return IGD_OK;
+}
+
+extern "C" {
+
+int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs)
+{
+    return load_contigs_impl(h, seq, offsets, n_contigs, true);
+}
+
+int igd_load_contigs_async(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs)
+{
+    return load_contigs_impl(h, seq, offsets, n_contigs, false);
 }
 
 // ---- FASTA ingest -----------------------------------------------------------------------------------

@@ -148,6 +148,8 @@ int empty_fragment_best(igd_handle *h, const uint8_t *gene, const int32_t *gene_
 // identical to the unpruned path (tests/test_gpu_pipeline.py::test_pruned_scoring_equals_full_scoring); planted genes
 // need 1-15 of 490 alignments per orientation, background candidates (best PI ~ 54 < 60 <= UB ~ 69) need them all.
 constexpr size_t PRUNE_TOP = 16;
+constexpr int PRUNE_MIN = 8;            // swept on the bench contig (min 2 / 4 / 8 x delta 0.015 / 0.03 / 0.06 / off): 8 and 0.03 cost least
+constexpr double PRUNE_DELTA = 0.03;
 struct PrunedPair { int32_t u, q0, count, slot; };           // fwd results at slot + k, reverse-complement at slot + count + k
 
 // DP over the listed (fragment, gene) pairs, both orientations; per fragment `lists[u]` must be ascending
@@ -295,12 +297,25 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     for (int32_t u = 0; u < U; ++u) acc.lcs_cells += 2ull * (uint64_t)(toff[2 * u + 1] - toff[2 * u]) * (uint64_t)gene_off[n_gene];
     if (getenv("IGD_DETECT_TRACE")) fprintf(stderr, "[igd_detect]   LCS kernels %.3f ms for %d x %d pairs\n", ms, 2 * U, n_gene);
     tr.mark("LCS bounds + D2H");
-    // Round one: the K largest bounds of every fragment.
+    // Round one: the largest bounds of every fragment (ub_topk_kernel lists them in descending order) -- the first
+    // PRUNE_MIN of them, and the rest of the K while they stay within PRUNE_DELTA of the largest: the gene of maximal PI is
+    // almost always among those, and whatever round one leaves out round two still aligns if its bound demands it.
+    // A fragment whose largest bound is below the cut-off cannot yield a row and is aligned against nothing.
     const double cut = std::min(prm->pi_strict[gt], prm->pi_relax[gt]);
+    const double delta = getenv("IGD_DETECT_TOP_DELTA") ? atof(getenv("IGD_DETECT_TOP_DELTA")) : PRUNE_DELTA;
+    const int kmin = getenv("IGD_DETECT_TOP_MIN") ? atoi(getenv("IGD_DETECT_TOP_MIN")) : PRUNE_MIN;
     std::vector<std::vector<int32_t>> lists((size_t)U);
     for (int32_t u = 0; u < U; ++u) {
         std::vector<int32_t> &l = lists[(size_t)u];
-        for (int k = 0; k < K; ++k) if (top[(size_t)u * K + k] >= 0) l.push_back(top[(size_t)u * K + k]);
+        double top_ratio = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int32_t g = top[(size_t)u * K + k];
+            if (g < 0) break;
+            const double ratio = ((double)ub[(size_t)u * n_gene + g] - 1.0) / (double)(gene_off[g + 1] - gene_off[g]);
+            if (k == 0) top_ratio = ratio;
+            if (k >= kmin && ratio < top_ratio - delta) break;
+            l.push_back(g);
+        }
         std::sort(l.begin(), l.end());
     }
     std::vector<Best> best((size_t)U, Best{-1, 0, 1, 0});

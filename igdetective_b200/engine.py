@@ -87,9 +87,11 @@ class Engine:
         assert f7.size == 16384 and f9.size == 262144
         _lib.check(self._lib.igd_set_motifs(self._h, f7.ctypes.data, f9.ctypes.data))
 
-    def load_contigs(self, seqs, ids=None):
+    def load_contigs(self, seqs, ids=None, wait=True):
         """seqs: dict {id: str} (parent_seq of the reference), list of str/bytes, or a
-        (uint8 buffer, uint64 offsets) pair already concatenated (e.g. pinned host memory)."""
+        (uint8 buffer, uint64 offsets) pair already concatenated (e.g. pinned host memory).
+        wait=False (igd_load_contigs_async): return once the letters have crossed the bus; the pack kernel stays queued
+        on this engine's stream, in front of whatever this engine is asked next."""
         if isinstance(seqs, dict):
             ids, seqs = list(seqs.keys()), list(seqs.values())
         if isinstance(seqs, tuple):
@@ -106,7 +108,7 @@ class Engine:
         n = len(off) - 1
         self.contig_ids = list(ids) if ids is not None else list(range(n))
         self.contig_lens = np.diff(off.astype(np.int64))
-        _lib.check(self._lib.igd_load_contigs(self._h, ptr, off.ctypes.data, n))
+        _lib.check((self._lib.igd_load_contigs if wait else self._lib.igd_load_contigs_async)(self._h, ptr, off.ctypes.data, n))
         self.h2d_bytes += int(off[-1] - off[0]) + off.nbytes
         return n
 

@@ -178,38 +178,37 @@ def _rows_from_device(res, ids, parent_seq, canonical_genes, scan, order):
 
     # group sizes, to ask for a rank map only where the order is not trivial
     want_order = order == "reference"
-    for r in vj.tolist():
-        hept, nona, fstart, ci, flen, best, matches, alen, start, ient, gt, sd, direction, _ = r
-        gene, strand, contig = (V, J)[gt], (FWD, REV)[sd], ids[ci]
-        s = parent_seq[contig]
-        if flen > 0:
-            # the aligned orientation of the fragment: reverse-complemented once for a '-' strand RSS and once more when
-            # the reverse complement aligned better (:309-317) -- two flips cancel
-            frag = s[fstart:fstart + flen].upper()
-            if (strand == REV) != (direction == 45):                # 45 == ord('-')
-                frag = reverse_complement(frag)
-            end = start + alen
-            query = frag[start:ient]
-        else:                                   # the reference's empty slice: ComputeAlignment('', gene) at :388
-            end, query = gene_len[gt][best], ""
-        if strand == FWD:
-            if gene == V:
-                ge = hept - 1
-                gs = hept - GENE_LENGTH[gene] + start
+    if len(vj):
+        # the numeric columns for all rows at once (:391-414); only the strings are made row by row
+        hept, start, alen_a = vj["hept"].astype(np.int64), vj["start"].astype(np.int64), vj["alen"].astype(np.int64)
+        is_v, fwd, has = vj["gene_type"] == 0, vj["strand"] == 0, vj["frag_len"] > 0
+        glen = np.where(is_v, GENE_LENGTH[V], GENE_LENGTH[J])
+        best_len = np.where(is_v, np.asarray(gene_len[0])[np.minimum(vj["best_gene"], len(gene_len[0]) - 1)],
+                            np.asarray(gene_len[1] or [0])[np.minimum(vj["best_gene"], max(len(gene_len[1]) - 1, 0))])
+        end = np.where(has, start + alen_a, best_len)                   # empty slice: ComputeAlignment('', gene) at :388
+        lead = is_v == fwd                                              # the gene lies in front of the heptamer
+        gs = np.where(lead, np.where(is_v, hept - glen + start, hept - end), hept + 7)
+        ge = np.where(lead, hept - 1, np.where(is_v, hept + 7 + glen - start - 1, hept + 7 + end))
+        pi = np.rint((vj["matches"].astype(np.int64) - 1) / alen_a * 100).astype(np.int64)     # int(round(pi)): half to even
+        first = np.where(is_v, hept, vj["nona"])
+        cols = zip(hept.tolist(), vj["nona"].tolist(), vj["frag_start"].tolist(), vj["contig"].tolist(), vj["frag_len"].tolist(),
+                   vj["best_gene"].tolist(), start.tolist(), vj["ient"].tolist(), vj["gene_type"].tolist(), vj["strand"].tolist(),
+                   vj["direction"].tolist(), gs.tolist(), ge.tolist(), pi.tolist(), alen_a.tolist(), first.tolist())
+        for h, n, fstart, ci, flen, best, st, ient, gt, sd, direction, g0, g1, p, al, fi in cols:
+            gene, strand, contig = (V, J)[gt], (FWD, REV)[sd], ids[ci]
+            s = parent_seq[contig]
+            if flen > 0:
+                # the aligned orientation of the fragment: reverse-complemented once for a '-' strand RSS and once more
+                # when the reverse complement aligned better (:309-317) -- two flips cancel
+                if (sd == 1) != (direction == 45):                      # 45 == ord('-')
+                    query = reverse_complement(s[fstart:fstart + flen])[st:ient].upper()
+                else:
+                    query = s[fstart + st:fstart + min(ient, flen)].upper()
             else:
-                gs = hept + 7
-                ge = gs + end
-        else:
-            if gene == V:
-                gs = hept + 7
-                ge = gs + GENE_LENGTH[gene] - start - 1
-            else:
-                ge = hept - 1
-                gs = hept - end
-        pi = (matches - 1) / alen * 100
-        rows[gene].append([contig, strand, hept, nona, _kmer(s, hept, 7, strand), _kmer(s, nona, 9, strand),
-                           gs, ge, gene_ids[gt][best], chr(direction), int(round(pi)), float(alen), query])
-        keys[gene].append((sd, ci, hept if gene == V else nona))
+                query = ""
+            rows[gene].append([contig, strand, h, n, _kmer(s, h, 7, strand), _kmer(s, n, 9, strand),
+                               g0, g1, gene_ids[gt][best], chr(direction), p, float(al), query])
+            keys[gene].append((sd, ci, fi))
     for r in dr.tolist():
         dlh, dln, drh, drn, ci, sd, _ = r
         strand, contig = (FWD, REV)[sd], ids[ci]

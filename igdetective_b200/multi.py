@@ -12,6 +12,8 @@ of ranks.
 import argparse
 import os
 
+import numpy as np
+
 from . import datafiles as dfiles
 from . import igdetective, shard
 from .engine import Engine
@@ -41,6 +43,65 @@ def detect_pieces(eng, seqs, ids, pieces, canonical, order="canonical", part=Non
         own = shard.own_rows({g: by_piece[g].get(k, []) for g in out}, piece, ids[piece[0]])
         for g in out:
             out[g].extend(own[g])
+    return out
+
+
+def detect_pieces_pipelined(engines, ids, pieces, canonical, part, buffer, groups=4, timings=None):
+    """load + detect_pieces of this rank's pieces in `groups` runs of consecutive pieces over len(engines) handles of the
+    same GPU (one host thread each): the upload of group k + 1 (H2D + pack, one at a time, in order) runs while group k is
+    scanned and scored on another handle's stream.  buffer = (address of the pieces' letters in pinned host memory,
+    uint64 offsets of the pieces in it); part = {piece number: str-like view of its letters}.  timings (optional list)
+    receives (group, upload seconds, scan + scoring seconds, scan kernel ms, pack kernel ms, bases, start of the upload
+    in seconds since the call, scoring kernel ms)."""
+    import threading
+    import time
+    ptr, off = buffer
+    n = len(pieces)
+    if n == 0:
+        return {V: [], D: [], J: []}
+    groups = max(1, min(groups, n))
+    cuts = sorted(set([0, n] + [int(np.searchsorted(off, int(off[n]) * g // groups)) for g in range(1, groups)]))
+    n_groups = len(cuts) - 1
+    turn = [threading.Event() for _ in range(n_groups + 1)]
+    turn[0].set()
+    results, errors = [None] * n_groups, []
+    t_begin = time.perf_counter()
+
+    def worker(e):
+        try:
+            for k in range(e, n_groups, len(engines)):
+                lo, hi = cuts[k], cuts[k + 1]
+                turn[k].wait()
+                t0 = time.perf_counter()
+                try:
+                    engines[e].load_contigs((ptr + int(off[lo]), (off[lo:hi + 1] - off[lo]).astype(np.uint64)), list(range(hi - lo)),
+                                            wait=False)           # the next upload may start: only the bus is taken in turns
+                finally:
+                    turn[k + 1].set()
+                t1 = time.perf_counter()
+                results[k] = detect_pieces(engines[e], None, ids, pieces[lo:hi], canonical, "canonical",
+                                           part={j - lo: part[j] for j in range(lo, hi)})
+                engines[e].sync()
+                if timings is not None:
+                    tk = engines[e].timing()
+                    timings.append((k, t1 - t0, time.perf_counter() - t1, tk["scan_ms"], tk["pack_ms"], int(off[hi] - off[lo]),
+                                    t0 - t_begin, tk["align_ms"]))
+        except BaseException as exc:                       # surfaced in the caller's thread
+            errors.append(exc)
+            for ev in turn:
+                ev.set()
+
+    threads = [threading.Thread(target=worker, args=(e,)) for e in range(min(len(engines), n_groups))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    out = {V: [], D: [], J: []}
+    for r in results:
+        for g in out:
+            out[g].extend(r[g])
     return out
 
 

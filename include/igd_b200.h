@@ -123,6 +123,10 @@ int igd_center_bitmap(const uint8_t *flags9, uint32_t *bitmap /* 8192 words */);
  * (any case, IUPAC allowed), concatenated; offsets[n_contigs+1].  Copies to the
  * device and packs to 2-bit planes + validity plane there. */
 int igd_load_contigs(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs);
+/* The same, returning as soon as the letters have crossed the bus (seq / offsets may be reused); the pack kernel stays
+ * queued on the handle's stream and every later call of this handle is ordered behind it.  For pipelines that upload the
+ * next set of contigs on one handle while another handle of the same GPU scans and scores (igdetective_b200/multi.py). */
+int igd_load_contigs_async(igd_handle *h, const uint8_t *seq, const uint64_t *offsets, int32_t n_contigs);
 
 /* Ingest ("next" row of the scope table): input_seq_dict = {rec.id: rec.seq for rec in
  * SeqIO.parse(INPUT_PATH, "fasta")} (py/IGDetective.py:129) done natively.  igd_fasta_open parses
