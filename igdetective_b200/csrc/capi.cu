@@ -91,6 +91,7 @@ void igd_destroy(igd_handle *h)
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
     if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (int i = 0; i < 2; ++i) if (h->h_pin[i]) cudaFreeHost(h->h_pin[i]);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1111,6 +1112,16 @@ static void init_comp()                                 // reachable from two ha
         const char *from = "ACGTMRWSYKVHDBXNacgtmrwsykvhdbxnUu", *to = "TGCAKYWSRMBDHVXNtgcakywsrmbdhvxnAa";
         for (int i = 0; from[i]; ++i) g_comp[(uint8_t)from[i]] = (uint8_t)to[i];
     });
+}
+
+int igd_pin_reserve(igd_handle *h, int which, size_t bytes)
+{
+    if (h->h_pin_cap[which] >= bytes) return IGD_OK;
+    if (h->h_pin[which]) { IGD_CUDA(cudaFreeHost(h->h_pin[which])); h->h_pin[which] = nullptr; h->h_pin_cap[which] = 0; }
+    const size_t cap = bytes + bytes / 4 + 4096;
+    IGD_CUDA(cudaMallocHost(&h->h_pin[which], cap));
+    h->h_pin_cap[which] = cap;
+    return IGD_OK;
 }
 
 int igd_stage_reserve(igd_handle *h, size_t bytes)

@@ -88,6 +88,8 @@ struct igd_handle {
     size_t scratch_cap[32] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
+    void *h_pin[2] = {nullptr, nullptr};   // more pinned buffers: [0] bounds read-back, [1] run tables on their way to the device
+    size_t h_pin_cap[2] = {0, 0};
     void *h_ring = nullptr;       // ring of pinned pieces for the upload of pageable genomes (capi.cu, upload_letters)
     cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 
@@ -107,6 +109,7 @@ enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_
        S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_TCLS, S_COUNT };
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
+int igd_pin_reserve(igd_handle *h, int which, size_t bytes);   // h->h_pin[which]
 // 0: no lower-case letter anywhere, 1: only in targets, 2: in queries (and maybe targets)
 int igd_case_mix(const uint8_t *tgt, size_t tbytes, const uint8_t *qry, size_t qbytes);
 // Every target against every query through the packed run-mode kernels, results left on the device

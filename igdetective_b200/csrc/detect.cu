@@ -195,7 +195,11 @@ static int prune_round(igd_handle *h, const std::vector<std::vector<int32_t>> &l
     if ((rc = igd_reserve(h, S_SCORE, n_pairs * 4))) return rc;
     if ((rc = igd_reserve(h, S_PAY, n_pairs * 4))) return rc;
     if ((rc = igd_stage_reserve(h, n_pairs * 4 + extra_stage))) return rc;
-    if (!all.empty()) IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    if (!all.empty()) {
+        if ((rc = igd_pin_reserve(h, 1, all.size() * sizeof(int4)))) return rc;
+        memcpy(h->h_pin[1], all.data(), all.size() * sizeof(int4));       // consumed before the round's synchronisation
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_RUNS], h->h_pin[1], all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    }
     IGD_CUDA(cudaMemsetAsync(h->d_count + 8, 0, 3 * NB * sizeof(unsigned long long), h->stream));
     h->timing.align_launches = 0;
     IGD_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -285,10 +289,14 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     // bounds of the better orientation (LCS; the bound on the match count is LCS - 1) and, per fragment, the K genes
     // with the largest bounds: round one (the gene with the best PI is among the 16 largest bounds for every planted
     // gene of the bench workload, among the 2 largest for two thirds of them)
-    std::vector<uint16_t> ub((size_t)U * n_gene);
-    std::vector<int32_t> top((size_t)U * K);
-    IGD_CUDA(cudaMemcpyAsync(ub.data(), h->d_scratch[S_UB], ub.size() * 2, cudaMemcpyDeviceToHost, h->stream));
-    IGD_CUDA(cudaMemcpyAsync(top.data(), h->d_scratch[S_TOP], top.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    // read back into pinned memory: a copy to pageable memory blocks inside the driver, which also stalls the other
+    // handles of this GPU when several of them work side by side (multi.detect_pieces_pipelined)
+    const size_t ub_bytes = ((size_t)U * n_gene * 2 + 15) & ~(size_t)15;
+    if ((rc = igd_pin_reserve(h, 0, ub_bytes + (size_t)U * K * 4))) return rc;
+    const uint16_t *ub = (const uint16_t *)h->h_pin[0];
+    const int32_t *top = (const int32_t *)((const uint8_t *)h->h_pin[0] + ub_bytes);
+    IGD_CUDA(cudaMemcpyAsync(h->h_pin[0], h->d_scratch[S_UB], (size_t)U * n_gene * 2, cudaMemcpyDeviceToHost, h->stream));
+    IGD_CUDA(cudaMemcpyAsync((uint8_t *)h->h_pin[0] + ub_bytes, h->d_scratch[S_TOP], (size_t)U * K * 4, cudaMemcpyDeviceToHost, h->stream));
     IGD_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0.f;
     IGD_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
