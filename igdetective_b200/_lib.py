@@ -62,7 +62,8 @@ EXPORTS = ("igd_last_error", "igd_device_count", "igd_create", "igd_destroy", "i
            "igd_fetch_kmer_hits", "igd_align_batch", "igd_fasta_open", "igd_fasta_close", "igd_fasta_count",
            "igd_fasta_info", "igd_fasta_read", "igd_load_fasta", "igd_align_dense", "igd_score_fragments", "igd_score_windows",
            "igd_detect", "igd_fetch_vj_rows", "igd_fetch_d_rows", "igd_fasta_open_range", "igd_fasta_range",
-           "igd_fasta_header_byte", "igd_match_bounds", "igd_load_contigs_async")
+           "igd_fasta_header_byte", "igd_match_bounds", "igd_load_contigs_async", "igd_row_text_size",
+           "igd_fetch_row_text")
 
 _lib = None
 
@@ -109,6 +110,10 @@ def load():
     lib.igd_fetch_vj_rows.restype = ctypes.c_int
     lib.igd_fetch_d_rows.argtypes = [vp, vp, ctypes.c_uint64]
     lib.igd_fetch_d_rows.restype = ctypes.c_int
+    lib.igd_row_text_size.argtypes = [vp, u64p, u64p]
+    lib.igd_row_text_size.restype = ctypes.c_int
+    lib.igd_fetch_row_text.argtypes = [vp, vp, ctypes.c_uint64, vp, ctypes.c_uint64]
+    lib.igd_fetch_row_text.restype = ctypes.c_int
     lib.igd_match_bounds.argtypes = [vp, vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp]
     lib.igd_match_bounds.restype = ctypes.c_int
     lib.igd_fasta_open.restype = vp

@@ -78,14 +78,16 @@ struct igd_handle {
     bool sorted_hits_valid = false;
     std::vector<igd_vj_row> vj_rows;             // last igd_detect
     std::vector<igd_d_row> d_rows;
+    std::vector<uint8_t> row_text;               // the rows' letters (igd_fetch_row_text), segment k = [row_text_off[k], row_text_off[k + 1])
+    std::vector<uint64_t> row_text_off;
     uint8_t *d_comp = nullptr;                   // 256-byte complement table (Bio.Seq's IUPAC table), detect.cu
     int last_scan_kind = 0;                      // 0 none, 1 rss, 2 kmers
     int last_k = 0;
     int32_t last_spacer[4] = {0, 0, 0, 0};
 
     // generic growable device scratch for the aligner
-    void *d_scratch[32] = {nullptr};
-    size_t scratch_cap[32] = {0};
+    void *d_scratch[40] = {nullptr};
+    size_t scratch_cap[40] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
     void *h_pin[2] = {nullptr, nullptr};   // more pinned buffers: [0] bounds read-back, [1] run tables on their way to the device
@@ -106,7 +108,8 @@ int igd_cuda_fail(cudaError_t e, const char *what);
 
 // growable device scratch slots (capi.cu, detect.cu)
 enum { S_SEQ = 0, S_SEQOFF, S_CHUNK0, S_TGT, S_TGTOFF, S_QRY, S_QRYOFF, S_PT, S_PQ, S_WORK, S_SCORE, S_PAY, S_RUNS, S_PICK,
-       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_TCLS, S_COUNT };
+       S_FRAG, S_BEST, S_TILEC, S_LCS, S_MASKS, S_UB, S_TOP, S_QCLS, S_YRUNS, S_Y, S_HITREC, S_HITOUT, S_HITKEY, S_HITIDX, S_CUBTMP, S_YPASS, S_TCLS, S_TEXT, S_TEXTDESC, S_COUNT };
+static_assert(S_COUNT <= 40, "igd_handle::d_scratch is too small");
 int igd_reserve(igd_handle *h, int slot, size_t bytes);
 int igd_stage_reserve(igd_handle *h, size_t bytes);       // pinned read-back buffer h->h_stage
 int igd_pin_reserve(igd_handle *h, int which, size_t bytes);   // h->h_pin[which]

@@ -56,6 +56,28 @@ gather_fragments_kernel(const uint8_t *__restrict__ seq, const FragDesc *__restr
     }
 }
 
+// The letters of the emitted rows (py/IGDetective.py:391-419, 238-249): segment k = upper(letters [g0, g0 + len)), reverse-
+// complemented when rc, written at out[off[k] ...).  Same letter handling as the fragment gather above.
+struct TextDesc { unsigned long long g0; unsigned long long off; int32_t len; int32_t rc; };
+
+__global__ void __launch_bounds__(128)
+gather_text_kernel(const uint8_t *__restrict__ seq, const TextDesc *__restrict__ d, const uint8_t *__restrict__ comp, int n,
+                   uint8_t *__restrict__ out)
+{
+    __shared__ uint8_t s_comp[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_comp[i] = comp[i];
+    __syncthreads();
+    for (int k = blockIdx.x; k < n; k += gridDim.x) {
+        const TextDesc t = d[k];
+        for (int i = threadIdx.x; i < t.len; i += blockDim.x) {
+            unsigned c = seq[t.g0 + (unsigned long long)(t.rc ? t.len - 1 - i : i)];
+            if (c - 'a' < 26u) c -= 32u;
+            if (t.rc) c = s_comp[c];
+            out[t.off + i] = (uint8_t)c;
+        }
+    }
+}
+
 // np.argmax(pi_mat[k]) (py/IGDetective.py:473): FIRST maximum of PI = (matches-1)/len*100 over the genes, compared
 // exactly by cross-multiplication (equal rationals give equal float64 PI, different ones differ by far more than
 // an ulp).  pick[u][g] = matches | len << 10 | forward << 31 (pick_orientation_kernel).  One warp per fragment.
@@ -624,7 +646,7 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
     if (prm->gene_length[0] < 1 || prm->gene_length[0] > IGD_MAX_TARGET_LEN || prm->gene_length[1] < 1 || prm->gene_length[1] > IGD_MAX_TARGET_LEN) {
         igd_set_error("gene_length must lie in 1..%d", IGD_MAX_TARGET_LEN); return IGD_ERR_ARG;
     }
-    h->vj_rows.clear(); h->d_rows.clear();
+    h->vj_rows.clear(); h->d_rows.clear(); h->row_text.clear(); h->row_text_off.clear();
     int rc;
     Trace tr;
     if ((rc = igd_run_rss_scan(h, spacer, n_hits))) return rc;
@@ -739,12 +761,90 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
         if ((rc = score_gene_type(h, gt, all, gt == 0 ? vgene : jgene, gt == 0 ? vgene_off : jgene_off, gt == 0 ? n_vgene : n_jgene,
                                   sc, prm, acc))) return rc;
     }
+    // ---- the rows' letters, read from the resident contigs: heptamer, nonamer and aligned gene sequence of a V / J row,
+    //      the four k-mers and the sequence between the heptamers of a D row; Python slice semantics, upper-cased ----
+    {
+        std::vector<TextDesc> segs;
+        segs.reserve(3 * h->vj_rows.size() + 5 * h->d_rows.size());
+        unsigned long long at = 0;
+        auto push = [&](uint32_t contig, int64_t a, int64_t b, bool rcomp) {
+            int64_t st, n;
+            py_slice(a, b, (int64_t)h->contig_len[contig], st, n);
+            segs.push_back({h->contig_seq_off[contig] + (unsigned long long)st, at, (int32_t)n, rcomp ? 1 : 0});
+            at += (unsigned long long)n;
+        };
+        for (const igd_vj_row &r : h->vj_rows) {
+            const bool rev = r.strand == IGD_STRAND_REV;
+            push(r.contig, r.hept, r.hept + 7, rev);
+            push(r.contig, r.nona, r.nona + 9, rev);
+            if (r.frag_len > 0) {
+                // the aligned orientation: reverse-complemented once for a '-' strand RSS and once more when the reverse
+                // complement aligned better (:309-317); [start, ient) of THAT string
+                const bool flip = rev != (r.direction == '-');
+                const int64_t lo = std::min<int64_t>(r.start, r.frag_len), hi = std::max<int64_t>(lo, std::min<int64_t>(r.ient, r.frag_len));
+                const int64_t a = flip ? r.frag_start + r.frag_len - hi : r.frag_start + lo;
+                segs.push_back({h->contig_seq_off[r.contig] + (unsigned long long)a, at, (int32_t)(hi - lo), flip ? 1 : 0});
+                at += (unsigned long long)(hi - lo);
+            } else {
+                segs.push_back({0ull, at, 0, 0});
+            }
+        }
+        for (const igd_d_row &r : h->d_rows) {
+            const bool rev = r.strand == IGD_STRAND_REV;
+            push(r.contig, r.dl_hept, r.dl_hept + 7, rev);
+            push(r.contig, r.dl_nona, r.dl_nona + 9, rev);
+            push(r.contig, r.dr_hept, r.dr_hept + 7, rev);
+            push(r.contig, r.dr_nona, r.dr_nona + 9, rev);
+            if (!rev) push(r.contig, r.dl_hept + 7, r.dr_hept, false); else push(r.contig, r.dr_hept + 7, r.dl_hept, true);
+        }
+        h->row_text_off.resize(segs.size() + 1);
+        for (size_t k = 0; k < segs.size(); ++k) h->row_text_off[k] = segs[k].off;
+        h->row_text_off[segs.size()] = at;
+        h->row_text.resize((size_t)at);
+        if (!segs.empty() && at > 0) {
+            if ((rc = igd_reserve(h, S_TEXT, (size_t)at))) return rc;
+            if ((rc = igd_reserve(h, S_TEXTDESC, segs.size() * sizeof(TextDesc)))) return rc;
+            if ((rc = igd_pin_reserve(h, 1, segs.size() * sizeof(TextDesc)))) return rc;
+            if ((rc = igd_stage_reserve(h, (size_t)at))) return rc;
+            memcpy(h->h_pin[1], segs.data(), segs.size() * sizeof(TextDesc));
+            IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_TEXTDESC], h->h_pin[1], segs.size() * sizeof(TextDesc), cudaMemcpyHostToDevice, h->stream));
+            gather_text_kernel<<<(unsigned)std::min<size_t>(segs.size(), (size_t)h->sm_count * 16), 128, 0, h->stream>>>(
+                (const uint8_t *)h->d_scratch[S_SEQ], (const TextDesc *)h->d_scratch[S_TEXTDESC], h->d_comp, (int)segs.size(),
+                (uint8_t *)h->d_scratch[S_TEXT]);
+            IGD_CUDA(cudaGetLastError());
+            h->timing.total_launches++;
+            IGD_CUDA(cudaMemcpyAsync(h->h_stage, h->d_scratch[S_TEXT], (size_t)at, cudaMemcpyDeviceToHost, h->stream));
+            IGD_CUDA(cudaStreamSynchronize(h->stream));
+            memcpy(h->row_text.data(), h->h_stage, (size_t)at);
+        }
+        tr.mark("row letters");
+    }
     h->timing.scan_ms = scan_ms;
     h->timing.align_ms = acc.ms; h->timing.align_cells = acc.cells; h->timing.align_launches = acc.launches;
     h->timing.lcs_ms = acc.lcs_ms; h->timing.k5_ms = acc.k5_ms; h->timing.dp_ms = acc.ms - acc.lcs_ms - acc.k5_ms;
     h->timing.lcs_cells = acc.lcs_cells; h->timing.k5_cells = acc.k5_cells;
     *n_vj_rows = h->vj_rows.size();
     *n_d_rows = h->d_rows.size();
+    return IGD_OK;
+}
+
+int igd_row_text_size(igd_handle *h, uint64_t *n_bytes, uint64_t *n_segments)
+{
+    if (!h || !n_bytes || !n_segments) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    *n_bytes = h->row_text.size();
+    *n_segments = h->row_text_off.empty() ? 0 : h->row_text_off.size() - 1;
+    return IGD_OK;
+}
+
+int igd_fetch_row_text(igd_handle *h, uint8_t *text, uint64_t text_capacity, uint64_t *offsets, uint64_t offsets_capacity)
+{
+    if (!h || (!text && text_capacity) || (!offsets && offsets_capacity)) { igd_set_error("null argument"); return IGD_ERR_ARG; }
+    if (h->row_text.size() > text_capacity || h->row_text_off.size() > offsets_capacity) {
+        igd_set_error("capacity too small for %llu bytes / %llu offsets", (unsigned long long)h->row_text.size(), (unsigned long long)h->row_text_off.size());
+        return IGD_ERR_CAPACITY;
+    }
+    if (!h->row_text.empty()) memcpy(text, h->row_text.data(), h->row_text.size());
+    if (!h->row_text_off.empty()) memcpy(offsets, h->row_text_off.data(), h->row_text_off.size() * sizeof(uint64_t));
     return IGD_OK;
 }
 

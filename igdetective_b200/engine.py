@@ -283,6 +283,11 @@ class Engine:
         _lib.check(self._lib.igd_fetch_vj_rows(self._h, vj.ctypes.data, nvj.value))
         d = np.zeros(nd.value, _lib.D_ROW_DTYPE)
         _lib.check(self._lib.igd_fetch_d_rows(self._h, d.ctypes.data, nd.value))
+        nb, ns = ctypes.c_uint64(), ctypes.c_uint64()
+        _lib.check(self._lib.igd_row_text_size(self._h, ctypes.byref(nb), ctypes.byref(ns)))
+        text = np.empty(nb.value, np.uint8)
+        text_off = np.empty(ns.value + 1, np.uint64)
+        _lib.check(self._lib.igd_fetch_row_text(self._h, text.ctypes.data if nb.value else None, nb.value, text_off.ctypes.data, ns.value + 1))
         t = self.timing()
         self.align_ms_total += t["align_ms"]
         self.align_cells_total += t["align_cells"]
@@ -290,8 +295,8 @@ class Engine:
         # winners' words out -- the device never sends letters back
         n_cand = int(np.count_nonzero((hits["sig_type"] == _lib.SIG_V) | (hits["sig_type"] == _lib.SIG_J)))
         self.h2d_bytes += vb.nbytes + vo.nbytes + jb.nbytes + jo.nbytes + 24 * n_cand + 12 * int(nvj.value)
-        self.d2h_bytes += 8 + 8 * int(nh.value) + 16 * n_cand + 8 * int(nvj.value)
-        return {"hits": hits, "vj": vj, "d": d}
+        self.d2h_bytes += 8 + 8 * int(nh.value) + 16 * n_cand + 8 * int(nvj.value) + int(nb.value)
+        return {"hits": hits, "vj": vj, "d": d, "text": text.tobytes().decode("latin-1"), "text_off": text_off.tolist()}
 
     def match_bounds(self, fragments, genes):
         """Upper bounds on the match count / PI of fragments[u] (and its reverse complement) against genes[g]

@@ -194,31 +194,41 @@ def _rows_from_device(res, ids, parent_seq, canonical_genes, scan, order):
         cols = zip(hept.tolist(), vj["nona"].tolist(), vj["frag_start"].tolist(), vj["contig"].tolist(), vj["frag_len"].tolist(),
                    vj["best_gene"].tolist(), start.tolist(), vj["ient"].tolist(), vj["gene_type"].tolist(), vj["strand"].tolist(),
                    vj["direction"].tolist(), gs.tolist(), ge.tolist(), pi.tolist(), alen_a.tolist(), first.tolist())
+        text, to = res.get("text"), res.get("text_off")
+        k = 0
         for h, n, fstart, ci, flen, best, st, ient, gt, sd, direction, g0, g1, p, al, fi in cols:
             gene, strand, contig = (V, J)[gt], (FWD, REV)[sd], ids[ci]
-            s = parent_seq[contig]
-            if flen > 0:
-                # the aligned orientation of the fragment: reverse-complemented once for a '-' strand RSS and once more
-                # when the reverse complement aligned better (:309-317) -- two flips cancel
-                if (sd == 1) != (direction == 45):                      # 45 == ord('-')
-                    query = reverse_complement(s[fstart:fstart + flen])[st:ient].upper()
-                else:
-                    query = s[fstart + st:fstart + min(ient, flen)].upper()
+            if text is not None:                                        # the rows' letters came with the rows (igd_fetch_row_text)
+                h7, n9, query = text[to[k]:to[k + 1]], text[to[k + 1]:to[k + 2]], text[to[k + 2]:to[k + 3]]
+                k += 3
             else:
-                query = ""
-            rows[gene].append([contig, strand, h, n, _kmer(s, h, 7, strand), _kmer(s, n, 9, strand),
-                               g0, g1, gene_ids[gt][best], chr(direction), p, float(al), query])
+                s = parent_seq[contig]
+                h7, n9 = _kmer(s, h, 7, strand), _kmer(s, n, 9, strand)
+                if flen > 0:
+                    # the aligned orientation of the fragment: reverse-complemented once for a '-' strand RSS and once more
+                    # when the reverse complement aligned better (:309-317) -- two flips cancel
+                    if (sd == 1) != (direction == 45):                  # 45 == ord('-')
+                        query = reverse_complement(s[fstart:fstart + flen])[st:ient].upper()
+                    else:
+                        query = s[fstart + st:fstart + min(ient, flen)].upper()
+                else:
+                    query = ""
+            rows[gene].append([contig, strand, h, n, h7, n9, g0, g1, gene_ids[gt][best], chr(direction), p, float(al), query])
             keys[gene].append((sd, ci, fi))
+    text, to = res.get("text"), res.get("text_off")
+    k = 3 * len(vj)
     for r in dr.tolist():
         dlh, dln, drh, drn, ci, sd, _ = r
         strand, contig = (FWD, REV)[sd], ids[ci]
-        s = parent_seq[contig]
-        lh, ln = _kmer(s, dlh, 7, strand), _kmer(s, dln, 9, strand)
-        rh, rn = _kmer(s, drh, 7, strand), _kmer(s, drn, 9, strand)
-        if strand == FWD:
-            gs, ge, seq = dlh + 7, drh - 1, s[dlh + 7:drh].upper()
+        gs, ge = (dlh + 7, drh - 1) if strand == FWD else (drh + 7, dlh - 1)
+        if text is not None:
+            lh, ln, rh, rn, seq = (text[to[k + i]:to[k + i + 1]] for i in range(5))
+            k += 5
         else:
-            gs, ge, seq = drh + 7, dlh - 1, reverse_complement(s[drh + 7:dlh]).upper()
+            s = parent_seq[contig]
+            lh, ln = _kmer(s, dlh, 7, strand), _kmer(s, dln, 9, strand)
+            rh, rn = _kmer(s, drh, 7, strand), _kmer(s, drn, 9, strand)
+            seq = s[dlh + 7:drh].upper() if strand == FWD else reverse_complement(s[drh + 7:dlh]).upper()
         rows[D].append([contig, strand, dlh, dln, lh, ln, drh, drn, rh, rn, gs, ge, seq])
         keys[D].append((sd, ci, drh, dln))
     if want_order:

@@ -293,6 +293,13 @@ int igd_detect(igd_handle *h, const int32_t spacer[4],
                uint64_t *n_hits, uint64_t *n_vj_rows, uint64_t *n_d_rows);
 int igd_fetch_vj_rows(igd_handle *h, igd_vj_row *out, uint64_t capacity);
 int igd_fetch_d_rows(igd_handle *h, igd_d_row *out, uint64_t capacity);
+/* The letters of the rows of the last igd_detect, read from the resident contigs with Python's slice semantics and
+ * upper-cased (py/IGDetective.py:238-249, 391-419): three segments per V / J row, in row order -- heptamer, nonamer (reverse-
+ * complemented for strand '-'), the aligned part of the fragment in its aligned orientation ('gene sequence') -- then five
+ * per D row: left heptamer, left nonamer, right heptamer, right nonamer, the sequence between the heptamers.
+ * Segment k = text[offsets[k] .. offsets[k + 1]); offsets has n_segments + 1 entries. */
+int igd_row_text_size(igd_handle *h, uint64_t *n_bytes, uint64_t *n_segments);
+int igd_fetch_row_text(igd_handle *h, uint8_t *text, uint64_t text_capacity, uint64_t *offsets, uint64_t offsets_capacity);
 
 /* The two upper bounds igd_detect prunes its scoring with, for every (fragment, gene) pair -- not a reference
  * interface: exposed so that tests can hold the bound kernels against the plain recurrences.
