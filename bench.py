@@ -189,10 +189,10 @@ class Clocks:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.first = [], None, 0
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -203,11 +203,22 @@ class Clocks:
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def wait_first(self, timeout):
+        """until the sampler has produced its first line (it is then in its steady polling loop)"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """samples from here on belong to the timed regions"""
+        self.first = max(0, len(self.rows) - 1)
+
     def stop(self):
         if not self.proc:
             return None
         self.proc.terminate()
         self.t.join(timeout=2)
+        self.rows = self.rows[self.first:] or self.rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         if not sm:
             return None
@@ -282,11 +293,16 @@ def gpu_arm(a):
             launches += eng.timing()["total_launches"] - l0
         return total, (eng.h2d_bytes - h0) / k, (eng.d2h_bytes - d0) / k, launches / k
 
+    # the clock sampler starts BEFORE the warm-up: nvidia-smi takes a few hundred ms to come up, and that must not fall
+    # into the 5-20 steps of the timed region (it did: steps of 4.5 ms measured 5.2 ms with the sampler starting beside them)
+    clocks = Clocks(local) if rank == 0 else None
     eng.load_contigs((pinned.data_ptr(), off), list(seqs))
     for _ in range(a.warmup):
         step(False)
     step(False, record=True)
-    clocks = Clocks(local) if rank == 0 else None
+    if clocks:
+        clocks.wait_first(2.0)
+        clocks.mark()
     t_dev, _, _, launches = timed(False, a.steps)
     # per-kernel device times of the last resident step: CUDA events on the library's stream
     eng.load_contigs((pinned.data_ptr(), off), list(seqs))
@@ -596,8 +612,8 @@ if __name__ == "__main__":
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mbases", type=float, default=100.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
