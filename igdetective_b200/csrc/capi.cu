@@ -91,7 +91,7 @@ void igd_destroy(igd_handle *h)
     cudaFree(h->d_hits); cudaFree(h->d_count);
     for (int i = 0; i < S_COUNT; ++i) cudaFree(h->d_scratch[i]);
     if (h->h_stage) cudaFreeHost(h->h_stage);
-    for (int i = 0; i < 2; ++i) if (h->h_pin[i]) cudaFreeHost(h->h_pin[i]);
+    for (int i = 0; i < 3; ++i) if (h->h_pin[i]) cudaFreeHost(h->h_pin[i]);
     if (h->h_ring) cudaFreeHost(h->h_ring);
     for (int i = 0; i < 4; ++i) if (h->ring_ev[i]) cudaEventDestroy(h->ring_ev[i]);
     if (h->ev0) cudaEventDestroy(h->ev0);

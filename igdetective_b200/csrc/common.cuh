@@ -90,8 +90,8 @@ struct igd_handle {
     size_t scratch_cap[40] = {0};
     void *h_stage = nullptr;      // pinned staging buffer for small result read-backs
     size_t h_stage_cap = 0;
-    void *h_pin[2] = {nullptr, nullptr};   // more pinned buffers: [0] bounds read-back, [1] run tables on their way to the device
-    size_t h_pin_cap[2] = {0, 0};
+    void *h_pin[3] = {nullptr, nullptr, nullptr};   // more pinned buffers: [0] bounds read-back, [1] / [2] run tables (alignments / K5) on their way to the device
+    size_t h_pin_cap[3] = {0, 0, 0};
     void *h_ring = nullptr;       // ring of pinned pieces for the upload of pageable genomes (capi.cu, upload_letters)
     cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 

@@ -358,6 +358,16 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     // every remaining gene, queued behind this round's alignments, and round three aligns what K5 lets through.
     const bool ybound_ok = cut >= 50.0 && !(getenv("IGD_DETECT_YBOUND") && atoi(getenv("IGD_DETECT_YBOUND")) == 0);
     std::vector<int32_t> yslot((size_t)U, -1);
+    std::vector<long long> len_values;                          // distinct gene lengths and each gene's index into them
+    std::vector<uint16_t> len_class((size_t)n_gene), min_lcs;
+    for (int32_t g = 0; g < n_gene; ++g) {
+        const long long len = gene_off[g + 1] - gene_off[g];
+        size_t c = 0;
+        while (c < len_values.size() && len_values[c] != len) ++c;
+        if (c == len_values.size()) len_values.push_back(len);
+        len_class[(size_t)g] = (uint16_t)c;
+    }
+    min_lcs.resize(len_values.size());
     std::vector<int4> yruns[2];
     size_t ywords = 0, needed = 0, n_below = 0;
     std::vector<int32_t> below;
@@ -367,13 +377,22 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
         const Best &b = best[(size_t)u];
         const bool by_best = b.gene >= 0 && (double)(b.matches - 1) / (double)b.alen * 100.0 >= cut;
         if (!by_best) { ++n_below; if (ybound_ok) { below.push_back(u); continue; } }
-        for (int32_t g = 0; g < n_gene; ++g) {
-            if (done[(size_t)u * n_gene + g]) continue;
-            const int32_t num = (int32_t)ub[(size_t)u * n_gene + g] - 1;
-            const long long len = gene_off[g + 1] - gene_off[g];
-            const bool need = by_best ? (long long)num * b.alen >= (long long)(b.matches - 1) * len
-                                      : (double)num / (double)len * 100.0 >= cut;
-            if (need) l.push_back(g);
+        if (by_best) {
+            // (LCS - 1) x alen >= (m - 1) x len  <=>  LCS >= 1 + ceil((m - 1) x len / alen): one threshold per distinct gene
+            // length (a few dozen), then one 16-bit comparison per gene
+            const long long m1 = b.matches - 1, al = b.alen;
+            for (size_t c = 0; c < len_values.size(); ++c) min_lcs[c] = (uint16_t)std::min<long long>(65535, 1 + (m1 * len_values[c] + al - 1) / al);
+            const uint16_t *ubu = ub + (size_t)u * n_gene;
+            const uint8_t *dn = done.data() + (size_t)u * n_gene;
+            for (int32_t g = 0; g < n_gene; ++g)
+                if (ubu[g] >= min_lcs[len_class[(size_t)g]] && !dn[g]) l.push_back(g);
+        } else {
+            for (int32_t g = 0; g < n_gene; ++g) {
+                if (done[(size_t)u * n_gene + g]) continue;
+                const int32_t num = (int32_t)ub[(size_t)u * n_gene + g] - 1;
+                const long long len = gene_off[g + 1] - gene_off[g];
+                if ((double)num / (double)len * 100.0 >= cut) l.push_back(g);
+            }
         }
         needed += l.size();
     }
@@ -401,7 +420,9 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
         if ((rc2 = igd_reserve(h, S_YRUNS, all.size() * sizeof(int4)))) return rc2;
         if ((rc2 = igd_reserve(h, S_Y, ywords * 4))) return rc2;
         if ((rc2 = igd_reserve(h, S_YPASS, (size_t)pass_cap * sizeof(uint2)))) return rc2;
-        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], all.data(), all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+        if ((rc2 = igd_pin_reserve(h, 2, all.size() * sizeof(int4)))) return rc2;
+        memcpy(h->h_pin[2], all.data(), all.size() * sizeof(int4));
+        IGD_CUDA(cudaMemcpyAsync(h->d_scratch[S_YRUNS], h->h_pin[2], all.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
         IGD_CUDA(cudaMemsetAsync(h->d_count + 32, 0, 3 * sizeof(unsigned long long), h->stream));
         if ((rc2 = igd_launch_gene_classes(h, (const uint8_t *)h->d_scratch[S_QRY], qbytes, (uint8_t *)h->d_scratch[S_QCLS]))) return rc2;
         for (int shape = 0; shape < 2; ++shape)
