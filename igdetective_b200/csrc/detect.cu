@@ -398,7 +398,8 @@ static int best_by_pruning(igd_handle *h, int gt, int32_t U, const std::vector<i
     }
     if (!below.empty()) {
         const size_t groups = (size_t)h->sm_count * 4 * 8;
-        const int ychunk = (int)std::min<size_t>(64, std::max<size_t>(2, below.size() * (size_t)n_gene / (groups * 16)));   // >= 16 runs per lane group
+        // >= 16 runs per lane group, at least two genes per run (swept 1..10 on the bench step: 2 is the fastest, 1.04 ms)
+        const int ychunk = (int)std::min<size_t>(64, std::max<size_t>(2, below.size() * (size_t)n_gene / (groups * 16)));
         for (int32_t u : below) {
             const int nA = toff[2 * u + 1] - toff[2 * u];
             yslot[(size_t)u] = (int32_t)ywords;
