@@ -1,16 +1,23 @@
 // igd_detect: the module body of py/IGDetective.py:439-487 in one call on the contigs resident in the handle.
 //
-//   RSS scan (rss_scan.cu)  ->  hit list (host: decode + sort, a few 10^3..10^5 records)
-//   combine_D_RSS (:210-224) -> sorted search over the D_left / D_right hits, host
+//   RSS scan (rss_scan.cu)  ->  hit list decoded and radix-sorted on the device (hits.cu), 24 bytes per hit to the host
+//   combine_D_RSS (:210-224) -> two pointers over the D_left / D_right hits of a contig and strand, host
 //   get_s_fragment_from_RSS (:268-300) -> gather_fragments_kernel over the resident ASCII letters: Python slice
 //       semantics incl. the negative-start quirk of parent_seq[index-length:index] (:265), upper-cased (:308),
 //       reverse-complemented for strand '-' with Bio.Seq's IUPAC table; each fragment and its reverse complement
 //       become targets 2u / 2u+1
-//   align_fragment_to_genes (:319-360) -> packed Gotoh kernels over [2U targets] x [all genes], the orientation
-//       choice of ComputeAlignment (:314-317) and np.argmax's first maximum (:473) on the device
+//   align_fragment_to_genes (:319-360) + np.argmax's first maximum (:473): the reference aligns every fragment with every
+//       gene in both orientations; here (best_by_pruning) two upper bounds on PI (lcs.cu: K4, the LCS; K5, a one-state DP
+//       that charges insertions) prove which of those alignments cannot decide a row, and the packed Gotoh kernels run on
+//       the rest in three rounds -- the same rows from ~2 % of the cells.  Tables of fewer than 64 genes (J) and
+//       IGD_DETECT_PRUNE=0 take the all-pairs path: packed kernels over [2U targets] x [all genes], the orientation
+//       choice of ComputeAlignment (:314-317) and the first-maximum argmax on the device.
 //   threshold (:387) on the host in float64, the winners' ComputeAlignment (:388) through the two-register
 //       Gotoh kernel for AlignmentRange()[0] and the end of QuerySeq()
-// Only integers cross the bus: 8 bytes per RSS hit in, 16 bytes per candidate and 8 per winner out.
+//   the rows' letters (:391-419): gather_text_kernel, fetched with igd_fetch_row_text
+// Environment switches, read per call (tests compare the paths): IGD_DETECT_PRUNE=0, IGD_DETECT_YBOUND=0 (K4 only),
+// IGD_DETECT_YPASS_CAP (size of K5's verdict list), IGD_DETECT_TOP_MIN / IGD_DETECT_TOP_DELTA (round one's lists),
+// IGD_DETECT_TRACE=1 (phase times on stderr).
 #include "common.cuh"
 #include <algorithm>
 #include <chrono>
