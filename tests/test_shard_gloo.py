@@ -223,3 +223,66 @@ def test_window_waves_score_exactly_what_the_reference_would_align(monkeypatch):
     assert len(scored) < sum(len(p) for p in positions.values()) / 2
     # the reference's own position dict shape and the (contig, array) list give the same table
     assert X.find_genes(None, CONTIGS, [(c, np.asarray(sorted(p))) for c, p in positions.items()], GENES, batch=50) == want
+
+
+def test_pipelined_groups_cover_the_pieces_in_order_and_surface_errors(monkeypatch):
+    """multi.detect_pieces_pipelined on CPU with stand-in engines: the groups are runs of consecutive pieces that cover
+    every piece once, uploads happen one at a time in group order with the offsets rebased, every group is scored on the
+    handle that loaded it, the rows come back in group order, and an exception in a worker reaches the caller."""
+    import threading
+
+    import numpy as np
+
+    from igdetective_b200 import multi
+
+    log, lock = [], threading.Lock()
+
+    class FakeEngine:
+        def __init__(self, name):
+            self.name, self.loaded, self.uploading = name, None, False
+
+        def load_contigs(self, seqs, ids=None, wait=True):
+            ptr, off = seqs
+            assert not wait and off[0] == 0 and off.dtype == np.uint64
+            with lock:
+                assert not any(e.uploading for e in engines), "two uploads at once"
+                self.uploading = True
+            self.loaded = (ptr, off.tolist(), list(ids))
+            with lock:
+                log.append(("load", self.name, ptr))
+                self.uploading = False
+
+        def sync(self):
+            pass
+
+        def timing(self):
+            return {"scan_ms": 1.0, "pack_ms": 0.0, "align_ms": 2.0}
+
+    def fake_detect_pieces(eng, seqs, ids, pieces, canonical, order="canonical", part=None):
+        ptr, off, names = eng.loaded
+        assert names == list(range(len(pieces))) and sorted(part) == names
+        assert [off[k + 1] - off[k] for k in names] == [p[4] - p[3] for p in pieces]
+        if any(p[0] == "boom" for p in pieces):
+            raise RuntimeError("scoring failed")
+        return {"V": [[p[0], eng.name] for p in pieces], "D": [], "J": []}
+
+    monkeypatch.setattr(multi, "detect_pieces", fake_detect_pieces)
+    pieces = [("c%d" % i, 0, n, 0, n) for i, n in enumerate([700, 10, 10, 900, 5, 300, 300, 40, 1000, 3])]
+    off = np.zeros(len(pieces) + 1, np.uint64)
+    off[1:] = np.cumsum([p[4] - p[3] for p in pieces])
+    part = {k: "x" * (p[4] - p[3]) for k, p in enumerate(pieces)}
+    for n_eng, groups in ((2, 4), (3, 3), (4, 20), (2, 1)):
+        engines = [FakeEngine("e%d" % i) for i in range(n_eng)]
+        log.clear()
+        tm = []
+        rows = multi.detect_pieces_pipelined(engines, None, pieces, None, part, (1000, off), groups, tm)
+        assert [r[0] for r in rows["V"]] == [p[0] for p in pieces]                  # every piece once, in order
+        starts = [x[2] for x in log]
+        assert starts == sorted(starts) and starts[0] == 1000                       # uploads in group order
+        assert sum(x[5] for x in tm) == int(off[-1]) and len(tm) == len(log) <= max(1, min(groups, len(pieces)))
+        by_group = sorted(tm)
+        assert [g[0] for g in by_group] == list(range(len(by_group)))
+    engines = [FakeEngine("e0"), FakeEngine("e1")]
+    bad = pieces[:4] + [("boom", 0, 5, 0, 5)] + pieces[5:]
+    with pytest.raises(RuntimeError, match="scoring failed"):
+        multi.detect_pieces_pipelined(engines, None, bad, None, part, (1000, off), 4)
