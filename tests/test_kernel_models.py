@@ -154,3 +154,35 @@ def test_pruning_bounds_hold_for_the_oracle_alignments():
             tight += 2 * m - c == y
             k += 1
     assert tight > 0                     # the bound is attained (closely related pairs), not vacuous
+
+
+def test_pruning_theorems_on_random_short_sequences():
+    """What igd_detect relies on, on many small random cases (where co-optimal alignments and end effects are common):
+    m <= LCS;  2 m - c <= Y;  and the two tests it applies -- PI <= (LCS - 1) / len(gene) x 100, and PI >= p >= 50 implies
+    50 Y >= p len(gene) + 100 -- for the alignment the oracle returns, in both orientations' worth of inputs."""
+    rng = np.random.default_rng(33)
+    frags, genes = [], []
+    for _ in range(400):
+        n, q = int(rng.integers(1, 48)), int(rng.integers(1, 40))
+        g = "".join(rng.choice(list("ACGTNacgt"), q, p=[0.22, 0.22, 0.22, 0.22, 0.04, 0.02, 0.02, 0.02, 0.02]))
+        if rng.random() < 0.5:                        # a related pair: the gene with a few edits, inside a random flank
+            body = "".join(ch for ch in g.upper() if rng.random() > 0.1)
+            f = "".join(rng.choice(list("ACGT"), int(rng.integers(0, 10)))) + body + "".join(rng.choice(list("ACGT"), int(rng.integers(0, 10))))
+            f = f[:max(1, n + q)] or "A"
+        else:
+            f = "".join(rng.choice(list("ACGTN"), n, p=[0.24, 0.24, 0.24, 0.24, 0.04]))
+        frags.append(f); genes.append(g)
+    idx = np.arange(len(frags))
+    st = O.align_stats(frags, genes, idx, idx)
+    strong = 0
+    for k, (f, g) in enumerate(zip(frags, genes)):
+        m, alen = int(st["matches"][k]), int(st["end"][k]) - int(st["start"][k])
+        c = alen - len(g)
+        lcs, y = KM.lcs_bound(f, g), KM.y_bound(f, g)
+        assert c >= 0 and m <= lcs and 2 * m - c <= y, (f, g, m, c, lcs, y)
+        pi = (m - 1) / alen * 100
+        assert pi <= (lcs - 1) / len(g) * 100 + 1e-9
+        if pi >= 50:
+            assert 50 * y >= pi * len(g) + 100 - 1e-9, (f, g, pi, y)
+            strong += 1
+    assert strong >= 60
