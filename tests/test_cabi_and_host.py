@@ -323,3 +323,56 @@ def test_byte_range_reader_partitions_the_file_and_rebuilds_every_contig(tmp_pat
     f = NativeFasta(dup, byte_range=(0, os.path.getsize(dup)))
     with pytest.raises(ValueError):
         shard.contig_table([shard.range_summary(f)])
+
+
+def test_rows_from_device_text_and_slice_paths_agree():
+    """igdetective._rows_from_device builds a row either from the letters that came with it (igd_fetch_row_text: three
+    segments per V / J row, five per D row, in row order) or by slicing parent_seq itself; both must give the same rows,
+    for both strands, both alignment directions, an empty fragment, and in reference order."""
+    from igdetective_b200 import _lib, igdetective
+    from igdetective_b200.fasta import reverse_complement
+    from igdetective_b200.rss import RssScan
+    from conftest import canonical
+    canon = canonical("combined_reference_genes")
+    rng = np.random.default_rng(4)
+    L = 60_000
+    s = np.frombuffer(b"ACGTacgtNR", np.uint8)[rng.integers(0, 10, L)].tobytes().decode()
+    seqs = {"c0": s, "c1": s[:20_000][::-1]}
+    n = 80
+    vj = np.zeros(n, _lib.VJ_ROW_DTYPE)
+    vj["contig"] = rng.integers(0, 2, n)
+    vj["hept"] = np.sort(rng.integers(1000, 19_000, n)); vj["nona"] = vj["hept"] + 30
+    vj["frag_start"] = vj["hept"] - 350; vj["frag_len"] = 350
+    vj["gene_type"] = rng.integers(0, 2, n); vj["strand"] = rng.integers(0, 2, n)
+    vj["best_gene"] = rng.integers(0, 13, n); vj["matches"] = rng.integers(150, 296, n); vj["alen"] = rng.integers(280, 320, n)
+    vj["start"] = rng.integers(0, 60, n); vj["ient"] = rng.integers(300, 351, n)
+    vj["direction"] = np.where(rng.integers(0, 2, n) == 1, 43, 45)
+    vj["frag_len"][::11] = 0
+    d = np.zeros(12, _lib.D_ROW_DTYPE)
+    d["contig"] = rng.integers(0, 2, 12); d["strand"] = rng.integers(0, 2, 12)
+    d["dl_hept"] = np.sort(rng.integers(1000, 19_000, 12)); d["dl_nona"] = d["dl_hept"] - 21
+    d["dr_hept"] = np.where(d["strand"] == 0, d["dl_hept"] + 40, d["dl_hept"] - 40); d["dr_nona"] = d["dr_hept"] + 19
+    hits = np.zeros(0, _lib.HIT_DTYPE)
+    ids = list(seqs)
+    scan = RssScan(None, seqs, order="canonical", load=False, hits=hits)
+    res = {"vj": vj, "d": d, "hits": hits}
+    want = igdetective._rows_from_device(res, ids, seqs, canon, scan, "canonical")
+    # the segments as the library documents them (include/igd_b200.h: igd_fetch_row_text), from the rows just built
+    segs, by_key = [], {}
+    for g in ("V", "J"):
+        for r in want[g]:
+            by_key[(r[0], r[1], r[2], r[3], g)] = r
+    for r in vj.tolist():
+        hept, nona, ci, gt, sd = r[0], r[1], r[3], r[10], r[11]
+        row = by_key[(ids[ci], "+-"[sd], hept, nona, "VJ"[gt])]
+        segs += [row[4], row[5], row[12]]
+    for r in want["D"]:
+        segs += [r[4], r[5], r[8], r[9], r[12]]
+    off = np.zeros(len(segs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in segs])
+    res_text = dict(res, text="".join(segs), text_off=off.tolist())
+    blank = {c: "x" * len(v) for c, v in seqs.items()}            # the letters must come from the text, not from parent_seq
+    got = igdetective._rows_from_device(res_text, ids, blank, canon, RssScan(None, blank, order="canonical", load=False, hits=hits), "canonical")
+    assert got == want
+    assert sum(len(want[g]) for g in want) == n + 12 and any(r[12] == "" for r in want["V"] + want["J"])
+    assert reverse_complement("ACGTn") == "nACGT"
